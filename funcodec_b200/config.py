@@ -1,0 +1,70 @@
+"""Model hyper-parameters for the codec hot path (host logic, no CUDA).
+
+Mirrors the YAML keys the reference feeds to GANSpeechCodecTask.build_model
+(/root/reference/funcodec/tasks/gan_speech_codec.py:301-358): `encoder_conf`, `quantizer_conf`,
+`decoder_conf`, `model_conf` of egs/LibriTTS/codec/conf/encodec_16k_n32_600k_step{,_ds640}.yaml.
+Only the branches the named configs use are representable (time_group_norm, non-causal,
+true_skip=False, compress=2, 2-layer LSTM, use_ddp RVQ without projections, segment_dur=null).
+"""
+from dataclasses import dataclass, field, asdict
+from typing import Dict, Optional, Tuple
+import math
+
+
+@dataclass(frozen=True)
+class CodecConfig:
+    name: str = "encodec_16k_n32_ds640"
+    ratios: Tuple[int, ...] = (8, 5, 4, 2, 2)   # encoder_conf.ratios / decoder_conf.ratios
+    n_filters: int = 32                          # SEANetEncoder default (seanet_encoder.py:90)
+    dimension: int = 128                         # model_conf.odim / quantizer input_size
+    kernel_size: int = 7
+    last_kernel_size: int = 7
+    residual_kernel_size: int = 3
+    lstm_layers: int = 2                         # seq_layer_num default
+    codebook_size: int = 1024                    # quantizer_conf.codebook_size
+    num_quantizers: int = 32                     # quantizer_conf.num_quantizers
+    sample_rate: int = 16000                     # quantizer_conf.sampling_rate / target_sample_hz
+    audio_normalize: bool = True                 # model_conf.audio_normalize
+    gn_eps: float = 1e-5                         # nn.GroupNorm default
+
+    @property
+    def hop_length(self) -> int:
+        return int(math.prod(self.ratios))
+
+    @property
+    def top_channels(self) -> int:
+        return self.n_filters * (2 ** len(self.ratios))
+
+    def frames(self, length: int) -> int:
+        return -(-length // self.hop_length)
+
+    def bandwidth_per_quantizer(self) -> float:
+        """ResidualVectorQuantizer.get_bandwidth_per_quantizer (funcodec/modules/quantization/vq.py:114-117)."""
+        return math.log2(self.codebook_size) * self.sample_rate / self.hop_length
+
+    def num_quantizers_for_bandwidth(self, bandwidth: Optional[float]) -> int:
+        """vq.py:105-112."""
+        n_q = self.num_quantizers
+        if bandwidth and bandwidth > 0.0:
+            n_q = int(max(1, math.floor(bandwidth / self.bandwidth_per_quantizer())))
+        return n_q
+
+    def to_dict(self) -> Dict:
+        return asdict(self)
+
+
+PRESETS: Dict[str, CodecConfig] = {
+    # BASELINE.json configs 1, 2, 5
+    "encodec_16k_n32_ds640": CodecConfig(),
+    # BASELINE.json config 3
+    "encodec_16k_n32_ds320": CodecConfig(name="encodec_16k_n32_ds320", ratios=(8, 5, 4, 2)),
+    # small shapes for parity tests (same topology, every kernel family exercised)
+    "tiny_ds40": CodecConfig(name="tiny_ds40", ratios=(5, 4, 2), n_filters=8, dimension=32,
+                             codebook_size=64, num_quantizers=8),
+    "small_ds320": CodecConfig(name="small_ds320", ratios=(8, 5, 4, 2), n_filters=8, dimension=64,
+                               codebook_size=256, num_quantizers=8),
+}
+
+
+def get_config(name: str) -> CodecConfig:
+    return PRESETS[name]

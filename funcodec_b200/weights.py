@@ -1,0 +1,117 @@
+"""Parameter naming (the reference's state_dict keys) and a seeded synthetic init.
+
+There is no network for pretrained checkpoints, so bench/tests use `init_state_dict(cfg, seed)`:
+reference-shaped tensors under the reference's names, drawn with a seeded CPU generator so that
+the CUDA path, the oracle and (in the build container) the real reference modules all consume
+bit-identical weights.  Host logic only.
+"""
+from typing import Dict, List, Tuple
+import math
+import torch
+
+from .config import CodecConfig
+
+
+def conv_specs(cfg: CodecConfig) -> List[Dict]:
+    """Every conv / transposed conv of encoder+decoder in execution order, with reference names.
+    Encoder: funcodec/models/encoder/seanet_encoder.py:108-162; decoder: seanet_decoder.py:107-172."""
+    specs = []
+    nf, D = cfg.n_filters, cfg.dimension
+
+    def rb(prefix, dim):
+        return [dict(name=prefix + ".block.1.conv", kind="conv", cin=dim, cout=dim // 2, k=cfg.residual_kernel_size, s=1),
+                dict(name=prefix + ".block.3.conv", kind="conv", cin=dim // 2, cout=dim, k=1, s=1),
+                dict(name=prefix + ".shortcut.conv", kind="conv", cin=dim, cout=dim, k=1, s=1)]
+
+    specs.append(dict(name="encoder.model.0.conv", kind="conv", cin=1, cout=nf, k=cfg.kernel_size, s=1))
+    n, mult = 1, 1
+    for r in reversed(cfg.ratios):
+        specs += rb(f"encoder.model.{n}", mult * nf)
+        specs.append(dict(name=f"encoder.model.{n + 2}.conv", kind="conv", cin=mult * nf, cout=2 * mult * nf, k=2 * r, s=r))
+        mult *= 2
+        n += 3
+    if cfg.lstm_layers > 0:
+        specs.append(dict(name=f"encoder.model.{n}.lstm", kind="lstm", dim=mult * nf))
+        n += 1
+    specs.append(dict(name=f"encoder.model.{n + 1}.conv", kind="conv", cin=mult * nf, cout=D, k=cfg.last_kernel_size, s=1))
+
+    specs.append(dict(name="decoder.model.0.conv", kind="conv", cin=D, cout=mult * nf, k=cfg.kernel_size, s=1))
+    n = 1
+    if cfg.lstm_layers > 0:
+        specs.append(dict(name="decoder.model.1.lstm", kind="lstm", dim=mult * nf))
+        n = 2
+    for r in cfg.ratios:
+        specs.append(dict(name=f"decoder.model.{n + 1}.convtr", kind="convtr", cin=mult * nf, cout=mult * nf // 2, k=2 * r, s=r))
+        specs += rb(f"decoder.model.{n + 2}", mult * nf // 2)
+        mult //= 2
+        n += 3
+    specs.append(dict(name=f"decoder.model.{n + 1}.conv", kind="conv", cin=nf, cout=1, k=cfg.last_kernel_size, s=1))
+    return specs
+
+
+def state_dict_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
+    shapes: Dict[str, Tuple[int, ...]] = {}
+    for sp in conv_specs(cfg):
+        n = sp["name"]
+        if sp["kind"] == "conv":
+            shapes[n + ".conv.weight"] = (sp["cout"], sp["cin"], sp["k"])
+            shapes[n + ".conv.bias"] = (sp["cout"],)
+            shapes[n + ".norm.weight"] = (sp["cout"],)
+            shapes[n + ".norm.bias"] = (sp["cout"],)
+        elif sp["kind"] == "convtr":
+            shapes[n + ".convtr.weight"] = (sp["cin"], sp["cout"], sp["k"])
+            shapes[n + ".convtr.bias"] = (sp["cout"],)
+            shapes[n + ".norm.weight"] = (sp["cout"],)
+            shapes[n + ".norm.bias"] = (sp["cout"],)
+        else:
+            H = sp["dim"]
+            for l in range(cfg.lstm_layers):
+                shapes[f"{n}.weight_ih_l{l}"] = (4 * H, H)
+                shapes[f"{n}.weight_hh_l{l}"] = (4 * H, H)
+                shapes[f"{n}.bias_ih_l{l}"] = (4 * H,)
+                shapes[f"{n}.bias_hh_l{l}"] = (4 * H,)
+    nq, K, D = cfg.num_quantizers, cfg.codebook_size, cfg.dimension
+    # use_ddp=True buffers (funcodec/modules/quantization/ddp_core_vq.py:349-352)
+    shapes["quantizer.rq.model.inited"] = (nq, 1)
+    shapes["quantizer.rq.model.cluster_size"] = (nq, K)
+    shapes["quantizer.rq.model.embed"] = (nq, K, D)
+    shapes["quantizer.rq.model.embed_avg"] = (nq, K, D)
+    return shapes
+
+
+def init_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic weights: conv/LSTM ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like torch's defaults,
+    GroupNorm affine perturbed away from (1, 0) so the affine path is exercised, codebooks
+    N(0, sigma_q^2) with geometrically shrinking sigma_q (residuals shrink stage by stage)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+    for name, shape in state_dict_shapes(cfg).items():
+        if name.startswith("quantizer."):
+            continue
+        if name.endswith("norm.weight"):
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("norm.bias"):
+            sd[name] = 0.1 * torch.randn(shape, generator=g)
+        elif ".lstm." in name:
+            H = shape[-1] if len(shape) == 2 else shape[0] // 4
+            sd[name] = uni(shape, 1.0 / math.sqrt(H))
+        elif name.endswith("convtr.weight"):
+            fan_in = shape[1] * shape[2]          # torch: fan_in of [Cin, Cout, k] uses dim 1
+            sd[name] = uni(shape, 1.0 / math.sqrt(fan_in))
+        elif name.endswith("conv.weight"):
+            fan_in = shape[1] * shape[2]
+            sd[name] = uni(shape, 1.0 / math.sqrt(fan_in))
+        else:  # conv / convtr bias
+            sd[name] = uni(shape, 0.1)
+    nq, K, D = cfg.num_quantizers, cfg.codebook_size, cfg.dimension
+    sigma = 0.6 * (0.93 ** torch.arange(nq, dtype=torch.float32)).view(nq, 1, 1)
+    embed = torch.randn((nq, K, D), generator=g) * sigma
+    sd["quantizer.rq.model.inited"] = torch.ones(nq, 1)
+    sd["quantizer.rq.model.cluster_size"] = torch.ones(nq, K)
+    sd["quantizer.rq.model.embed"] = embed
+    sd["quantizer.rq.model.embed_avg"] = embed.clone()
+    return sd
