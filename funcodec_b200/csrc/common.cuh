@@ -1,0 +1,78 @@
+// Shared device/host definitions for the funcodec_b200 kernels (sm_100a).
+//
+// HBM layout: every activation is stored CHANNELS-LAST, [B][T][C] fp32, RAW
+// (= conv output incl. bias, before GroupNorm).  GroupNorm(1,C) needs the statistics of the whole
+// (C x T) plane of a clip, so a layer cannot normalise its own output in its epilogue; instead each
+// conv emits per-CTA (sum, sum^2) partials, a tiny finalize kernel turns them into (mean, rstd) per
+// clip, and the CONSUMER applies   y = x * (rstd*gamma[c]) + (beta[c] - mean*rstd*gamma[c])
+// (ATen's GroupNorm formulation) + optional second operand (resblock sum) + optional ELU while it
+// stages its input tile into shared memory.  No normalised tensor is ever written to HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcb {
+
+// A (possibly normalised) view of a raw activation tensor.
+struct InView {
+    const float* x;          // raw [B][rows][C]; nullptr => view unused
+    const float* stats;      // [B][2] = (mean, rstd); nullptr => identity (plain tensor)
+    const float* gamma;      // [C] GroupNorm weight (used when stats != nullptr)
+    const float* beta;       // [C] GroupNorm bias
+    long long clip_stride;   // elements between consecutive clips
+    int row_off;             // first logical row (transposed-conv trim, conv.py:299-303)
+};
+
+struct ConvParams {
+    InView in0, in1;         // input = f(in0) [+ f(in1)]   (resblock: shortcut + block)
+    const float* div_scale;  // [B] or nullptr: input = x / scale[b]  (codec_basic.py:366-371)
+    int elu;                 // apply ELU(alpha=1) to the summed input
+    int T_in, C_in;
+    int K, S, D;             // taps, stride, dilation
+    int pad_l;               // left padding
+    int T_ext;               // reflect period length (== T_in unless the tiny-input branch, conv.py:89-97)
+    int pad_zero;            // 1: out-of-range taps read 0 (transposed conv as 2-tap conv); 0: reflect
+    const float* w;          // packed [K][C_in][C_out]
+    const float* bias;       // [C_out]
+    float* out;              // raw [B][T_out][C_out]
+    int T_out, C_out;
+    long long out_clip_stride;
+    double* partials;        // [B][n_parts][2] (sum, sum of squares) or nullptr
+    int cic;                 // input-channel chunk staged per iteration
+};
+
+__device__ __forceinline__ float elu1(float v) {
+    // ATen CPU ELU: x <= 0 ? (exp(x) - 1) : x   (alpha = 1)
+    return v > 0.f ? v : (expf(v) - 1.0f);
+}
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    // F.pad(mode='reflect') index map for one reflection (|pad| < n is guaranteed by the caller)
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// Block-wide sum of two doubles (deterministic order).  red must hold 2*32 doubles.
+__device__ __forceinline__ void block_reduce_2d(double& a, double& b, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        a = lane < nwarps ? red[lane] : 0.0;
+        b = lane < nwarps ? red[32 + lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+    }
+}
+
+}  // namespace fcb

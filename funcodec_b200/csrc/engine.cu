@@ -1,0 +1,738 @@
+// Host-side engine + C ABI (include/funcodec_b200.h): weight repacking, the layer walk of the SEANet
+// encoder / decoder, the RVQ call and stream-ordered workspace management.
+//
+// Layer walk follows SEANetEncoder.__init__ (funcodec/models/encoder/seanet_encoder.py:108-162),
+// SEANetDecoder.__init__ (funcodec/models/decoder/seanet_decoder.py:107-172) and Encodec._encode_frame /
+// _decode_frame (funcodec/models/codec_basic.py:361-408).  Activations are raw channels-last tensors with
+// deferred GroupNorm (common.cuh); temporaries come from the CUDA stream-ordered pool (cudaMallocAsync), so
+// a whole call enqueues without host synchronisation and memory is recycled layer by layer.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/funcodec_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace fcb;
+
+namespace {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl_kernel
+    int cin = 0, cout = 0, k = 0, s = 1;
+    bool transposed = false;
+    float* w = nullptr;      // [K_eff][cin][cout_eff]
+    float* bias = nullptr;   // [cout_eff]
+    float* gamma = nullptr;  // [cout]
+    float* beta = nullptr;   // [cout]
+};
+
+struct LstmW {
+    int H = 0, layers = 0;
+    std::vector<float*> wih, whh, bias;   // packed [H][4H], [H][4H], [4H]
+};
+
+struct ResBlockW { ConvW c1, c2, sc; };
+
+// A raw activation plus its deferred GroupNorm.
+struct Act {
+    float* p = nullptr;
+    int T = 0, C = 0;
+    long long clip_stride = 0;
+    int row_off = 0;
+    float* stats = nullptr;          // [B][2] or nullptr (plain tensor)
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    bool owned = false;              // p (and stats) were allocated from the pool by the engine
+};
+
+}  // namespace
+
+struct fcb_handle {
+    fcb_config cfg{};
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, HostTensor> host;
+    std::string err;
+    int64_t launches = 0;
+
+    ConvW enc_conv0, enc_final, dec_conv0, dec_final;
+    std::vector<ResBlockW> enc_rb, dec_rb;
+    std::vector<ConvW> enc_down, dec_up;
+    LstmW enc_lstm, dec_lstm;
+    float* embed = nullptr;   // [n_q][K][D]
+    float* cnorm = nullptr;   // [n_q][K]
+    int* err_flag = nullptr;
+    std::vector<void*> dev_allocs;
+
+    bool profiling = false;
+    cudaEvent_t ev[FCB_NUM_PHASES + 1][2]{};
+    bool ev_used[FCB_NUM_PHASES]{};
+    bool ev_created = false;
+
+    int hop() const { int h = 1; for (int i = 0; i < cfg.n_ratios; ++i) h *= cfg.ratios[i]; return h; }
+    int top_channels() const { return cfg.n_filters << cfg.n_ratios; }
+};
+
+namespace {
+
+#define FCB_CK(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            char buf__[512];                                                                      \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            h->err = buf__;                                                                       \
+            return FCB_E_CUDA;                                                                    \
+        }                                                                                         \
+    } while (0)
+
+#define FCB_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != FCB_OK) return rc__; \
+    } while (0)
+
+int fail(fcb_handle* h, int code, const std::string& msg) { h->err = msg; return code; }
+
+// ------------------------------------------------------------------------------------------- weights
+const HostTensor* find(fcb_handle* h, const std::string& name) {
+    auto it = h->host.find(name);
+    return it == h->host.end() ? nullptr : &it->second;
+}
+
+int upload(fcb_handle* h, const std::vector<float>& v, float** out) {
+    float* d = nullptr;
+    FCB_CK(cudaMalloc(&d, v.size() * sizeof(float)));
+    h->dev_allocs.push_back(d);
+    FCB_CK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = d;
+    return FCB_OK;
+}
+
+int need(fcb_handle* h, const std::string& name, std::vector<int64_t> shape, const HostTensor** out) {
+    const HostTensor* t = find(h, name);
+    if (!t) return fail(h, FCB_E_MISSING, "missing tensor: " + name);
+    if (t->shape != shape) return fail(h, FCB_E_INVALID, "shape mismatch for " + name);
+    *out = t;
+    return FCB_OK;
+}
+
+// SConv1d: conv.conv.weight [cout][cin][k] -> [k][cin][cout]
+int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k, int s, ConvW* o) {
+    const HostTensor *w, *b, *g, *be;
+    FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, k}, &w));
+    FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
+    FCB_TRY(need(h, prefix + ".conv.norm.weight", {cout}, &g));
+    FCB_TRY(need(h, prefix + ".conv.norm.bias", {cout}, &be));
+    std::vector<float> p((size_t)k * cin * cout);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int kk = 0; kk < k; ++kk)
+                p[((size_t)kk * cin + ci) * cout + co] = w->data[((size_t)co * cin + ci) * k + kk];
+    o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->transposed = false;
+    FCB_TRY(upload(h, p, &o->w));
+    FCB_TRY(upload(h, b->data, &o->bias));
+    FCB_TRY(upload(h, g->data, &o->gamma));
+    FCB_TRY(upload(h, be->data, &o->beta));
+    return FCB_OK;
+}
+
+// SConvTranspose1d (k = 2s): convtr.convtr.weight [cin][cout][2s].  out_full[t*s + p] =
+//   sum_ci x[t][ci] W[ci][co][p] + x[t-1][ci] W[ci][co][p+s]   (t in [0, T], x[-1] = x[T] = 0)
+// == a 2-tap zero-padded conv with C_out' = s*cout whose channels-last output IS out_full[(T+1)*s][cout].
+// packed [tap][cin][p*cout + co]: tap 0 <-> x[t-1] (W[..][p+s]), tap 1 <-> x[t] (W[..][p]).
+int pack_convtr(fcb_handle* h, const std::string& prefix, int cin, int cout, int s, ConvW* o) {
+    const int k = 2 * s;
+    const HostTensor *w, *b, *g, *be;
+    FCB_TRY(need(h, prefix + ".convtr.convtr.weight", {cin, cout, k}, &w));
+    FCB_TRY(need(h, prefix + ".convtr.convtr.bias", {cout}, &b));
+    FCB_TRY(need(h, prefix + ".convtr.norm.weight", {cout}, &g));
+    FCB_TRY(need(h, prefix + ".convtr.norm.bias", {cout}, &be));
+    const int ce = s * cout;
+    std::vector<float> p((size_t)2 * cin * ce), bias(ce);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+            for (int ph = 0; ph < s; ++ph) {
+                p[((size_t)0 * cin + ci) * ce + ph * cout + co] = w->data[((size_t)ci * cout + co) * k + ph + s];
+                p[((size_t)1 * cin + ci) * ce + ph * cout + co] = w->data[((size_t)ci * cout + co) * k + ph];
+            }
+    for (int ph = 0; ph < s; ++ph)
+        for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
+    o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->transposed = true;
+    FCB_TRY(upload(h, p, &o->w));
+    FCB_TRY(upload(h, bias, &o->bias));
+    FCB_TRY(upload(h, g->data, &o->gamma));
+    FCB_TRY(upload(h, be->data, &o->beta));
+    return FCB_OK;
+}
+
+// nn.LSTM weights [4H][H] (rows gate-major i,f,g,o) -> [H][4H] with unit-major columns n' = 4*j + gate.
+int pack_lstm(fcb_handle* h, const std::string& prefix, int H, int layers, LstmW* o) {
+    o->H = H; o->layers = layers;
+    for (int l = 0; l < layers; ++l) {
+        const HostTensor *wih, *whh, *bih, *bhh;
+        const std::string sl = std::to_string(l);
+        FCB_TRY(need(h, prefix + ".lstm.weight_ih_l" + sl, {4 * H, H}, &wih));
+        FCB_TRY(need(h, prefix + ".lstm.weight_hh_l" + sl, {4 * H, H}, &whh));
+        FCB_TRY(need(h, prefix + ".lstm.bias_ih_l" + sl, {4 * H}, &bih));
+        FCB_TRY(need(h, prefix + ".lstm.bias_hh_l" + sl, {4 * H}, &bhh));
+        std::vector<float> pi((size_t)H * 4 * H), ph((size_t)H * 4 * H), pb(4 * H);
+        for (int g = 0; g < 4; ++g)
+            for (int j = 0; j < H; ++j) {
+                const size_t row = (size_t)g * H + j;
+                const size_t col = (size_t)j * 4 + g;
+                for (int k = 0; k < H; ++k) {
+                    pi[(size_t)k * 4 * H + col] = wih->data[row * H + k];
+                    ph[(size_t)k * 4 * H + col] = whh->data[row * H + k];
+                }
+                pb[col] = bih->data[row] + bhh->data[row];
+            }
+        float *dwi, *dwh, *db;
+        FCB_TRY(upload(h, pi, &dwi));
+        FCB_TRY(upload(h, ph, &dwh));
+        FCB_TRY(upload(h, pb, &db));
+        o->wih.push_back(dwi); o->whh.push_back(dwh); o->bias.push_back(db);
+    }
+    return FCB_OK;
+}
+
+int pack_resblock(fcb_handle* h, const std::string& prefix, int dim, ResBlockW* o) {
+    FCB_TRY(pack_conv(h, prefix + ".block.1", dim, dim / 2, h->cfg.residual_kernel_size, 1, &o->c1));
+    FCB_TRY(pack_conv(h, prefix + ".block.3", dim / 2, dim, 1, 1, &o->c2));
+    FCB_TRY(pack_conv(h, prefix + ".shortcut", dim, dim, 1, 1, &o->sc));
+    return FCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- run helpers
+struct Run {
+    fcb_handle* h;
+    int B;
+    cudaStream_t st;
+    int phase = -1;
+};
+
+int alloc_f(Run& r, float** p, size_t n) {
+    fcb_handle* h = r.h;
+    FCB_CK(cudaMallocAsync((void**)p, n * sizeof(float), r.st));
+    return FCB_OK;
+}
+
+int release(Run& r, Act& a) {
+    fcb_handle* h = r.h;
+    if (a.owned) {
+        if (a.p) FCB_CK(cudaFreeAsync(a.p, r.st));
+        if (a.stats) FCB_CK(cudaFreeAsync(a.stats, r.st));
+    }
+    a = Act();
+    return FCB_OK;
+}
+
+int phase_begin(Run& r, int ph) {
+    fcb_handle* h = r.h;
+    if (!h->profiling) return FCB_OK;
+    r.phase = ph;
+    h->ev_used[ph] = true;
+    FCB_CK(cudaEventRecord(h->ev[ph][0], r.st));
+    return FCB_OK;
+}
+int phase_end(Run& r) {
+    fcb_handle* h = r.h;
+    if (!h->profiling || r.phase < 0) return FCB_OK;
+    FCB_CK(cudaEventRecord(h->ev[r.phase][1], r.st));
+    r.phase = -1;
+    return FCB_OK;
+}
+
+InView view_of(const Act& a) {
+    InView v;
+    v.x = a.p; v.stats = a.stats; v.gamma = a.gamma; v.beta = a.beta;
+    v.clip_stride = a.clip_stride; v.row_off = a.row_off;
+    return v;
+}
+
+// One SConv1d / SConvTranspose1d.  in1 may be null.  want_norm=false -> plain output (LSTM input projection).
+int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_scale, const ConvW& L,
+             bool want_norm, Act* out, const float* w_override = nullptr, const float* bias_override = nullptr,
+             int cout_override = 0) {
+    fcb_handle* h = r.h;
+    ConvParams p{};
+    p.in0 = view_of(in0);
+    if (in1) p.in1 = view_of(*in1); else p.in1.x = nullptr;
+    p.div_scale = div_scale;
+    p.elu = elu ? 1 : 0;
+    p.T_in = in0.T; p.C_in = in0.C;
+    if (in0.C != L.cin && !w_override) return fail(h, FCB_E_INVALID, "internal: channel mismatch");
+    Act o;
+    if (!L.transposed || w_override) {
+        const int k = w_override ? 1 : L.k, s = w_override ? 1 : L.s, d = 1;
+        const int cout = w_override ? cout_override : L.cout;
+        const int padding_total = (k - 1) * d - (s - 1);
+        // get_extra_padding_for_conv1d (conv.py:57-64), integer form of ceil((T - k + pt)/s)
+        const int num = in0.T - k + padding_total;
+        const int n_frames_ceil = (num >= 0 ? (num + s - 1) / s : -((-num) / s)) + 1;
+        const int ideal = (n_frames_ceil - 1) * s + (k - padding_total);
+        const int extra = ideal - in0.T;
+        const int pr = padding_total / 2, pl = padding_total - pr;
+        const int pr_tot = pr + extra;
+        const int max_pad = pl > pr_tot ? pl : pr_tot;
+        p.K = k; p.S = s; p.D = d; p.pad_l = pl; p.pad_zero = 0;
+        p.T_ext = in0.T <= max_pad ? max_pad + 1 : in0.T;     // pad1d tiny-input branch (conv.py:89-97)
+        p.T_out = (in0.T + pl + pr_tot - k) / s + 1;
+        p.C_out = cout;
+        p.w = w_override ? w_override : L.w;
+        p.bias = bias_override ? bias_override : L.bias;
+        o.T = p.T_out; o.C = cout; o.clip_stride = (long long)p.T_out * cout; o.row_off = 0;
+    } else {
+        const int s = L.s;
+        p.K = 2; p.S = 1; p.D = 1; p.pad_l = 1; p.pad_zero = 1; p.T_ext = in0.T;
+        p.T_out = in0.T + 1;
+        p.C_out = s * L.cout;
+        p.w = L.w; p.bias = L.bias;
+        const int padding_total = L.k - s;                    // conv.py:283-303
+        const int pr = padding_total / 2, pl = padding_total - pr;
+        o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
+    }
+    p.out_clip_stride = (long long)p.T_out * p.C_out;
+    FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
+    o.owned = true;
+    double* partials = nullptr;
+    int nparts = conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B);
+    if (want_norm) {
+        FCB_CK(cudaMallocAsync((void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double), r.st));
+        FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
+        o.gamma = L.gamma; o.beta = L.beta;
+    }
+    p.partials = partials;
+    int np2 = 0;
+    FCB_CK(launch_conv(p, r.B, r.st, &np2));
+    h->launches++;
+    if (want_norm) {
+        if (np2 != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch");
+        FCB_CK(launch_stats_finalize(partials, nparts, (double)p.T_out * p.C_out, h->cfg.gn_eps, 0, o.stats, r.B, r.st));
+        h->launches++;
+        FCB_CK(cudaFreeAsync(partials, r.st));
+    }
+    *out = o;
+    return FCB_OK;
+}
+
+// SLSTM (lstm.py:22-28): y = LSTM(x) + x.  x is a normalised view; y is a plain tensor.
+int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
+    fcb_handle* h = r.h;
+    const int H = W.H, T = x.T, B = r.B;
+    if (x.C != H) return fail(h, FCB_E_INVALID, "internal: lstm width mismatch");
+    float* c_state = nullptr;
+    FCB_TRY(alloc_f(r, &c_state, (size_t)B * H));
+    Act cur = x;       // not owned copy semantics: only release what we allocate
+    cur.owned = false;
+    Act y;
+    for (int l = 0; l < W.layers; ++l) {
+        Act gx;
+        ConvW dummy;
+        dummy.cin = H;
+        FCB_TRY(run_conv(r, cur, nullptr, false, nullptr, dummy, false, &gx, W.wih[l], W.bias[l], 4 * H));
+        Act hs;
+        FCB_TRY(alloc_f(r, &hs.p, (size_t)B * T * H));
+        hs.owned = true; hs.T = T; hs.C = H; hs.clip_stride = (long long)T * H;
+        const bool last = (l == W.layers - 1);
+        if (last) {
+            FCB_TRY(alloc_f(r, &y.p, (size_t)B * T * H));
+            y.owned = true; y.T = T; y.C = H; y.clip_stride = (long long)T * H;
+        }
+        LstmStepParams sp{};
+        sp.gx = gx.p; sp.whh = W.whh[l]; sp.h_seq = hs.p; sp.c_state = c_state;
+        sp.y_out = last ? y.p : nullptr;
+        sp.skip = view_of(x);
+        sp.B = B; sp.T = T; sp.H = H;
+        for (int t = 0; t < T; ++t) {
+            sp.t = t;
+            FCB_CK(launch_lstm_step(sp, r.st));
+        }
+        h->launches += T;
+        FCB_TRY(release(r, gx));
+        if (l > 0) FCB_TRY(release(r, cur));
+        cur = hs;
+    }
+    FCB_TRY(release(r, cur));
+    FCB_CK(cudaFreeAsync(c_state, r.st));
+    *out = y;
+    return FCB_OK;
+}
+
+int run_resblock(Run& r, const Act& x, const ResBlockW& W, Act* sc_out, Act* blk_out) {
+    Act h1, h2, sc;
+    FCB_TRY(run_conv(r, x, nullptr, true, nullptr, W.c1, true, &h1));
+    FCB_TRY(run_conv(r, h1, nullptr, true, nullptr, W.c2, true, &h2));
+    FCB_TRY(release(r, h1));
+    FCB_TRY(run_conv(r, x, nullptr, false, nullptr, W.sc, true, &sc));
+    *sc_out = sc; *blk_out = h2;
+    return FCB_OK;
+}
+
+// Encodec._encode_frame (codec_basic.py:361-380) + SEANetEncoder.forward; returns the final conv's raw
+// output view (GroupNorm deferred into the RVQ kernel's load).
+int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
+    fcb_handle* h = r.h;
+    const int B = r.B;
+    FCB_TRY(phase_begin(r, FCB_PHASE_ENCODER_CONV));
+    float* scale = nullptr;
+    bool scale_owned = false;
+    if (h->cfg.audio_normalize) {
+        double* partials = nullptr;
+        int nparts = sumsq_num_parts(L), np2 = 0;
+        FCB_CK(cudaMallocAsync((void**)&partials, (size_t)B * nparts * 2 * sizeof(double), r.st));
+        if (scale_out) scale = scale_out; else { FCB_TRY(alloc_f(r, &scale, B)); scale_owned = true; }
+        FCB_CK(launch_sumsq_partials(wav, B, L, partials, &np2, r.st));
+        FCB_CK(launch_stats_finalize(partials, nparts, (double)L, 0.f, 1, scale, B, r.st));
+        h->launches += 2;
+        FCB_CK(cudaFreeAsync(partials, r.st));
+    } else if (scale_out) {
+        FCB_CK(launch_fill(scale_out, 1.0f, B, r.st));
+        h->launches++;
+    }
+    Act x;
+    x.p = const_cast<float*>(wav); x.T = L; x.C = 1; x.clip_stride = L;
+    Act a;
+    FCB_TRY(run_conv(r, x, nullptr, false, scale, h->enc_conv0, true, &a));
+    if (scale_owned) FCB_CK(cudaFreeAsync(scale, r.st));
+    for (size_t i = 0; i < h->enc_rb.size(); ++i) {
+        Act sc, blk, d;
+        FCB_TRY(run_resblock(r, a, h->enc_rb[i], &sc, &blk));
+        FCB_TRY(release(r, a));
+        FCB_TRY(run_conv(r, sc, &blk, true, nullptr, h->enc_down[i], true, &d));
+        FCB_TRY(release(r, sc));
+        FCB_TRY(release(r, blk));
+        a = d;
+    }
+    FCB_TRY(phase_end(r));
+    // phase ENCODER_LSTM = SLSTM + the final k7 conv (both live at T' frames)
+    FCB_TRY(phase_begin(r, FCB_PHASE_ENCODER_LSTM));
+    if (h->cfg.lstm_layers > 0) {
+        Act y;
+        FCB_TRY(run_lstm(r, a, h->enc_lstm, &y));
+        FCB_TRY(release(r, a));
+        a = y;
+    }
+    Act f;
+    FCB_TRY(run_conv(r, a, nullptr, true, nullptr, h->enc_final, true, &f));
+    FCB_TRY(release(r, a));
+    FCB_TRY(phase_end(r));
+    *out = f;
+    return FCB_OK;
+}
+
+// SEANetDecoder.forward + Encodec._decode_frame (codec_basic.py:398-408) + trim (:711).
+int run_decoder(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
+    fcb_handle* h = r.h;
+    const int hop = h->hop();
+    if (out_len > n_frames * hop || out_len <= 0) return fail(h, FCB_E_INVALID, "out_len must be in (0, T'*hop]");
+    Act e;
+    e.p = const_cast<float*>(emb); e.T = n_frames; e.C = h->cfg.dimension; e.clip_stride = (long long)n_frames * e.C;
+    FCB_TRY(phase_begin(r, FCB_PHASE_DECODER_LSTM));
+    Act a;
+    FCB_TRY(run_conv(r, e, nullptr, false, nullptr, h->dec_conv0, true, &a));
+    if (h->cfg.lstm_layers > 0) {
+        Act y;
+        FCB_TRY(run_lstm(r, a, h->dec_lstm, &y));
+        FCB_TRY(release(r, a));
+        a = y;
+    }
+    FCB_TRY(phase_end(r));
+    FCB_TRY(phase_begin(r, FCB_PHASE_DECODER_CONV));
+    Act sc = a, blk;   // "sc + blk" is the current tensor; blk unused before the first resblock
+    bool have_blk = false;
+    for (size_t i = 0; i < h->dec_up.size(); ++i) {
+        Act u;
+        FCB_TRY(run_conv(r, sc, have_blk ? &blk : nullptr, true, nullptr, h->dec_up[i], true, &u));
+        FCB_TRY(release(r, sc));
+        if (have_blk) FCB_TRY(release(r, blk));
+        FCB_TRY(run_resblock(r, u, h->dec_rb[i], &sc, &blk));
+        FCB_TRY(release(r, u));
+        have_blk = true;
+    }
+    Act f;
+    FCB_TRY(run_conv(r, sc, have_blk ? &blk : nullptr, true, nullptr, h->dec_final, true, &f));
+    FCB_TRY(release(r, sc));
+    if (have_blk) FCB_TRY(release(r, blk));
+    FCB_CK(launch_final_output(f.p, f.stats, f.gamma, f.beta, scale, r.B, f.T, out_len, wav_out, r.st));
+    h->launches++;
+    FCB_TRY(release(r, f));
+    FCB_TRY(phase_end(r));
+    return FCB_OK;
+}
+
+int check_ready(fcb_handle* h) {
+    if (!h) return FCB_E_INVALID;
+    if (!h->finalized) return fail(h, FCB_E_STATE, "fcb_finalize has not been called");
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device)
+        return fail(h, FCB_E_STATE, "handle used on a different CUDA device than it was created on");
+    return FCB_OK;
+}
+
+int do_encode(fcb_handle* h, const float* wav, int B, int L, int n_q, int64_t* codes, float* quant, float* scale,
+              float* sub_quants, float* encoder_out, cudaStream_t st) {
+    if (!wav || !codes || B <= 0 || L <= 0) return fail(h, FCB_E_INVALID, "fcb_encode: bad arguments");
+    if (n_q <= 0 || n_q > h->cfg.num_quantizers) return fail(h, FCB_E_INVALID, "fcb_encode: n_q out of range");
+    Run r{h, B, st};
+    Act f;
+    FCB_TRY(run_encoder(r, wav, L, scale, &f));
+    FCB_TRY(phase_begin(r, FCB_PHASE_RVQ));
+    RvqParams q{};
+    q.in = view_of(f);
+    q.embed = h->embed; q.cnorm = h->cnorm;
+    q.B = B; q.T = f.T; q.D = h->cfg.dimension; q.K = h->cfg.codebook_size; q.n_q = n_q;
+    q.codes = reinterpret_cast<long long*>(codes);
+    q.quant = quant; q.sub_quants = sub_quants; q.enc_out = encoder_out;
+    FCB_CK(launch_rvq(q, st));
+    h->launches++;
+    FCB_TRY(release(r, f));
+    FCB_TRY(phase_end(r));
+    return FCB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+const char* fcb_version(void) { return "funcodec_b200 0.1.0 sm_100a"; }
+
+int fcb_create(const fcb_config* cfg, fcb_handle** out) {
+    if (!cfg || !out) return FCB_E_INVALID;
+    if (cfg->n_ratios < 1 || cfg->n_ratios > FCB_MAX_RATIOS || cfg->n_filters < 2 || cfg->dimension < 4 ||
+        cfg->dimension % 4 != 0 || cfg->codebook_size < 1 || cfg->num_quantizers < 1 || cfg->lstm_layers < 0 ||
+        cfg->kernel_size < 1 || cfg->last_kernel_size < 1 || cfg->residual_kernel_size < 1)
+        return FCB_E_INVALID;
+    for (int i = 0; i < cfg->n_ratios; ++i)
+        if (cfg->ratios[i] < 1) return FCB_E_INVALID;
+    fcb_handle* h = new (std::nothrow) fcb_handle();
+    if (!h) return FCB_E_NOMEM;
+    h->cfg = *cfg;
+    if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
+    // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = h;
+    return FCB_OK;
+}
+
+int fcb_set_tensor(fcb_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape) {
+    if (!h || !name || !data || ndim < 0 || ndim > 4) return FCB_E_INVALID;
+    if (h->finalized) return fail(h, FCB_E_STATE, "fcb_set_tensor after fcb_finalize");
+    std::string n(name);
+    const bool known = n.rfind("encoder.model.", 0) == 0 || n.rfind("decoder.model.", 0) == 0 ||
+                       n == "quantizer.rq.model.embed";
+    if (!known) return 1;   // ignored (discriminator, EMA buffers, ...), like filter_state_dict
+    HostTensor t;
+    size_t cnt = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); cnt *= (size_t)shape[i]; }
+    t.data.assign(data, data + cnt);
+    h->host[n] = std::move(t);
+    return FCB_OK;
+}
+
+int fcb_finalize(fcb_handle* h) {
+    if (!h) return FCB_E_INVALID;
+    if (h->finalized) return fail(h, FCB_E_STATE, "already finalized");
+    const fcb_config& c = h->cfg;
+    const int nf = c.n_filters, D = c.dimension;
+    FCB_TRY(pack_conv(h, "encoder.model.0", 1, nf, c.kernel_size, 1, &h->enc_conv0));
+    int n = 1, mult = 1;
+    for (int i = c.n_ratios - 1; i >= 0; --i) {      // encoder applies the ratios reversed (seanet_encoder.py:102)
+        const int ratio = c.ratios[i];
+        ResBlockW rb; ConvW down;
+        FCB_TRY(pack_resblock(h, "encoder.model." + std::to_string(n), mult * nf, &rb));
+        FCB_TRY(pack_conv(h, "encoder.model." + std::to_string(n + 2), mult * nf, 2 * mult * nf, 2 * ratio, ratio, &down));
+        h->enc_rb.push_back(rb); h->enc_down.push_back(down);
+        mult *= 2; n += 3;
+    }
+    if (c.lstm_layers > 0) {
+        FCB_TRY(pack_lstm(h, "encoder.model." + std::to_string(n), mult * nf, c.lstm_layers, &h->enc_lstm));
+        n += 1;
+    }
+    FCB_TRY(pack_conv(h, "encoder.model." + std::to_string(n + 1), mult * nf, D, c.last_kernel_size, 1, &h->enc_final));
+
+    FCB_TRY(pack_conv(h, "decoder.model.0", D, mult * nf, c.kernel_size, 1, &h->dec_conv0));
+    n = 1;
+    if (c.lstm_layers > 0) {
+        FCB_TRY(pack_lstm(h, "decoder.model.1", mult * nf, c.lstm_layers, &h->dec_lstm));
+        n = 2;
+    }
+    for (int i = 0; i < c.n_ratios; ++i) {
+        const int ratio = c.ratios[i];
+        ConvW up; ResBlockW rb;
+        FCB_TRY(pack_convtr(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, ratio, &up));
+        FCB_TRY(pack_resblock(h, "decoder.model." + std::to_string(n + 2), mult * nf / 2, &rb));
+        h->dec_up.push_back(up); h->dec_rb.push_back(rb);
+        mult /= 2; n += 3;
+    }
+    FCB_TRY(pack_conv(h, "decoder.model." + std::to_string(n + 1), nf, 1, c.last_kernel_size, 1, &h->dec_final));
+
+    const HostTensor* emb;
+    FCB_TRY(need(h, "quantizer.rq.model.embed", {c.num_quantizers, c.codebook_size, D}, &emb));
+    FCB_TRY(upload(h, emb->data, &h->embed));
+    FCB_CK(cudaMalloc((void**)&h->cnorm, (size_t)c.num_quantizers * c.codebook_size * sizeof(float)));
+    h->dev_allocs.push_back(h->cnorm);
+    FCB_CK(cudaMalloc((void**)&h->err_flag, sizeof(int)));
+    h->dev_allocs.push_back(h->err_flag);
+    FCB_CK(cudaMemset(h->err_flag, 0, sizeof(int)));
+    FCB_CK(launch_code_norms(h->embed, h->cnorm, c.num_quantizers * c.codebook_size, D, 0));
+    h->launches++;
+    FCB_CK(cudaDeviceSynchronize());
+    h->host.clear();
+    h->finalized = true;
+    return FCB_OK;
+}
+
+int fcb_num_frames(const fcb_handle* h, int32_t L) {
+    if (!h || L <= 0) return FCB_E_INVALID;
+    const int hop = h->hop();
+    return (L + hop - 1) / hop;
+}
+
+int fcb_num_quantizers_for_bandwidth(const fcb_handle* h, double bandwidth) {
+    if (!h) return FCB_E_INVALID;
+    const double bw_per_q = log2((double)h->cfg.codebook_size) * h->cfg.sample_rate / h->hop();
+    int n_q = h->cfg.num_quantizers;
+    if (bandwidth > 0.0) {
+        n_q = (int)floor(bandwidth / bw_per_q);
+        if (n_q < 1) n_q = 1;
+    }
+    return n_q;
+}
+
+int fcb_encode(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t n_q, int64_t* codes, float* quant,
+               float* scale, float* sub_quants, float* encoder_out, void* stream) {
+    FCB_TRY(check_ready(h));
+    return do_encode(h, wav, B, L, n_q, codes, quant, scale, sub_quants, encoder_out, (cudaStream_t)stream);
+}
+
+int fcb_decode_emb(fcb_handle* h, const float* emb, int32_t B, int32_t n_frames, const float* scale, float* wav_out,
+                   int32_t out_len, void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!emb || !wav_out || B <= 0 || n_frames <= 0) return fail(h, FCB_E_INVALID, "fcb_decode_emb: bad arguments");
+    Run r{h, B, (cudaStream_t)stream};
+    return run_decoder(r, emb, n_frames, scale, wav_out, out_len);
+}
+
+int fcb_decode_codes(fcb_handle* h, const int64_t* codes, int32_t B, int32_t n_frames, int32_t n_q, float* emb_out,
+                     float* wav_out, int32_t out_len, void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!codes || !wav_out || B <= 0 || n_frames <= 0) return fail(h, FCB_E_INVALID, "fcb_decode_codes: bad arguments");
+    if (n_q <= 0 || n_q > h->cfg.num_quantizers) return fail(h, FCB_E_INVALID, "fcb_decode_codes: n_q out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    Run r{h, B, st};
+    float* emb = emb_out;
+    const size_t n = (size_t)B * n_frames * h->cfg.dimension;
+    if (!emb) FCB_TRY(alloc_f(r, &emb, n));
+    FCB_TRY(phase_begin(r, FCB_PHASE_RVQ));
+    FCB_CK(launch_embed_sum(reinterpret_cast<const long long*>(codes), h->embed, B, n_frames, n_q, h->cfg.codebook_size,
+                            h->cfg.dimension, emb, h->err_flag, st));
+    h->launches++;
+    FCB_TRY(phase_end(r));
+    int rc = run_decoder(r, emb, n_frames, nullptr, wav_out, out_len);
+    if (!emb_out) FCB_CK(cudaFreeAsync(emb, st));
+    return rc;
+}
+
+int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t n_q, int32_t use_scale, int64_t* codes,
+                  float* quant, float* scale, float* sub_quants, float* recon, void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!recon) return fail(h, FCB_E_INVALID, "fcb_roundtrip: recon is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    Run r{h, B, st};
+    const int Tf = fcb_num_frames(h, L);
+    const size_t nq = (size_t)B * Tf * h->cfg.dimension;
+    float* q = quant;
+    float* sc = scale;
+    if (!q) FCB_TRY(alloc_f(r, &q, nq));
+    if (!sc) FCB_TRY(alloc_f(r, &sc, B));
+    int rc = do_encode(h, wav, B, L, n_q, codes, q, sc, sub_quants, nullptr, st);
+    if (rc == FCB_OK) {
+        const bool apply = use_scale && h->cfg.audio_normalize;
+        rc = run_decoder(r, q, Tf, apply ? sc : nullptr, recon, L);
+    }
+    if (!quant) FCB_CK(cudaFreeAsync(q, st));
+    if (!scale) FCB_CK(cudaFreeAsync(sc, st));
+    return rc;
+}
+
+int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t L, int32_t n_q, int32_t use_scale,
+                       int64_t* codes_host, float* recon_host, void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!wav_host || !codes_host || !recon_host || B <= 0 || L <= 0)
+        return fail(h, FCB_E_INVALID, "fcb_roundtrip_host: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    Run r{h, B, st};
+    const int Tf = fcb_num_frames(h, L);
+    float *d_wav, *d_recon;
+    int64_t* d_codes;
+    FCB_TRY(alloc_f(r, &d_wav, (size_t)B * L));
+    FCB_TRY(alloc_f(r, &d_recon, (size_t)B * L));
+    FCB_CK(cudaMallocAsync((void**)&d_codes, (size_t)n_q * B * Tf * sizeof(int64_t), st));
+    FCB_CK(cudaMemcpyAsync(d_wav, wav_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = fcb_roundtrip(h, d_wav, B, L, n_q, use_scale, d_codes, nullptr, nullptr, nullptr, d_recon, stream);
+    if (rc == FCB_OK) {
+        FCB_CK(cudaMemcpyAsync(codes_host, d_codes, (size_t)n_q * B * Tf * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        FCB_CK(cudaMemcpyAsync(recon_host, d_recon, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    FCB_CK(cudaFreeAsync(d_wav, st));
+    FCB_CK(cudaFreeAsync(d_recon, st));
+    FCB_CK(cudaFreeAsync(d_codes, st));
+    FCB_CK(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int64_t fcb_launch_count(const fcb_handle* h) { return h ? h->launches : -1; }
+
+int fcb_set_profiling(fcb_handle* h, int32_t enabled) {
+    if (!h) return FCB_E_INVALID;
+    if (enabled && !h->ev_created) {
+        for (int i = 0; i < FCB_NUM_PHASES; ++i)
+            for (int j = 0; j < 2; ++j) FCB_CK(cudaEventCreate(&h->ev[i][j]));
+        h->ev_created = true;
+    }
+    h->profiling = enabled != 0;
+    for (int i = 0; i < FCB_NUM_PHASES; ++i) h->ev_used[i] = false;
+    return FCB_OK;
+}
+
+int fcb_get_phase_ms(fcb_handle* h, float* ms_out) {
+    if (!h || !ms_out) return FCB_E_INVALID;
+    for (int i = 0; i < FCB_NUM_PHASES; ++i) {
+        ms_out[i] = 0.f;
+        if (h->ev_created && h->ev_used[i]) {
+            FCB_CK(cudaEventSynchronize(h->ev[i][1]));
+            FCB_CK(cudaEventElapsedTime(&ms_out[i], h->ev[i][0], h->ev[i][1]));
+        }
+    }
+    return FCB_OK;
+}
+
+const char* fcb_last_error(const fcb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void fcb_destroy(fcb_handle* h) {
+    if (!h) return;
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->ev_created)
+        for (int i = 0; i < FCB_NUM_PHASES; ++i)
+            for (int j = 0; j < 2; ++j) cudaEventDestroy(h->ev[i][j]);
+    delete h;
+}
+
+}  // extern "C"

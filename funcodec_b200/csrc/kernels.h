@@ -1,0 +1,51 @@
+// Host-callable launchers of the funcodec_b200 kernels (all asynchronous on the given stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace fcb {
+
+// conv_simt.cu
+void conv_pick_tile(int T_out, int C_out, int C_in, int K, int B, int* tx, int* tm, bool* two);
+int conv_num_parts(int T_out, int C_out, int C_in, int K, int B);
+cudaError_t launch_conv(const ConvParams& p, int B, cudaStream_t st, int* nparts);
+cudaError_t launch_stats_finalize(const double* partials, int nparts, double count, float eps, int mode,
+                                  float* out, int B, cudaStream_t st);
+int sumsq_num_parts(int L);
+cudaError_t launch_sumsq_partials(const float* x, int B, int L, double* partials, int* nparts, cudaStream_t st);
+
+// lstm.cu
+struct LstmStepParams {
+    const float* gx;      // [B][T][4H] input projection incl. both biases, columns packed unit-major (n' = 4*j + gate)
+    const float* whh;     // [H][4H] packed W_hh^T, same column order
+    float* h_seq;         // [B][T][H] hidden states of this layer (row t written at step t)
+    float* c_state;       // [B][H]
+    float* y_out;         // nullptr, or [B][T][H]: y = h + skip   (SLSTM skip, lstm.py:25-26)
+    InView skip;          // the SLSTM input (normalised on load) when y_out != nullptr
+    int B, T, H, t;
+};
+cudaError_t launch_lstm_step(const LstmStepParams& p, cudaStream_t st);
+
+// rvq.cu
+struct RvqParams {
+    InView in;            // encoder output view [B][T'][D] (normalised on load)
+    const float* embed;   // [n_q_max][K][D]
+    const float* cnorm;   // [n_q_max][K]  |c|^2
+    int B, T, D, K, n_q;
+    long long* codes;     // [n_q][B][T]
+    float* quant;         // [B][T][D] or nullptr
+    float* sub_quants;    // [n_q][B][D][T] or nullptr
+    float* enc_out;       // [B][T][D] or nullptr
+};
+cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
+cudaError_t launch_code_norms(const float* embed, float* cnorm, int rows, int D, cudaStream_t st);
+cudaError_t launch_embed_sum(const long long* codes_btq, const float* embed, int B, int T, int n_q, int K, int D,
+                             float* out, int* err_flag, cudaStream_t st);
+
+// misc.cu
+cudaError_t launch_final_output(const float* raw, const float* stats, const float* gamma, const float* beta,
+                                const float* scale, int B, int T_raw, int out_len, float* out, cudaStream_t st);
+cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
+
+}  // namespace fcb

@@ -1,0 +1,145 @@
+/*
+ * funcodec_b200 -- C ABI of the B200-native (sm_100a) codec encode -> RVQ -> decode hot path.
+ *
+ * The reference (modelscope/FunCodec) is pure Python and has no FFI; the seam this library sits
+ * under is the method seam of its `Encodec` model class:
+ *     Encodec.inference / inference_encoding   funcodec/models/codec_basic.py:670-764
+ *     Encodec.inference_decoding               funcodec/models/codec_basic.py:766-802
+ *     Encodec.inference_decoding_emb           funcodec/models/codec_basic.py:804-836
+ * as called by Speech2Token.__call__            funcodec/bin/codec_inference.py:86-134.
+ * The reference-side binding is a ctypes stub; funcodec_b200/encodec.py is that stub.
+ *
+ * Conventions
+ *   - plain C types only; no torch types.  All *device* pointers are caller-owned CUDA global memory on
+ *     the device that was current at fcb_create(); `stream` is a cudaStream_t passed as void*.
+ *   - every call is asynchronous on `stream` (no host synchronisation) unless stated otherwise.
+ *   - return value: 0 = OK, negative = error (FCB_E_*); fcb_last_error() gives the text.  No C++
+ *     exception crosses the ABI.  One handle per caller thread/stream; handles are not internally locked.
+ *   - tensors use the reference's user-facing layouts: wav [B, L] fp32; codes int64
+ *     [n_q, B, T'] (encode side) and [B, T', n_q] (decode side, codec_basic.py:789); embeddings
+ *     [B, T', D] fp32; sub_quants [n_q, B, D, T'] fp32.
+ */
+#ifndef FUNCODEC_B200_H_
+#define FUNCODEC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FCB_API __attribute__((visibility("default")))
+#else
+#define FCB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCB_OK            0
+#define FCB_E_INVALID    -1   /* bad argument / shape / name */
+#define FCB_E_STATE      -2   /* call order (e.g. encode before finalize) */
+#define FCB_E_CUDA       -3   /* CUDA runtime error */
+#define FCB_E_MISSING    -4   /* a required tensor was never set */
+#define FCB_E_NOMEM      -5
+
+#define FCB_MAX_RATIOS 8
+
+/* Hyper-parameters == the YAML keys GANSpeechCodecTask.build_model consumes
+ * (funcodec/tasks/gan_speech_codec.py:301-358; egs/LibriTTS/codec/conf/encodec_16k_n32_600k_step*.yaml). */
+typedef struct fcb_config {
+    int32_t n_ratios;
+    int32_t ratios[FCB_MAX_RATIOS]; /* decoder order, e.g. {8,5,4,2,2}; the encoder applies them reversed */
+    int32_t n_filters;              /* 32 */
+    int32_t dimension;              /* D = 128 */
+    int32_t kernel_size;            /* 7 */
+    int32_t last_kernel_size;       /* 7 */
+    int32_t residual_kernel_size;   /* 3 */
+    int32_t lstm_layers;            /* 2 (0 disables the SLSTM) */
+    int32_t codebook_size;          /* K = 1024 */
+    int32_t num_quantizers;         /* n_q max = 32 */
+    int32_t sample_rate;            /* 16000 */
+    int32_t audio_normalize;        /* model_conf.audio_normalize */
+    float   gn_eps;                 /* nn.GroupNorm eps, 1e-5 */
+} fcb_config;
+
+typedef struct fcb_handle fcb_handle;
+
+/* Library / build identification ("funcodec_b200 x.y sm_100a"). */
+FCB_API const char* fcb_version(void);
+
+/* Create a model instance bound to the current CUDA device.  Replaces the module construction in
+ * GANSpeechCodecTask.build_model (gan_speech_codec.py:319-343). */
+FCB_API int fcb_create(const fcb_config* cfg, fcb_handle** out);
+
+/* Feed one tensor of the reference state_dict (names per SURVEY.md App. D, e.g.
+ * "encoder.model.0.conv.conv.weight", "decoder.model.3.convtr.convtr.weight",
+ * "encoder.model.16.lstm.weight_ih_l0", "quantizer.rq.model.embed").  `data` is a HOST pointer to
+ * contiguous fp32; the library copies it.  Unknown names are ignored with return 1 (mirrors
+ * filter_state_dict, funcodec/torch_utils/load_pretrained_model.py:12-43); shape mismatches are errors.
+ * Replaces load_state_dict in AbsTask.build_model_from_file (funcodec/tasks/abs_task.py:1939-1944). */
+FCB_API int fcb_set_tensor(fcb_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape);
+
+/* Repack weights for the kernels, upload, precompute |c|^2.  Synchronous. */
+FCB_API int fcb_finalize(fcb_handle* h);
+
+/* T' for a clip of L samples: ceil(L / hop). */
+FCB_API int fcb_num_frames(const fcb_handle* h, int32_t L);
+/* n_q for a target bandwidth (<=0: all), ResidualVectorQuantizer.get_num_quantizers_for_bandwidth
+ * (funcodec/modules/quantization/vq.py:105-112). */
+FCB_API int fcb_num_quantizers_for_bandwidth(const fcb_handle* h, double bandwidth);
+
+/* Encodec.inference_encoding (codec_basic.py:720-764) / the encode half of Encodec.inference:
+ * RMS-normalise (:366-371) -> SEANetEncoder -> RVQ (ddp_core_vq.py:367-418).
+ *   wav          dev [B, L] fp32
+ *   codes        dev [n_q, B, T'] int64                               (required)
+ *   quant        dev [B, T', D] fp32 quantized embeddings            (nullable)
+ *   scale        dev [B] fp32 per-clip RMS scale (1.0 when !audio_normalize)   (nullable)
+ *   sub_quants   dev [n_q, B, D, T'] fp32                            (nullable)
+ *   encoder_out  dev [B, T', D] fp32 un-quantized encoder output     (nullable; parity/debug) */
+FCB_API int fcb_encode(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t n_q,
+               int64_t* codes, float* quant, float* scale, float* sub_quants, float* encoder_out,
+               void* stream);
+
+/* Encodec.inference_decoding_emb (codec_basic.py:804-836) and the decode half of Encodec.inference
+ * (:709-711): SEANetDecoder -> optional * scale -> keep the first out_len samples.
+ *   emb dev [B, T', D]; scale dev [B] or NULL; wav_out dev [B, out_len], out_len <= T' * hop. */
+FCB_API int fcb_decode_emb(fcb_handle* h, const float* emb, int32_t B, int32_t n_frames, const float* scale,
+                   float* wav_out, int32_t out_len, void* stream);
+
+/* Encodec.inference_decoding (codec_basic.py:766-802): codes dev [B, T', n_q] int64 ->
+ * sum_q embed[q][code] (ddp_core_vq.py:442-453) -> decoder.  emb_out dev [B, T', D] nullable. */
+FCB_API int fcb_decode_codes(fcb_handle* h, const int64_t* codes, int32_t B, int32_t n_frames, int32_t n_q,
+                     float* emb_out, float* wav_out, int32_t out_len, void* stream);
+
+/* Encodec.inference (codec_basic.py:670-718) with need_recon=True in one call: fcb_encode followed by
+ * decode of the quantized embeddings, recon dev [B, L].  use_scale as in the reference. */
+FCB_API int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t n_q, int32_t use_scale,
+                  int64_t* codes, float* quant, float* scale, float* sub_quants, float* recon,
+                  void* stream);
+
+/* Same as fcb_roundtrip but with HOST buffers (pinned for real asynchrony): the library stages the
+ * H2D copy of wav and the D2H copies of codes/recon on `stream` and synchronises it before returning.
+ * This is the call a non-PyTorch host (the drop-in CLI worker) makes. */
+FCB_API int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t L, int32_t n_q,
+                       int32_t use_scale, int64_t* codes_host, float* recon_host, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+FCB_API int64_t fcb_launch_count(const fcb_handle* h);
+/* Enable/disable per-phase device timing (CUDA events on `stream`); phase ids FCB_PHASE_*. */
+#define FCB_PHASE_ENCODER_CONV 0
+#define FCB_PHASE_ENCODER_LSTM 1
+#define FCB_PHASE_RVQ          2
+#define FCB_PHASE_DECODER_LSTM 3
+#define FCB_PHASE_DECODER_CONV 4
+#define FCB_NUM_PHASES         5
+FCB_API int fcb_set_profiling(fcb_handle* h, int32_t enabled);
+/* Milliseconds spent per phase in the most recent call (synchronises the recorded events). */
+FCB_API int fcb_get_phase_ms(fcb_handle* h, float* ms_out /* [FCB_NUM_PHASES] */);
+
+FCB_API const char* fcb_last_error(const fcb_handle* h);
+FCB_API void fcb_destroy(fcb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUNCODEC_B200_H_ */
