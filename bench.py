@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- codec frames/s (encode + RVQ + decode) on synthetic 16 kHz audio, BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                   (CPU arm: the oracle port of the reference path)
+
+A "step" = one Encodec.inference-equivalent pass (RMS-normalise -> SEANet encoder -> 32-stage RVQ ->
+SEANet decoder) over one batch.  Workload at N=1 = BASELINE.json configs[1]: encodec ds640, batch 16,
+10 s clips, n_q=32.  For N>1 every rank processes its own 16 clips (weak scaling; clips are independent,
+SURVEY.md §8(e)); the end-to-end number additionally scatters/gathers the clips over NCCL from rank 0.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric through
+the C-ABI host-buffer call (fcb_roundtrip_host: pinned host wav in, codes + recon out, copies inside).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config, per-GPU batch, samples, bit_width)
+    "config2": ("encodec_16k_n32_ds640", 16, 160000, None),
+    "config1": ("encodec_16k_n32_ds640", 1, 160000, None),
+    "config3": ("encodec_16k_n32_ds320", 64, 480000, None),
+    "config5": ("encodec_16k_n32_ds640", 64, 160000, None),
+}
+# SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
+ALGO = {
+    "encodec_16k_n32_ds640": dict(conv_bytes_per_10s=1066.6e6, conv_gmac_per_10s=33.10, lstm_gmac_per_10s=8.39,
+                                  rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
+    "encodec_16k_n32_ds320": dict(conv_bytes_per_10s=780.1e6, conv_gmac_per_10s=15.67, lstm_gmac_per_10s=4.19,
+                                  rvq_gflop_per_10s_nq32=4.19, weight_bytes=59.4e6),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops", 0)), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_time(cfg, sd, B, L, bit_width, reps, warm):
+    """Times the oracle (CPU port of the reference's PyTorch path) on a bounded sample; returns (frames/s, s/pass)."""
+    import torch
+    from oracle.encodec_oracle import OracleEncodec
+    o = OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    g = torch.Generator().manual_seed(1235)
+    wav = 0.1 * torch.randn(B, L, generator=g)
+    ts = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        o.inference(wav, need_recon=True, bit_width=bit_width, use_scale=True)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            ts.append(dt)
+    med = statistics.median(ts)
+    return B * cfg.frames(L) / med, med
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the GPU box)."""
+    import torch
+    from funcodec_b200 import get_config, init_state_dict
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_name, B, L, bw = WORKLOADS[args.workload]
+    cfg = get_config(cfg_name)
+    sd = init_state_dict(cfg, 0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = min(B, 2)            # bounded sample: 2 clips of the workload's length per step
+    from oracle.encodec_oracle import OracleEncodec
+    o = OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    g = torch.Generator().manual_seed(1235)
+    wav = 0.1 * torch.randn(sample_B, L, generator=g)
+    for _ in range(args.warmup):
+        o.inference(wav, need_recon=True, bit_width=bw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.inference(wav, need_recon=True, bit_width=bw)
+    dt = time.perf_counter() - t0
+    frames = sample_B * cfg.frames(L) * args.steps
+    value = frames / dt
+    sample = f"{sample_B} x {L / cfg.sample_rate:.0f} s clips per step (bounded sample of batch {B}), {cores} torch threads"
+    line = dict(metric="codec frames/sec (encode+RVQ+decode)", value=value, unit="frames/s", impl="reference",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                rtf=dt / (sample_B * L / cfg.sample_rate * args.steps),
+                config=dict(workload=f"{cfg_name} B={B} L={L} n_q={cfg.num_quantizers_for_bandwidth(bw)} (BASELINE {args.workload})",
+                            sample=sample),
+                cpu_baseline=dict(value=value, unit="frames/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): skip the host-buffer leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from funcodec_b200 import get_config, init_state_dict
+    from funcodec_b200.encodec import B200Encodec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg_name, B, L, bw = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = get_config(cfg_name)
+    sd = init_state_dict(cfg, 0)
+    model = B200Encodec(cfg, sd, str(dev))
+    n_q = cfg.num_quantizers_for_bandwidth(bw)
+    Tf = cfg.frames(L)
+    peaks = load_peaks()
+
+    # inputs: rotate over enough distinct batches that consecutive steps never re-read an L2-resident input
+    n_rot = max(2, int(140e6 // (B * L * 4)) + 1)
+    g = torch.Generator().manual_seed(1234 + 2 + rank)
+    wavs = [(0.1 * torch.randn(B, L, generator=g)).to(dev) for _ in range(n_rot)]
+    codes = torch.empty((n_q, B, Tf), dtype=torch.int64, device=dev)
+    quant = torch.empty((B, Tf, cfg.dimension), dtype=torch.float32, device=dev)
+    scale = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+    import ctypes
+    from funcodec_b200.encodec import _ptr
+
+    def step(i):
+        x = wavs[i % n_rot]
+        model._ck(model._lib.fcb_roundtrip(model._h, _ptr(x), B, L, n_q, 1, _ptr(codes), _ptr(quant), _ptr(scale),
+                                           None, _ptr(recon), model._stream()), "fcb_roundtrip")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---------------- timed region: device-resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.set_profiling(True)
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.launch_count() - launches0
+    phases = model.phase_ms()           # the last timed step's phase durations
+    model.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_total = world * B * Tf * args.steps
+    value = frames_total / (ms_max * 1e-3)
+    audio_s = world * B * L / cfg.sample_rate * args.steps
+
+    # ---------------- end-to-end: host buffers through the C ABI (+ NCCL scatter/gather of clips for N>1)
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, h2d, d2h = float("nan"), 0, 0
+    if args.skip_e2e:
+        pass
+    elif world == 1:
+        hw = (0.1 * torch.randn(B, L, generator=g)).pin_memory()
+        hc = torch.empty((n_q, B, Tf), dtype=torch.int64).pin_memory()
+        hr = torch.empty((B, 1, L), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            model.roundtrip_host(hw, hc, hr)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(e2e_steps):
+            model.roundtrip_host(hw, hc, hr)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        h2d = B * L * 4
+        d2h = hc.numel() * 8 + hr.numel() * 4
+    else:
+        GB = world * B
+        if rank == 0:
+            hw = (0.1 * torch.randn(GB, L, generator=g)).pin_memory()
+            hc = torch.empty((world, n_q, B, Tf), dtype=torch.int64).pin_memory()
+            hr = torch.empty((GB, 1, L), dtype=torch.float32).pin_memory()
+            dw = torch.empty((GB, L), dtype=torch.float32, device=dev)
+            gc = torch.empty((world, n_q, B, Tf), dtype=torch.int64, device=dev)
+            gr = torch.empty((GB, 1, L), dtype=torch.float32, device=dev)
+        my = torch.empty((B, L), dtype=torch.float32, device=dev)
+
+        def e2e_step():
+            if rank == 0:
+                dw.copy_(hw, non_blocking=True)
+                dist.scatter(my, list(dw.view(world, B, L).unbind(0)), src=0)
+            else:
+                dist.scatter(my, None, src=0)
+            model._ck(model._lib.fcb_roundtrip(model._h, _ptr(my), B, L, n_q, 1, _ptr(codes), None, None, None,
+                                               _ptr(recon), model._stream()), "fcb_roundtrip")
+            if rank == 0:
+                dist.gather(codes, list(gc.unbind(0)), dst=0)
+                dist.gather(recon, list(gr.view(world, B, 1, L).unbind(0)), dst=0)
+                hc.copy_(gc, non_blocking=True)
+                hr.copy_(gr, non_blocking=True)
+            else:
+                dist.gather(codes, None, dst=0)
+                dist.gather(recon, None, dst=0)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d = GB * L * 4
+        d2h = world * n_q * B * Tf * 8 + GB * L * 4
+    e2e_value = world * B * Tf * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        algo = ALGO[cfg_name]
+        clip10 = L / 160000.0
+        conv_ms = phases["encoder_conv"] + phases["decoder_conv"]
+        conv_bytes = algo["conv_bytes_per_10s"] * clip10 * B + algo["weight_bytes"]
+        achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
+        conv_tflops = 2 * algo["conv_gmac_per_10s"] * clip10 * B / (conv_ms * 1e-3) / 1e3 if conv_ms > 0 else 0.0
+        roofline = dict(bound="hbm", kernel="conv1d_cl_kernel (all SEANet conv/convtr launches of one step, "
+                                            "encoder_conv + decoder_conv phases)",
+                        achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                        traffic=None, peak_source=peaks["source"], algorithmic_bytes=conv_bytes,
+                        kernel_ms_per_step=conv_ms, conv_fp32_tflops=conv_tflops)
+        cpu = None
+        if not args.no_cpu_baseline:
+            import torch as _t
+            cores = os.cpu_count() or 1
+            _t.set_num_threads(cores)
+            v, sec = cpu_oracle_time(cfg, sd, 1, 160000, None, reps=5, warm=1)
+            cpu = dict(value=v, unit="frames/s", cores=cores, kind="port",
+                       sample="1 x 10 s clip (BASELINE config 1), n_q=32, median of 5 after 1 warm-up; "
+                              "oracle = torch-CPU restatement of the reference modules", seconds_per_pass=sec,
+                       rtf=sec / 10.0)
+        line = dict(metric="codec frames/sec (encode+RVQ+decode)", value=value, unit="frames/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="b200",
+                    rtf=(ms_max * 1e-3) / audio_s,
+                    config=dict(workload=f"{cfg_name} B={B}/GPU L={L} n_q={n_q} (BASELINE {args.workload})",
+                                global_batch=world * B, clip_seconds=L / cfg.sample_rate,
+                                l2="inputs rotated over %d distinct batches (>126 MB); per-step activation traffic >> L2" % n_rot,
+                                parallelism=f"dp{world} (independent clips per GPU)"),
+                    clocks=clocks, gpu_launches=int(launches),
+                    e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                             ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
+                             path="fcb_roundtrip_host (pinned host buffers)" if world == 1 else
+                                  "rank0 pinned host -> H2D -> NCCL scatter -> fcb_roundtrip -> NCCL gather -> D2H"),
+                    roofline=roofline, cpu_baseline=cpu, phase_ms_last_step=phases)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -306,6 +306,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
     o.owned = true;
+    p.out = o.p;
     double* partials = nullptr;
     int nparts = conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B);
     if (want_norm) {
