@@ -1,0 +1,37 @@
+"""Condense `ncu --page raw --csv` into one line per kernel launch with the metrics the roofline needs."""
+import csv
+import sys
+
+KEYS = [("gpu__time_duration.sum", "dur"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_inst%"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
+        ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
+        ("launch__grid_size", "grid"), ("launch__shared_mem_per_block_dynamic", "dsmem"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "bank_conf"),
+        ("smsp__average_warp_latency_issue_stalled_short_scoreboard", "stall_short_sb"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_bar"),
+        ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "st_mio"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%")]
+with open(sys.argv[1], newline="") as f:
+    rd = list(csv.reader(f))
+hdr = rd[0]
+units = rd[1]
+idx = {h: i for i, h in enumerate(hdr)}
+print("columns:", " ".join(k for _, k in KEYS if _ in idx))
+for row in rd[2:]:
+    if len(row) < len(hdr):
+        continue
+    name = row[idx["Kernel Name"]].split("(")[0][-40:]
+    out = [f"{row[idx['ID']]:>5s}", f"{name:40s}"]
+    for key, short in KEYS:
+        if key in idx:
+            out.append(f"{short}={row[idx[key]]}{units[idx[key]] if short in ('dur', 'dram_rd', 'dram_wr') else ''}")
+    print(" ".join(out))
