@@ -33,6 +33,8 @@ struct ConvParams {
     int T_ext;               // reflect period length (== T_in unless the tiny-input branch, conv.py:89-97)
     int pad_zero;            // 1: out-of-range taps read 0 (transposed conv as 2-tap conv); 0: reflect
     const float* w;          // packed [K][C_in][C_out]
+    const float* w_tc;       // tensor-core image (conv_tc.cu) or nullptr
+    int n_tile;              // output channels per CTA on the tensor-core path
     const float* bias;       // [C_out]
     float* out;              // raw [B][T_out][C_out]
     int T_out, C_out;

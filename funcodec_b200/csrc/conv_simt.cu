@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(256, TWO_LEVEL ? 1 : 2) conv1d_cl_kernel(const
                 float a[TM];
 #pragma unroll
                 for (int i = 0; i < TM; ++i) a[i] = xr[i * TY * S * pitch];
-                const float4* wr = reinterpret_cast<const float4*>(Ws + (k * cic + c) * CO_TILE + tx * TN);
-                const float4 w0 = wr[0], w1 = wr[1];
+                // a thread owns channels {4tx..4tx+3} and {CO_TILE/2 + 4tx..+3}: both float4 reads are contiguous
+                // across the lanes of a warp (no bank conflicts), and so are the output stores
+                const float* wrow = Ws + (k * cic + c) * CO_TILE + tx * 4;
+                const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrow + CO_TILE / 2);
 #pragma unroll
                 for (int i = 0; i < TM; ++i) {
                     acc[i][0] = fmaf(a[i], w0.x, acc[i][0]);
@@ -147,10 +150,13 @@ __global__ void __launch_bounds__(256, TWO_LEVEL ? 1 : 2) conv1d_cl_kernel(const
 
     // ---- epilogue: bias, raw store, GroupNorm partial statistics
     float s = 0.f, ss = 0.f;
-    const int co = co0 + tx * TN;
+    const int coA = co0 + tx * 4, coB = co0 + CO_TILE / 2 + tx * 4;    // channel of acc[.][0] and acc[.][4]
     float bias[TN];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) bias[j] = (co + j < p.C_out) ? __ldg(p.bias + co + j) : 0.f;
+    for (int j = 0; j < TN; ++j) {
+        const int co = (j < 4 ? coA : coB - 4) + j;
+        bias[j] = (co < p.C_out) ? __ldg(p.bias + co) : 0.f;
+    }
     float* outb = p.out + (long long)b * p.out_clip_stride;
     const bool vec_ok = (p.C_out % 4 == 0);
 #pragma unroll
@@ -160,17 +166,21 @@ __global__ void __launch_bounds__(256, TWO_LEVEL ? 1 : 2) conv1d_cl_kernel(const
         float o[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            const int co = (j < 4 ? coA : coB - 4) + j;
             o[j] = (TWO_LEVEL ? tot[TWO_LEVEL ? i : 0][TWO_LEVEL ? j : 0] : acc[i][j]) + bias[j];
-            if (co + j < p.C_out) { s += o[j]; ss = fmaf(o[j], o[j], ss); }
+            if (co < p.C_out) { s += o[j]; ss = fmaf(o[j], o[j], ss); }
         }
-        float* dst = outb + (long long)t * p.C_out + co;
-        if (vec_ok && co + TN <= p.C_out) {
-            reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
+        float* row = outb + (long long)t * p.C_out;
 #pragma unroll
-            for (int j = 0; j < TN; ++j)
-                if (co + j < p.C_out) dst[j] = o[j];
+        for (int half = 0; half < 2; ++half) {
+            const int co = half ? coB : coA;
+            if (vec_ok && co + 4 <= p.C_out) {
+                *reinterpret_cast<float4*>(row + co) = make_float4(o[4 * half], o[4 * half + 1], o[4 * half + 2], o[4 * half + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (co + j < p.C_out) row[co + j] = o[4 * half + j];
+            }
         }
     }
     if (p.partials) {

@@ -1,0 +1,308 @@
+// Implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM),
+// fp32-faithful through the 3xTF32 split (x = hi + lo, D += lo*hi + hi*lo + hi*hi).
+//
+// Same contract as conv_simt.cu (fused [GroupNorm apply + resblock add + ELU + reflect pad] on the input,
+// bias + raw store + GroupNorm partial statistics on the output), reference semantics
+// funcodec/modules/normed_modules/conv.py:243-261 / :281-305.
+//
+// GEMM view (channels-last makes both operands K-major):
+//     D[t (M = 128 time rows), co (N = n_tile)] = sum_{tap k} sum_{ci} X[t*S + k - pad_l][ci] * W[k][ci][co]
+//   * A (activations): one "unit" = (32-channel chunk, stride phase p): the rows {(t0+u)*S + p - pad_l}
+//     are transformed by 4 producer warps and written (hi and lo slabs) into the canonical SWIZZLE_128B
+//     K-major layout; every tap k = q*S + p of that phase is then just a ROW-SHIFTED view (start address
+//     + q*128 B, descriptor base_offset = q & 7) of the same slab -- no im2col copy, no re-transform.
+//   * B (weights): pre-split, pre-swizzled slab images in HBM (engine.cu pack_tc_weights), one
+//     cp.async.bulk (TMA engine, 1-D) per (chunk, tap) into a 3-stage ring, completion on an mbarrier.
+//   * warp roles: warps 0-3 producers, then epilogue (TMEM lane == time row; tcgen05.ld 32 columns at a
+//     time -> bias -> coalesced channels-last store -> statistics); warp 4 weight copies + TMEM alloc;
+//     warp 5 lane 0 issues tcgen05.mma and frees ring slots with tcgen05.commit.
+// Roofline: tensor pipe (3 MMAs per fp32-equivalent product) for C_in*K >= 128; HBM for the C <= 64 layers.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_sm100.cuh"
+
+namespace fcb {
+
+using namespace tc;
+
+constexpr int TC_M = 128;          // time rows per CTA
+constexpr int TC_KC = 32;          // channels per chunk (one 128-byte swizzle row)
+constexpr int TC_NA = 2;           // A ring depth
+constexpr int TC_THREADS = 192;
+
+struct TcSmemLayout {
+    int a_rows;        // rows per A slab (multiple of 8)
+    int a_stage;       // bytes per A stage (hi + lo)
+    int b_stage;       // bytes per B stage (hi + lo)
+    int nb;            // B ring depth
+    int off_b, off_coef, off_bar, total;
+};
+
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int C_in, int n_tile, bool has1, int nb) {
+    TcSmemLayout L;
+    const int qmax = (K - 1) / S;
+    L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
+    L.a_stage = 2 * L.a_rows * 128;
+    L.b_stage = 2 * n_tile * 128;
+    L.nb = nb;
+    L.off_b = TC_NA * L.a_stage;
+    L.off_coef = L.off_b + nb * L.b_stage;
+    L.off_bar = L.off_coef + C_in * 4 * (has1 ? 4 : 2);
+    L.off_bar = (L.off_bar + 15) & ~15;
+    L.total = L.off_bar + 8 * (2 * TC_NA + 2 * nb + 1) + 16;
+    return L;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int nb_stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * TC_M;
+    const int nt = blockIdx.y;
+    const int n_tile = p.n_tile;
+    const int C_in = p.C_in, K = p.K, S = p.S;
+    const bool has1 = p.in1.x != nullptr;
+    const TcSmemLayout L = tc_layout(K, S, C_in, n_tile, has1, nb_stages);
+    const int n_chunks = C_in / TC_KC;
+    const int n_units = n_chunks * S;
+
+    uint8_t* smA = smem_raw;
+    uint8_t* smB = smem_raw + L.off_b;
+    float* coefA0 = reinterpret_cast<float*>(smem_raw + L.off_coef);
+    float* coefB0 = coefA0 + C_in;
+    float* coefA1 = coefB0 + C_in;
+    float* coefB1 = coefA1 + (has1 ? C_in : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* a_full = bars;                       // [TC_NA]   128 producer arrivals
+    uint64_t* a_empty = a_full + TC_NA;            // [TC_NA]   tcgen05.commit
+    uint64_t* b_full = a_empty + TC_NA;            // [nb]      expect_tx
+    uint64_t* b_empty = b_full + nb_stages;        // [nb]      tcgen05.commit
+    uint64_t* acc_full = b_empty + nb_stages;      // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < n_tile) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < TC_NA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_ptr, tmem_cols);
+    // per-clip GroupNorm coefficients of the input view(s)
+    {
+        float mean0 = 0.f, rstd0 = 1.f, mean1 = 0.f, rstd1 = 1.f;
+        if (p.in0.stats) { mean0 = p.in0.stats[2 * b]; rstd0 = p.in0.stats[2 * b + 1]; }
+        if (has1 && p.in1.stats) { mean1 = p.in1.stats[2 * b]; rstd1 = p.in1.stats[2 * b + 1]; }
+        for (int c = tid; c < C_in; c += TC_THREADS) {
+            float a = 1.f, bb = 0.f;
+            if (p.in0.stats) { a = rstd0 * p.in0.gamma[c]; bb = p.in0.beta[c] - a * mean0; }
+            coefA0[c] = a; coefB0[c] = bb;
+            if (has1) {
+                a = 1.f; bb = 0.f;
+                if (p.in1.stats) { a = rstd1 * p.in1.gamma[c]; bb = p.in1.beta[c] - a * mean1; }
+                coefA1[c] = a; coefB1[c] = bb;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 4) {
+        // =========================================================== producers: transformed A slabs
+        const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
+        const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
+        const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
+        const int jchunk = tid & 7;                 // 16-byte chunk (4 channels) inside the 128-byte row
+        const int rsub = tid >> 3;                  // 16 rows per pass
+        for (int unit = 0; unit < n_units; ++unit) {
+            const int chunk = unit / S, ph = unit - chunk * S;
+            const int as = unit % TC_NA;
+            const uint32_t par = ((unit / TC_NA) & 1) ^ 1;
+            mbar_wait(a_empty + as, par);
+            uint8_t* hi = smA + as * L.a_stage;
+            uint8_t* lo = hi + L.a_rows * 128;
+            const int c = chunk * TC_KC + jchunk * 4;
+            const float4 a0 = *reinterpret_cast<const float4*>(coefA0 + c);
+            const float4 b0 = *reinterpret_cast<const float4*>(coefB0 + c);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+            if (has1) { a1 = *reinterpret_cast<const float4*>(coefA1 + c); b1 = *reinterpret_cast<const float4*>(coefB1 + c); }
+            for (int u = rsub; u < L.a_rows; u += 16) {
+                const int gt = (t0 + u) * S + ph - p.pad_l;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool ok = gt <= gt_max;
+                int src = gt;
+                if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
+                else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
+                if (ok) {
+                    const long long off = (long long)src * C_in + c;
+                    const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + off));
+                    v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
+                    v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
+                    if (has1) {
+                        const float4 yv = __ldg(reinterpret_cast<const float4*>(x1 + off));
+                        v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
+                        v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
+                    }
+                    if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                }
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
+                *reinterpret_cast<float4*>(hi + o) = h;
+                *reinterpret_cast<float4*>(lo + o) = l;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(a_full + as);
+        }
+        // =========================================================== epilogue: TMEM -> bias -> store + stats
+        mbar_wait(acc_full, 0);
+        tc_fence_after_sync();
+        const int t = t0 + warp * 32 + lane;
+        const bool row_ok = t < p.T_out;
+        float* orow = p.out + (long long)b * p.out_clip_stride + (long long)t * p.C_out + (long long)nt * n_tile;
+        const float* bias = p.bias + nt * n_tile;
+        float s = 0.f, ss = 0.f;
+        for (int c0 = 0; c0 < n_tile; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (c0 + j < n_tile) {       // n_tile is a multiple of 16
+                        float4 o;
+                        o.x = __uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0);
+                        o.y = __uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1);
+                        o.z = __uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2);
+                        o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
+                        s += (o.x + o.y) + (o.z + o.w);
+                        ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
+                        *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                    }
+                }
+            }
+        }
+        if (p.partials) {
+            // 4 epilogue warps: shuffle reduce then combine through shared memory (coef area is free now)
+            double ds = (double)s, dss = (double)ss;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                dss += __shfl_xor_sync(0xffffffffu, dss, o);
+            }
+            double* red = reinterpret_cast<double*>(smA);     // A slabs are dead (all MMAs committed)
+            if (lane == 0) { red[warp * 2] = ds; red[warp * 2 + 1] = dss; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) {
+                const int nparts = gridDim.x * gridDim.y;
+                double* dst = p.partials + ((long long)b * nparts + blockIdx.y * gridDim.x + blockIdx.x) * 2;
+                dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
+                dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
+            }
+        }
+        tc_fence_before_sync();
+    } else if (warp == 4) {
+        // =========================================================== weight slabs via the bulk-copy engine
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)L.b_stage;
+            const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)nt * n_chunks * K * bytes;
+            int it = 0;
+            for (int unit = 0; unit < n_units; ++unit) {
+                const int chunk = unit / S, ph = unit - chunk * S;
+                for (int k = ph; k < K; k += S, ++it) {
+                    const int bs = it % nb_stages;
+                    const uint32_t par = ((it / nb_stages) & 1) ^ 1;
+                    mbar_wait(b_empty + bs, par);
+                    mbar_arrive_expect_tx(b_full + bs, bytes);
+                    bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+                }
+            }
+        }
+        tc_fence_before_sync();
+    } else {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, n_tile);
+            const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
+            int it = 0;
+            uint32_t accum = 0;
+            for (int unit = 0; unit < n_units; ++unit) {
+                const int ph = unit % S;
+                const int as = unit % TC_NA;
+                mbar_wait(a_full + as, (unit / TC_NA) & 1);
+                tc_fence_after_sync();
+                const uint32_t a_hi0 = a_base + as * L.a_stage;
+                const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
+                int q = 0;
+                for (int k = ph; k < K; k += S, ++it, ++q) {
+                    const int bs = it % nb_stages;
+                    mbar_wait(b_full + bs, (it / nb_stages) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t b_hi0 = b_base + bs * L.b_stage;
+                    const uint32_t b_lo0 = b_hi0 + n_tile * 128;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
+                        const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
+                        const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
+                        const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
+                        mma_tf32_ss(tmem_base, da_lo, db_hi, idesc, accum);
+                        accum = 1;
+                        mma_tf32_ss(tmem_base, da_hi, db_lo, idesc, 1);
+                        mma_tf32_ss(tmem_base, da_hi, db_hi, idesc, 1);
+                    }
+                    mma_commit(b_empty + bs);
+                }
+                mma_commit(a_empty + as);
+            }
+            mma_commit(acc_full);
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D) {
+    return D == 1 && C_in % TC_KC == 0 && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 120;
+}
+
+int conv_tc_n_tile(int C_out_eff) {
+    if (C_out_eff >= 128 && C_out_eff % 128 == 0) return 128;
+    if (C_out_eff % 64 == 0) return 64;
+    if (C_out_eff % 32 == 0) return 32;
+    return 16;
+}
+
+int conv_tc_num_parts(int T_out, int C_out_eff) {
+    return ((T_out + TC_M - 1) / TC_M) * (C_out_eff / conv_tc_n_tile(C_out_eff));
+}
+
+cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
+    const bool has1 = p.in1.x != nullptr;
+    int nb = 3;
+    TcSmemLayout L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb);
+    if (L.total + 1024 > 225 * 1024) { nb = 2; L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb); }
+    if (L.total + 1024 > 225 * 1024) return cudaErrorInvalidConfiguration;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.T_out + TC_M - 1) / TC_M, p.C_out / p.n_tile, B);
+    *nparts = grid.x * grid.y;
+    conv1d_tc_kernel<<<grid, TC_THREADS, L.total, st>>>(p, nb);
+    return cudaGetLastError();
+}
+
+}  // namespace fcb

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -35,11 +36,14 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl
     float* bias = nullptr;   // [cout_eff]
     float* gamma = nullptr;  // [cout]
     float* beta = nullptr;   // [cout]
+    float* w_tc = nullptr;   // tensor-core image: [n_tile idx][chunk][tap][hi|lo][n_tile rows x 128 B swizzled]
+    int n_tile = 0;          // 0: no tensor-core image (layer runs on the SIMT kernel)
 };
 
 struct LstmW {
     int H = 0, layers = 0;
-    std::vector<float*> wih, whh, bias;   // packed [H][4H], [H][4H], [4H]
+    std::vector<ConvW> ih;                // input projections as 1x1 convs: [1][H][4H] + bias (b_ih + b_hh)
+    std::vector<float*> whh;              // packed [H][4H]
 };
 
 struct ResBlockW { ConvW c1, c2, sc; };
@@ -73,7 +77,10 @@ struct fcb_handle {
     float* embed = nullptr;   // [n_q][K][D]
     float* cnorm = nullptr;   // [n_q][K]
     int* err_flag = nullptr;
+    unsigned* lstm_barrier = nullptr;
+    bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     std::vector<void*> dev_allocs;
+    std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
 
     bool profiling = false;
     cudaEvent_t ev[FCB_NUM_PHASES + 1][2]{};
@@ -128,6 +135,39 @@ int need(fcb_handle* h, const std::string& name, std::vector<int64_t> shape, con
     return FCB_OK;
 }
 
+// Tensor-core weight image (conv_tc.cu): for every (n-tile, 32-channel chunk, tap) one hi slab and one lo
+// slab of [n_tile rows (output channels) x 32 tf32] in the canonical K-major SWIZZLE_128B layout, so that a
+// single 1-D bulk copy drops it into shared memory ready for tcgen05.mma.  hi/lo = 3xTF32 split.
+int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, ConvW* o) {
+    o->n_tile = 0;
+    if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, 1)) return FCB_OK;
+    const int n_tile = conv_tc_n_tile(cout_eff);
+    const int n_chunks = cin / 32, n_nt = cout_eff / n_tile;
+    const size_t slab = (size_t)n_tile * 32;                 // floats per hi (or lo) slab
+    std::vector<float> img((size_t)n_nt * n_chunks * K * 2 * slab);
+    for (int nt = 0; nt < n_nt; ++nt)
+        for (int c = 0; c < n_chunks; ++c)
+            for (int k = 0; k < K; ++k) {
+                float* hi = img.data() + (((size_t)nt * n_chunks + c) * K + k) * 2 * slab;
+                float* lo = hi + slab;
+                for (int n = 0; n < n_tile; ++n)
+                    for (int col = 0; col < 32; ++col) {
+                        const float x = wp[((size_t)k * cin + c * 32 + col) * cout_eff + nt * n_tile + n];
+                        uint32_t u;
+                        memcpy(&u, &x, 4);
+                        u = (u + 0x1000u) & 0xFFFFE000u;
+                        float xh;
+                        memcpy(&xh, &u, 4);
+                        const size_t off = (size_t)n * 32 + ((((col >> 2) ^ (n & 7)) << 2) | (col & 3));
+                        hi[off] = xh;
+                        lo[off] = x - xh;
+                    }
+            }
+    FCB_TRY(upload(h, img, &o->w_tc));
+    o->n_tile = n_tile;
+    return FCB_OK;
+}
+
 // SConv1d: conv.conv.weight [cout][cin][k] -> [k][cin][cout]
 int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k, int s, ConvW* o) {
     const HostTensor *w, *b, *g, *be;
@@ -141,6 +181,7 @@ int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k
             for (int kk = 0; kk < k; ++kk)
                 p[((size_t)kk * cin + ci) * cout + co] = w->data[((size_t)co * cin + ci) * k + kk];
     o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->transposed = false;
+    FCB_TRY(pack_tc(h, p, k, cin, cout, o));
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, b->data, &o->bias));
     FCB_TRY(upload(h, g->data, &o->gamma));
@@ -170,6 +211,7 @@ int pack_convtr(fcb_handle* h, const std::string& prefix, int cin, int cout, int
     for (int ph = 0; ph < s; ++ph)
         for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
     o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->transposed = true;
+    FCB_TRY(pack_tc(h, p, 2, cin, ce, o));
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, bias, &o->bias));
     FCB_TRY(upload(h, g->data, &o->gamma));
@@ -198,11 +240,14 @@ int pack_lstm(fcb_handle* h, const std::string& prefix, int H, int layers, LstmW
                 }
                 pb[col] = bih->data[row] + bhh->data[row];
             }
-        float *dwi, *dwh, *db;
-        FCB_TRY(upload(h, pi, &dwi));
+        ConvW ih;
+        ih.cin = H; ih.cout = 4 * H; ih.k = 1; ih.s = 1;
+        FCB_TRY(pack_tc(h, pi, 1, H, 4 * H, &ih));
+        FCB_TRY(upload(h, pi, &ih.w));
+        FCB_TRY(upload(h, pb, &ih.bias));
+        float* dwh;
         FCB_TRY(upload(h, ph, &dwh));
-        FCB_TRY(upload(h, pb, &db));
-        o->wih.push_back(dwi); o->whh.push_back(dwh); o->bias.push_back(db);
+        o->ih.push_back(ih); o->whh.push_back(dwh);
     }
     return FCB_OK;
 }
@@ -261,10 +306,11 @@ InView view_of(const Act& a) {
     return v;
 }
 
-// One SConv1d / SConvTranspose1d.  in1 may be null.  want_norm=false -> plain output (LSTM input projection).
+// One SConv1d / SConvTranspose1d / 1x1 GEMM.  in1 may be null.  want_norm=false -> plain output (LSTM input
+// projection).  Dispatch: tensor-core implicit GEMM (conv_tc.cu) when the layer has a TC weight image and the
+// input needs no division prologue, else the fp32 SIMT kernel (conv_simt.cu).
 int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_scale, const ConvW& L,
-             bool want_norm, Act* out, const float* w_override = nullptr, const float* bias_override = nullptr,
-             int cout_override = 0) {
+             bool want_norm, Act* out) {
     fcb_handle* h = r.h;
     ConvParams p{};
     p.in0 = view_of(in0);
@@ -272,11 +318,10 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     p.div_scale = div_scale;
     p.elu = elu ? 1 : 0;
     p.T_in = in0.T; p.C_in = in0.C;
-    if (in0.C != L.cin && !w_override) return fail(h, FCB_E_INVALID, "internal: channel mismatch");
+    if (in0.C != L.cin) return fail(h, FCB_E_INVALID, "internal: channel mismatch");
     Act o;
-    if (!L.transposed || w_override) {
-        const int k = w_override ? 1 : L.k, s = w_override ? 1 : L.s, d = 1;
-        const int cout = w_override ? cout_override : L.cout;
+    if (!L.transposed) {
+        const int k = L.k, s = L.s, d = 1;
         const int padding_total = (k - 1) * d - (s - 1);
         // get_extra_padding_for_conv1d (conv.py:57-64), integer form of ceil((T - k + pt)/s)
         const int num = in0.T - k + padding_total;
@@ -289,26 +334,25 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         p.K = k; p.S = s; p.D = d; p.pad_l = pl; p.pad_zero = 0;
         p.T_ext = in0.T <= max_pad ? max_pad + 1 : in0.T;     // pad1d tiny-input branch (conv.py:89-97)
         p.T_out = (in0.T + pl + pr_tot - k) / s + 1;
-        p.C_out = cout;
-        p.w = w_override ? w_override : L.w;
-        p.bias = bias_override ? bias_override : L.bias;
-        o.T = p.T_out; o.C = cout; o.clip_stride = (long long)p.T_out * cout; o.row_off = 0;
+        p.C_out = L.cout;
+        o.T = p.T_out; o.C = L.cout; o.clip_stride = (long long)p.T_out * L.cout; o.row_off = 0;
     } else {
         const int s = L.s;
         p.K = 2; p.S = 1; p.D = 1; p.pad_l = 1; p.pad_zero = 1; p.T_ext = in0.T;
         p.T_out = in0.T + 1;
         p.C_out = s * L.cout;
-        p.w = L.w; p.bias = L.bias;
         const int padding_total = L.k - s;                    // conv.py:283-303
         const int pr = padding_total / 2, pl = padding_total - pr;
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
+    p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
+    const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
     o.owned = true;
     p.out = o.p;
     double* partials = nullptr;
-    int nparts = conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B);
+    const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B);
     if (want_norm) {
         FCB_CK(cudaMallocAsync((void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double), r.st));
         FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
@@ -316,7 +360,8 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     }
     p.partials = partials;
     int np2 = 0;
-    FCB_CK(launch_conv(p, r.B, r.st, &np2));
+    if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
+    else FCB_CK(launch_conv(p, r.B, r.st, &np2));
     h->launches++;
     if (want_norm) {
         if (np2 != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch");
@@ -333,16 +378,13 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
     fcb_handle* h = r.h;
     const int H = W.H, T = x.T, B = r.B;
     if (x.C != H) return fail(h, FCB_E_INVALID, "internal: lstm width mismatch");
-    float* c_state = nullptr;
-    FCB_TRY(alloc_f(r, &c_state, (size_t)B * H));
+    if (lstm_pick_units(H) == 0) return fail(h, FCB_E_INVALID, "lstm width not supported (needs H % 4 == 0 and the W_hh slice to fit shared memory)");
     Act cur = x;       // not owned copy semantics: only release what we allocate
     cur.owned = false;
     Act y;
     for (int l = 0; l < W.layers; ++l) {
         Act gx;
-        ConvW dummy;
-        dummy.cin = H;
-        FCB_TRY(run_conv(r, cur, nullptr, false, nullptr, dummy, false, &gx, W.wih[l], W.bias[l], 4 * H));
+        FCB_TRY(run_conv(r, cur, nullptr, false, nullptr, W.ih[l], false, &gx));
         Act hs;
         FCB_TRY(alloc_f(r, &hs.p, (size_t)B * T * H));
         hs.owned = true; hs.T = T; hs.C = H; hs.clip_stride = (long long)T * H;
@@ -351,22 +393,19 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
             FCB_TRY(alloc_f(r, &y.p, (size_t)B * T * H));
             y.owned = true; y.T = T; y.C = H; y.clip_stride = (long long)T * H;
         }
-        LstmStepParams sp{};
-        sp.gx = gx.p; sp.whh = W.whh[l]; sp.h_seq = hs.p; sp.c_state = c_state;
+        LstmSeqParams sp{};
+        sp.gx = gx.p; sp.whh = W.whh[l]; sp.h_seq = hs.p;
         sp.y_out = last ? y.p : nullptr;
         sp.skip = view_of(x);
+        sp.barrier = h->lstm_barrier;
         sp.B = B; sp.T = T; sp.H = H;
-        for (int t = 0; t < T; ++t) {
-            sp.t = t;
-            FCB_CK(launch_lstm_step(sp, r.st));
-        }
-        h->launches += T;
+        FCB_CK(launch_lstm_seq(sp, r.st));
+        h->launches += 1;
         FCB_TRY(release(r, gx));
         if (l > 0) FCB_TRY(release(r, cur));
         cur = hs;
     }
     FCB_TRY(release(r, cur));
-    FCB_CK(cudaFreeAsync(c_state, r.st));
     *out = y;
     return FCB_OK;
 }
@@ -521,6 +560,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     fcb_handle* h = new (std::nothrow) fcb_handle();
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
+    { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
     cudaMemPool_t pool;
@@ -592,10 +632,39 @@ int fcb_finalize(fcb_handle* h) {
     FCB_CK(cudaMalloc((void**)&h->err_flag, sizeof(int)));
     h->dev_allocs.push_back(h->err_flag);
     FCB_CK(cudaMemset(h->err_flag, 0, sizeof(int)));
+    FCB_CK(cudaMalloc((void**)&h->lstm_barrier, sizeof(unsigned)));
+    h->dev_allocs.push_back(h->lstm_barrier);
     FCB_CK(launch_code_norms(h->embed, h->cnorm, c.num_quantizers * c.codebook_size, D, 0));
     h->launches++;
     FCB_CK(cudaDeviceSynchronize());
     h->host.clear();
+    {   // name map for fcb_debug_conv1d (vectors are final now: pointers stay valid)
+        const fcb_config& cc = h->cfg;
+        h->by_name["encoder.model.0"] = &h->enc_conv0;
+        int nn = 1;
+        for (size_t i = 0; i < h->enc_rb.size(); ++i, nn += 3) {
+            const std::string pre = "encoder.model." + std::to_string(nn);
+            h->by_name[pre + ".block.1"] = &h->enc_rb[i].c1;
+            h->by_name[pre + ".block.3"] = &h->enc_rb[i].c2;
+            h->by_name[pre + ".shortcut"] = &h->enc_rb[i].sc;
+            h->by_name["encoder.model." + std::to_string(nn + 2)] = &h->enc_down[i];
+        }
+        if (cc.lstm_layers > 0) {
+            for (int l = 0; l < cc.lstm_layers; ++l) h->by_name["encoder.model." + std::to_string(nn) + ".lstm.ih" + std::to_string(l)] = &h->enc_lstm.ih[l];
+            nn += 1;
+        }
+        h->by_name["encoder.model." + std::to_string(nn + 1)] = &h->enc_final;
+        h->by_name["decoder.model.0"] = &h->dec_conv0;
+        nn = cc.lstm_layers > 0 ? 2 : 1;
+        for (size_t i = 0; i < h->dec_up.size(); ++i, nn += 3) {
+            h->by_name["decoder.model." + std::to_string(nn + 1)] = &h->dec_up[i];
+            const std::string pre = "decoder.model." + std::to_string(nn + 2);
+            h->by_name[pre + ".block.1"] = &h->dec_rb[i].c1;
+            h->by_name[pre + ".block.3"] = &h->dec_rb[i].c2;
+            h->by_name[pre + ".shortcut"] = &h->dec_rb[i].sc;
+        }
+        h->by_name["decoder.model." + std::to_string(nn + 1)] = &h->dec_final;
+    }
     h->finalized = true;
     return FCB_OK;
 }
@@ -700,6 +769,40 @@ int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t 
 }
 
 int64_t fcb_launch_count(const fcb_handle* h) { return h ? h->launches : -1; }
+
+int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
+    if (!h || !key) return FCB_E_INVALID;
+    if (strcmp(key, "use_tc") == 0) {
+        if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
+        h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    return fail(h, FCB_E_INVALID, std::string("unknown option: ") + key);
+}
+
+int fcb_debug_conv1d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t T, int32_t elu,
+                     float* y, int64_t y_capacity, float* stats, int32_t* t_out, int32_t* c_out, int32_t* row_off,
+                     void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!layer || !x || !y || !t_out || !c_out || !row_off) return fail(h, FCB_E_INVALID, "fcb_debug_conv1d: bad arguments");
+    const ConvW* L = nullptr;
+    std::string n(layer);
+    auto it = h->by_name.find(n);
+    if (it == h->by_name.end()) return fail(h, FCB_E_INVALID, "fcb_debug_conv1d: unknown layer " + n);
+    L = it->second;
+    Run r{h, B, (cudaStream_t)stream};
+    Act in;
+    in.p = const_cast<float*>(x); in.T = T; in.C = L->cin; in.clip_stride = (long long)T * L->cin;
+    Act o;
+    FCB_TRY(run_conv(r, in, nullptr, elu != 0, nullptr, *L, stats != nullptr, &o));
+    const long long rows = o.clip_stride / o.C;
+    if ((long long)B * o.clip_stride > y_capacity) { release(r, o); return fail(h, FCB_E_INVALID, "fcb_debug_conv1d: y too small"); }
+    FCB_CK(cudaMemcpyAsync(y, o.p, (size_t)B * o.clip_stride * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+    if (stats) FCB_CK(cudaMemcpyAsync(stats, o.stats, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+    *t_out = (int32_t)rows; *c_out = o.C; *row_off = o.row_off;
+    FCB_TRY(release(r, o));
+    return FCB_OK;
+}
 
 int fcb_set_profiling(fcb_handle* h, int32_t enabled) {
     if (!h) return FCB_E_INVALID;

@@ -15,17 +15,24 @@ cudaError_t launch_stats_finalize(const double* partials, int nparts, double cou
 int sumsq_num_parts(int L);
 cudaError_t launch_sumsq_partials(const float* x, int B, int L, double* partials, int* nparts, cudaStream_t st);
 
+// conv_tc.cu
+bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D);
+int conv_tc_n_tile(int C_out_eff);
+int conv_tc_num_parts(int T_out, int C_out_eff);
+cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts);
+
 // lstm.cu
-struct LstmStepParams {
+struct LstmSeqParams {
     const float* gx;      // [B][T][4H] input projection incl. both biases, columns packed unit-major (n' = 4*j + gate)
     const float* whh;     // [H][4H] packed W_hh^T, same column order
-    float* h_seq;         // [B][T][H] hidden states of this layer (row t written at step t)
-    float* c_state;       // [B][H]
+    float* h_seq;         // [B][T][H] hidden states of this layer
     float* y_out;         // nullptr, or [B][T][H]: y = h + skip   (SLSTM skip, lstm.py:25-26)
     InView skip;          // the SLSTM input (normalised on load) when y_out != nullptr
-    int B, T, H, t;
+    unsigned* barrier;    // device counter for the per-step grid barrier (zeroed by the launcher)
+    int B, T, H;
 };
-cudaError_t launch_lstm_step(const LstmStepParams& p, cudaStream_t st);
+cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st);
+int lstm_pick_units(int H);
 
 // rvq.cu
 struct RvqParams {

@@ -37,7 +37,8 @@ def _ptr(t: Optional[torch.Tensor]):
 class B200Encodec:
     """Inference-only stand-in for funcodec.models.codec_basic.Encodec backed by the CUDA library."""
 
-    def __init__(self, cfg: CodecConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0"):
+    def __init__(self, cfg: CodecConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
+                 options: Optional[Dict[str, int]] = None):
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -59,6 +60,9 @@ class B200Encodec:
             rc = self._lib.fcb_create(ctypes.byref(c), ctypes.byref(self._h))
             if rc != 0:
                 raise _capi.FcbError(f"fcb_create failed (rc={rc})")
+            for key, val in (options or {}).items():
+                _capi.check(self._lib, self._h, self._lib.fcb_set_option(self._h, key.encode(), int(val)),
+                            f"fcb_set_option({key})")
             for name, t in state_dict.items():
                 if not t.is_floating_point():
                     continue
@@ -101,6 +105,22 @@ class B200Encodec:
         arr = (ctypes.c_float * _capi.FCB_NUM_PHASES)()
         self._ck(self._lib.fcb_get_phase_ms(self._h, arr), "fcb_get_phase_ms")
         return {n: float(arr[i]) for i, n in enumerate(_capi.PHASE_NAMES)}
+
+    def debug_conv(self, layer: str, x_btc: torch.Tensor, elu: bool = False, want_stats: bool = True):
+        """fcb_debug_conv1d test hook: one packed layer on a plain channels-last input -> (raw y [B,t_out,c_out],
+        stats [B,2] | None, row_off)."""
+        x = x_btc.to(self.device, torch.float32).contiguous()
+        B, T, _ = x.shape
+        cap = B * (T + 2) * 8192
+        y = torch.empty(cap, dtype=torch.float32, device=self.device)
+        stats = torch.empty((B, 2), dtype=torch.float32, device=self.device) if want_stats else None
+        t_out, c_out, row_off = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            self._ck(self._lib.fcb_debug_conv1d(self._h, layer.encode(), _ptr(x), B, T, int(elu), _ptr(y), cap, _ptr(stats),
+                                                ctypes.byref(t_out), ctypes.byref(c_out), ctypes.byref(row_off),
+                                                self._stream()), f"fcb_debug_conv1d({layer})")
+        n = B * t_out.value * c_out.value
+        return y[:n].view(B, t_out.value, c_out.value), stats, row_off.value
 
     def _prep_speech(self, speech: torch.Tensor) -> torch.Tensor:
         if speech.dim() == 3:

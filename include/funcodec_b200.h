@@ -136,6 +136,19 @@ FCB_API int fcb_set_profiling(fcb_handle* h, int32_t enabled);
 /* Milliseconds spent per phase in the most recent call (synchronises the recorded events). */
 FCB_API int fcb_get_phase_ms(fcb_handle* h, float* ms_out /* [FCB_NUM_PHASES] */);
 
+/* Options (integer valued): "use_tc" 1/0 -- tensor-core (tcgen05) conv path vs fp32 SIMT path; must be set
+ * before fcb_finalize to enable, may be cleared at any time.  Env FCB_DISABLE_TC=1 sets the default to 0. */
+FCB_API int fcb_set_option(fcb_handle* h, const char* key, int32_t value);
+
+/* TEST HOOK (tests/test_gpu_layers.py): run ONE packed conv layer, addressed by its reference module prefix
+ * ("encoder.model.3", "decoder.model.3", "encoder.model.1.block.1", "encoder.model.16.lstm.ih0", ...), on a plain
+ * channels-last input x dev [B][T][C_in] (optional ELU on load).  y dev receives the RAW output (bias added,
+ * GroupNorm not applied) as [B][t_out][c_out] where for a transposed conv t_out is the UNtrimmed length and
+ * row_off the first kept row (conv.py:299-303); stats dev [B][2] = (mean, rstd) of the layer's GroupNorm or NULL. */
+FCB_API int fcb_debug_conv1d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t T, int32_t elu,
+                             float* y, int64_t y_capacity, float* stats, int32_t* t_out, int32_t* c_out,
+                             int32_t* row_off, void* stream);
+
 FCB_API const char* fcb_last_error(const fcb_handle* h);
 FCB_API void fcb_destroy(fcb_handle* h);
 
