@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     const uint32_t b_lo0 = b_hi0 + n_tile * 128;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
-                        const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
+                        const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32, p.dbg_mode);
+                        const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32, p.dbg_mode);
                         const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
                         const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
                         mma_tf32_ss(tmem_base, da_lo, db_hi, idesc, accum);

@@ -95,13 +95,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // 1024 bytes apart (SBO), 16-byte chunk index XOR (row & 7).  `addr` = shared address of row 0 (+ k*32 bytes to
 // step along K inside the 128-byte row).  When the row-0 address is not 1024-byte aligned (tap-shifted views
 // of an activation slab) base_offset = (addr >> 7) & 7 keeps the swizzle phase (PTX matrix-descriptor table).
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t addr) {
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t addr, int base_offset_mode = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);            // [0,14)  start address >> 4
     d |= (uint64_t)1 << 16;                              // [16,30) leading byte offset (unused for swizzled K-major) = 1
     d |= (uint64_t)(1024 >> 4) << 32;                    // [32,46) stride byte offset = 1024 B between 8-row groups
     d |= (uint64_t)1 << 46;                              // [46,48) descriptor version = 1 (sm_100)
-    d |= (uint64_t)((addr >> 7) & 7) << 49;              // [49,52) base offset
+    if (base_offset_mode == 0) d |= (uint64_t)((addr >> 7) & 7) << 49;   // [49,52) base offset
     d |= (uint64_t)2 << 61;                              // [61,64) layout type: SWIZZLE_128B
     return d;
 }
