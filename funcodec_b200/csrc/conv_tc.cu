@@ -28,7 +28,8 @@ using namespace tc;
 constexpr int TC_M = 128;          // time rows per CTA
 constexpr int TC_KC = 32;          // channels per chunk (one 128-byte swizzle row)
 constexpr int TC_NA = 2;           // A ring depth
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;    // 4 producer warps, 1 copy warp, 1 MMA warp, 4 accumulator/epilogue warps
+constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TMEM before the fp32 fold
 
 struct TcSmemLayout {
     int a_rows;        // rows per A slab (multiple of 8)
@@ -49,22 +50,37 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int C_in, int n_
     L.off_coef = L.off_b + nb * L.b_stage;
     L.off_bar = L.off_coef + C_in * 4 * (has1 ? 4 : 2);
     L.off_bar = (L.off_bar + 15) & ~15;
-    L.total = L.off_bar + 8 * (2 * TC_NA + 2 * nb + 1) + 16;
+    L.total = L.off_bar + 8 * (2 * TC_NA + 2 * nb + 4) + 16;
     return L;
 }
 
+// units (chunk, phase) chained in one TMEM accumulation group
+__host__ __device__ inline int tc_units_per_group(int K, int S) {
+    const int taps = (K + S - 1) / S;                  // max taps of a phase
+    int g = TC_GROUP_MMAS / (12 * taps);
+    return g < 1 ? 1 : g;
+}
+
+// The tensor core adds into its fp32 accumulator with truncation, so the error of a TMEM-resident chain grows
+// linearly with the number of chained MMAs (measured: ~5e-5 relative after 384 MMAs).  Chains are therefore cut
+// every ~48 MMAs: the MMA warp ping-pongs between two TMEM accumulators and the accumulator warps fold each
+// finished group into fp32 registers with round-to-nearest adds.
+template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int nb_stages) {
+    constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator buffer
+    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                 // power of two >= 64
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int t0 = blockIdx.x * TC_M;
     const int nt = blockIdx.y;
-    const int n_tile = p.n_tile;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, C_in, n_tile, has1, nb_stages);
+    const TcSmemLayout L = tc_layout(K, S, C_in, N_TILE, has1, nb_stages);
     const int n_chunks = C_in / TC_KC;
     const int n_units = n_chunks * S;
+    const int upg = tc_units_per_group(K, S);
+    const int n_groups = (n_units + upg - 1) / upg;
 
     uint8_t* smA = smem_raw;
     uint8_t* smB = smem_raw + L.off_b;
@@ -77,19 +93,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     uint64_t* a_empty = a_full + TC_NA;            // [TC_NA]   tcgen05.commit
     uint64_t* b_full = a_empty + TC_NA;            // [nb]      expect_tx
     uint64_t* b_empty = b_full + nb_stages;        // [nb]      tcgen05.commit
-    uint64_t* acc_full = b_empty + nb_stages;      // [1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < n_tile) tmem_cols <<= 1;
+    uint64_t* acc_full = b_empty + nb_stages;      // [2]       tcgen05.commit
+    uint64_t* acc_empty = acc_full + 2;            // [2]       128 accumulator-warp arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     if (tid == 0) {
         for (int i = 0; i < TC_NA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, tmem_cols);
+    if (warp == 4) tmem_alloc(tmem_ptr, TMEM_COLS);
     // per-clip GroupNorm coefficients of the input view(s)
     {
         float mean0 = 0.f, rstd0 = 1.f, mean1 = 0.f, rstd1 = 1.f;
@@ -159,53 +173,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             fence_proxy_async_smem();
             mbar_arrive(a_full + as);
         }
-        // =========================================================== epilogue: TMEM -> bias -> store + stats
-        mbar_wait(acc_full, 0);
-        tc_fence_after_sync();
-        const int t = t0 + warp * 32 + lane;
-        const bool row_ok = t < p.T_out;
-        float* orow = p.out + (long long)b * p.out_clip_stride + (long long)t * p.C_out + (long long)nt * n_tile;
-        const float* bias = p.bias + nt * n_tile;
-        float s = 0.f, ss = 0.f;
-        for (int c0 = 0; c0 < n_tile; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (c0 + j < n_tile) {       // n_tile is a multiple of 16
-                        float4 o;
-                        o.x = __uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0);
-                        o.y = __uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1);
-                        o.z = __uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2);
-                        o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
-                        s += (o.x + o.y) + (o.z + o.w);
-                        ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
-                        *reinterpret_cast<float4*>(orow + c0 + j) = o;
-                    }
-                }
-            }
-        }
-        if (p.partials) {
-            // 4 epilogue warps: shuffle reduce then combine through shared memory (coef area is free now)
-            double ds = (double)s, dss = (double)ss;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ds += __shfl_xor_sync(0xffffffffu, ds, o);
-                dss += __shfl_xor_sync(0xffffffffu, dss, o);
-            }
-            double* red = reinterpret_cast<double*>(smA);     // A slabs are dead (all MMAs committed)
-            if (lane == 0) { red[warp * 2] = ds; red[warp * 2 + 1] = dss; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0) {
-                const int nparts = gridDim.x * gridDim.y;
-                double* dst = p.partials + ((long long)b * nparts + blockIdx.y * gridDim.x + blockIdx.x) * 2;
-                dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
-                dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
-            }
-        }
-        tc_fence_before_sync();
     } else if (warp == 4) {
         // =========================================================== weight slabs via the bulk-copy engine
         if (lane == 0) {
@@ -223,51 +190,116 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
             }
         }
-        tc_fence_before_sync();
-    } else {
+    } else if (warp == 5) {
         // =========================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, n_tile);
+            const uint32_t idesc = make_idesc_tf32(TC_M, N_TILE);
             const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
             int it = 0;
-            uint32_t accum = 0;
-            for (int unit = 0; unit < n_units; ++unit) {
-                const int ph = unit % S;
-                const int as = unit % TC_NA;
-                mbar_wait(a_full + as, (unit / TC_NA) & 1);
+            for (int g = 0; g < n_groups; ++g) {
+                const int buf = g & 1;
+                mbar_wait(acc_empty + buf, ((g >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
-                const uint32_t a_hi0 = a_base + as * L.a_stage;
-                const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
-                int q = 0;
-                for (int k = ph; k < K; k += S, ++it, ++q) {
-                    const int bs = it % nb_stages;
-                    mbar_wait(b_full + bs, (it / nb_stages) & 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BUF_COLS);
+                uint32_t accum = 0;
+                const int u_end = min(n_units, (g + 1) * upg);
+                for (int unit = g * upg; unit < u_end; ++unit) {
+                    const int ph = unit % S;
+                    const int as = unit % TC_NA;
+                    mbar_wait(a_full + as, (unit / TC_NA) & 1);
                     tc_fence_after_sync();
-                    const uint32_t b_hi0 = b_base + bs * L.b_stage;
-                    const uint32_t b_lo0 = b_hi0 + n_tile * 128;
+                    const uint32_t a_hi0 = a_base + as * L.a_stage;
+                    const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
+                    int q = 0;
+                    for (int k = ph; k < K; k += S, ++it, ++q) {
+                        const int bs = it % nb_stages;
+                        mbar_wait(b_full + bs, (it / nb_stages) & 1);
+                        tc_fence_after_sync();
+                        const uint32_t b_hi0 = b_base + bs * L.b_stage;
+                        const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32, p.dbg_mode);
-                        const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32, p.dbg_mode);
-                        const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
-                        const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
-                        mma_tf32_ss(tmem_base, da_lo, db_hi, idesc, accum);
-                        accum = 1;
-                        mma_tf32_ss(tmem_base, da_hi, db_lo, idesc, 1);
-                        mma_tf32_ss(tmem_base, da_hi, db_hi, idesc, 1);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32, p.dbg_mode);
+                            const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32, p.dbg_mode);
+                            const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
+                            const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
+                            mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, accum);
+                            accum = 1;
+                            mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
+                            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
+                        }
+                        mma_commit(b_empty + bs);
                     }
-                    mma_commit(b_empty + bs);
+                    mma_commit(a_empty + as);
                 }
-                mma_commit(a_empty + as);
+                mma_commit(acc_full + buf);
             }
-            mma_commit(acc_full);
         }
-        tc_fence_before_sync();
+    } else {
+        // =========================================================== accumulator warps: fold groups, then epilogue
+        const int ew = warp - 6;                       // TMEM lanes [32*ew, 32*ew + 32): warp id % 4 == ew + 2 ... see note
+        float tot[N_TILE];
+#pragma unroll
+        for (int j = 0; j < N_TILE; ++j) tot[j] = 0.f;
+        const uint32_t lane_base = (uint32_t)(((warp & 3) * 32)) << 16;   // a warp may only touch lanes 32*(warp%4)..+31
+        for (int g = 0; g < n_groups; ++g) {
+            const int buf = g & 1;
+            mbar_wait(acc_full + buf, (g >> 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + (uint32_t)(buf * BUF_COLS + c0), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < N_TILE) tot[c0 + j] += __uint_as_float(v[j]);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(acc_empty + buf);
+        }
+        (void)ew;
+        const int t = t0 + (warp & 3) * 32 + lane;
+        const bool row_ok = t < p.T_out;
+        float* orow = p.out + (long long)b * p.out_clip_stride + (long long)t * p.C_out + (long long)nt * N_TILE;
+        const float* bias = p.bias + nt * N_TILE;
+        float s = 0.f, ss = 0.f;
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < N_TILE; j += 4) {
+                float4 o;
+                o.x = tot[j + 0] + __ldg(bias + j + 0);
+                o.y = tot[j + 1] + __ldg(bias + j + 1);
+                o.z = tot[j + 2] + __ldg(bias + j + 2);
+                o.w = tot[j + 3] + __ldg(bias + j + 3);
+                s += (o.x + o.y) + (o.z + o.w);
+                ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
+                *reinterpret_cast<float4*>(orow + j) = o;
+            }
+        }
+        if (p.partials) {
+            double ds = (double)s, dss = (double)ss;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                dss += __shfl_xor_sync(0xffffffffu, dss, o);
+            }
+            double* red = reinterpret_cast<double*>(smA);     // A slabs are dead (all MMAs committed)
+            if (lane == 0) { red[(warp - 6) * 2] = ds; red[(warp - 6) * 2 + 1] = dss; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 6 * 32) {
+                const int nparts = gridDim.x * gridDim.y;
+                double* dst = p.partials + ((long long)b * nparts + blockIdx.y * gridDim.x + blockIdx.x) * 2;
+                dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
+                dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
+            }
+        }
     }
+    tc_fence_before_sync();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, tmem_cols);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -287,22 +319,34 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
     return ((T_out + TC_M - 1) / TC_M) * (C_out_eff / conv_tc_n_tile(C_out_eff));
 }
 
+template <int N_TILE>
+static cudaError_t launch_tc_n(const ConvParams& p, int B, cudaStream_t st, int nb, int smem, dim3 grid) {
+    auto kern = conv1d_tc_kernel<N_TILE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    kern<<<grid, TC_THREADS, smem, st>>>(p, nb);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
     const bool has1 = p.in1.x != nullptr;
     int nb = 3;
     TcSmemLayout L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb);
-    if (L.total + 1024 > 225 * 1024) { nb = 2; L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb); }
-    if (L.total + 1024 > 225 * 1024) return cudaErrorInvalidConfiguration;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    if (L.total > 225 * 1024) { nb = 2; L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb); }
+    if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
     dim3 grid((p.T_out + TC_M - 1) / TC_M, p.C_out / p.n_tile, B);
     *nparts = grid.x * grid.y;
-    conv1d_tc_kernel<<<grid, TC_THREADS, L.total, st>>>(p, nb);
-    return cudaGetLastError();
+    switch (p.n_tile) {
+        case 16: return launch_tc_n<16>(p, B, st, nb, L.total, grid);
+        case 32: return launch_tc_n<32>(p, B, st, nb, L.total, grid);
+        case 64: return launch_tc_n<64>(p, B, st, nb, L.total, grid);
+        case 128: return launch_tc_n<128>(p, B, st, nb, L.total, grid);
+        default: return cudaErrorInvalidConfiguration;
+    }
 }
 
 }  // namespace fcb

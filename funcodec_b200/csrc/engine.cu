@@ -562,6 +562,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
+    { const char* e = getenv("FCB_TC_DBG_MODE"); if (e) h->tc_dbg_mode = atoi(e); }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
     cudaMemPool_t pool;
