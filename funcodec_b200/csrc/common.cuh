@@ -41,7 +41,6 @@ struct ConvParams {
     long long out_clip_stride;
     double* partials;        // [B][n_parts][2] (sum, sum of squares) or nullptr
     int cic;                 // input-channel chunk staged per iteration
-    int dbg_mode;            // debug: tensor-core descriptor variant (0 = spec'd base_offset)
 };
 
 __device__ __forceinline__ float elu1(float v) {

@@ -10,7 +10,7 @@
 //   * A (activations): one "unit" = (32-channel chunk, stride phase p): the rows {(t0+u)*S + p - pad_l}
 //     are transformed by 4 producer warps and written (hi and lo slabs) into the canonical SWIZZLE_128B
 //     K-major layout; every tap k = q*S + p of that phase is then just a ROW-SHIFTED view (start address
-//     + q*128 B, descriptor base_offset = q & 7) of the same slab -- no im2col copy, no re-transform.
+//     + q*128 B; the hardware swizzle works on absolute address bits) of the same slab -- no im2col copy.
 //   * B (weights): pre-split, pre-swizzled slab images in HBM (engine.cu pack_tc_weights), one
 //     cp.async.bulk (TMA engine, 1-D) per (chunk, tap) into a 3-stage ring, completion on an mbarrier.
 //   * warp roles: warps 0-3 producers, then epilogue (TMEM lane == time row; tcgen05.ld 32 columns at a
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32, p.dbg_mode);
-                            const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32, p.dbg_mode);
+                            const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
+                            const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
                             const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
                             const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
                             mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, accum);

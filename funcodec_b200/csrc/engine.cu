@@ -78,7 +78,6 @@ struct fcb_handle {
     float* cnorm = nullptr;   // [n_q][K]
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
-    int tc_dbg_mode = 0;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
@@ -346,7 +345,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         const int pr = padding_total / 2, pl = padding_total - pr;
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
-    p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.dbg_mode = h->tc_dbg_mode;
+    p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
@@ -562,7 +561,6 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
-    { const char* e = getenv("FCB_TC_DBG_MODE"); if (e) h->tc_dbg_mode = atoi(e); }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
     cudaMemPool_t pool;
@@ -779,7 +777,6 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
         h->use_tc = value != 0;
         return FCB_OK;
     }
-    if (strcmp(key, "tc_dbg_mode") == 0) { h->tc_dbg_mode = value; return FCB_OK; }
     return fail(h, FCB_E_INVALID, std::string("unknown option: ") + key);
 }
 

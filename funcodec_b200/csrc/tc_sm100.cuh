@@ -93,15 +93,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------------ descriptors
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 bytes (32 tf32), 8-row groups
 // 1024 bytes apart (SBO), 16-byte chunk index XOR (row & 7).  `addr` = shared address of row 0 (+ k*32 bytes to
-// step along K inside the 128-byte row).  When the row-0 address is not 1024-byte aligned (tap-shifted views
-// of an activation slab) base_offset = (addr >> 7) & 7 keeps the swizzle phase (PTX matrix-descriptor table).
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t addr, int base_offset_mode = 0) {
+// step along K inside the 128-byte row).  The row-0 address may be any multiple of 128 bytes inside a slab whose
+// base is 1024-byte aligned and that was written with chunk ^= (absolute_row & 7): tap-shifted views.
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t addr) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);            // [0,14)  start address >> 4
     d |= (uint64_t)1 << 16;                              // [16,30) leading byte offset (unused for swizzled K-major) = 1
     d |= (uint64_t)(1024 >> 4) << 32;                    // [32,46) stride byte offset = 1024 B between 8-row groups
     d |= (uint64_t)1 << 46;                              // [46,48) descriptor version = 1 (sm_100)
-    if (base_offset_mode == 0) d |= (uint64_t)((addr >> 7) & 7) << 49;   // [49,52) base offset
+    // [49,52) base offset = 0: measured on B200 -- the 128B swizzle XOR is taken from the ABSOLUTE shared-memory
+    // address bits [7,10), so a view that starts r rows into a 1024-byte-aligned slab needs no phase correction
+    // (setting base_offset = r & 7 double-corrects and scrambles the operand).
     d |= (uint64_t)2 << 61;                              // [61,64) layout type: SWIZZLE_128B
     return d;
 }
