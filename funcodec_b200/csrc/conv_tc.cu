@@ -136,7 +136,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const int chunk = unit / S, ph = unit - chunk * S;
             const int as = unit % TC_NA;
             const uint32_t par = ((unit / TC_NA) & 1) ^ 1;
-            mbar_wait(a_empty + as, par);
             uint8_t* hi = smA + as * L.a_stage;
             uint8_t* lo = hi + L.a_rows * 128;
             const int c = chunk * TC_KC + jchunk * 4;
@@ -144,31 +143,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const float4 b0 = *reinterpret_cast<const float4*>(coefB0 + c);
             float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
             if (has1) { a1 = *reinterpret_cast<const float4*>(coefA1 + c); b1 = *reinterpret_cast<const float4*>(coefB1 + c); }
-            for (int u = rsub; u < L.a_rows; u += 16) {
+            // all row loads of the unit are issued before the ring slot is waited for: one exposed memory latency
+            // per unit instead of one per row
+            constexpr int NR = 9;                      // a_rows <= 144
+            float4 xa[NR], xb[NR];
+            bool okr[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int u = rsub + 16 * i;
                 const int gt = (t0 + u) * S + ph - p.pad_l;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool ok = gt <= gt_max;
+                bool ok = u < L.a_rows && gt <= gt_max;
                 int src = gt;
                 if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
                 else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
+                okr[i] = ok;
+                xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[i] = xa[i];
                 if (ok) {
                     const long long off = (long long)src * C_in + c;
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + off));
-                    v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
-                    v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
-                    if (has1) {
-                        const float4 yv = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                        v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
-                        v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
-                    }
-                    if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                    xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
+                    if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
                 }
-                float4 h, l;
-                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
-                *reinterpret_cast<float4*>(hi + o) = h;
-                *reinterpret_cast<float4*>(lo + o) = l;
+            }
+            mbar_wait(a_empty + as, par);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int u = rsub + 16 * i;
+                if (u < L.a_rows) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (okr[i]) {
+                        const float4 xv = xa[i];
+                        v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
+                        v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
+                        if (has1) {
+                            const float4 yv = xb[i];
+                            v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
+                            v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
+                        }
+                        if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                    }
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
+                    *reinterpret_cast<float4*>(hi + o) = h;
+                    *reinterpret_cast<float4*>(lo + o) = l;
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(a_full + as);
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
 
 // ------------------------------------------------------------------------------------------ host side
 bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D) {
-    return D == 1 && C_in % TC_KC == 0 && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 120;
+    return D == 1 && C_in % TC_KC == 0 && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 16;
 }
 
 int conv_tc_n_tile(int C_out_eff) {

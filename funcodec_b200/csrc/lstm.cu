@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p)
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                           // [H][COLS]
     float* Hs = Ws + (size_t)H * COLS;          // [LSTM_BG][H]
-    float* red = Hs + LSTM_BG * H;              // [8 warps][COLS][LSTM_BG]
+    float* red = Hs + LSTM_BG * H;              // [8 warps][LSTM_BG][COLS]
     float* cS = red + 8 * COLS * LSTM_BG;       // [nbg][LSTM_BG][UNITS] cell state
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u = lane % UNITS, ks = lane / UNITS;
@@ -119,11 +119,11 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p)
                         for (int o = UNITS; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                         acc[g][i] = v;
                     }
-                if (ks == 0) {
+                if (ks == 0) {      // lanes u = 0..UNITS-1 write consecutive float4: conflict-free
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-#pragma unroll
-                        for (int i = 0; i < LSTM_BG; ++i) red[(warp * COLS + u * 4 + g) * LSTM_BG + i] = acc[g][i];
+                    for (int i = 0; i < LSTM_BG; ++i)
+                        *reinterpret_cast<float4*>(red + (warp * LSTM_BG + i) * COLS + u * 4) =
+                            make_float4(acc[0][i], acc[1][i], acc[2][i], acc[3][i]);
                 }
                 __syncthreads();
             }
@@ -131,13 +131,13 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p)
                 const int b = b0 + fbb, j = j0 + fu;
                 float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
                 if (t > 0) {
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8) s += red[(w8 * COLS + fu * 4 + g) * LSTM_BG + fbb];
-                        g4[g] += s;
+                    for (int w8 = 0; w8 < 8; ++w8) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(red + (w8 * LSTM_BG + fbb) * COLS + fu * 4);
+                        s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
                     }
+                    g4[0] += s4.x; g4[1] += s4.y; g4[2] += s4.z; g4[3] += s4.w;
                 }
                 const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
                 float* cp = cS + (bg * LSTM_BG + fbb) * UNITS + fu;
