@@ -19,6 +19,7 @@ struct InView {
     const float* stats;      // [B][2] = (mean, rstd); nullptr => identity (plain tensor)
     const float* gamma;      // [C] GroupNorm weight (used when stats != nullptr)
     const float* beta;       // [C] GroupNorm bias
+    const float* coef;       // [B][2][C] precomputed (rstd*gamma, beta - mean*rstd*gamma) or nullptr (identity)
     long long clip_stride;   // elements between consecutive clips
     int row_off;             // first logical row (transposed-conv trim, conv.py:299-303)
 };

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256, TWO_LEVEL ? 1 : 2) conv1d_cl_kernel(const
 // (ATen group_norm CPU kernel).  mode 1: RMS scale of the input clip, 1e-8 + sqrt(mean(x^2))
 // (funcodec/models/codec_basic.py:366-369).
 __global__ void stats_finalize_kernel(const double* __restrict__ partials, int nparts, double count,
-                                      float eps, int mode, float* __restrict__ out) {
+                                      float eps, int mode, float* __restrict__ out, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int C, float* __restrict__ coef) {
     __shared__ double red[64];
     const int b = blockIdx.x;
     double s = 0.0, ss = 0.0;
@@ -209,15 +210,27 @@ __global__ void stats_finalize_kernel(const double* __restrict__ partials, int n
         ss += partials[((long long)b * nparts + i) * 2 + 1];
     }
     block_reduce_2d(s, ss, red);
+    __shared__ float mr[2];
     if (threadIdx.x == 0) {
         if (mode == 0) {
             const double mean = s / count;
             double var = ss / count - mean * mean;
             if (var < 0.0) var = 0.0;
-            out[2 * b] = (float)mean;
-            out[2 * b + 1] = (float)(1.0 / sqrt(var + (double)eps));
+            mr[0] = (float)mean;
+            mr[1] = (float)(1.0 / sqrt(var + (double)eps));
+            out[2 * b] = mr[0];
+            out[2 * b + 1] = mr[1];
         } else {
             out[b] = 1e-8f + sqrtf((float)(ss / count));
+        }
+    }
+    if (mode == 0 && coef) {      // per-channel affine of the deferred GroupNorm, consumed by the tensor-core producers
+        __syncthreads();
+        const float mean = mr[0], rstd = mr[1];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float a = rstd * gamma[c];
+            coef[(long long)b * 2 * C + c] = a;
+            coef[(long long)b * 2 * C + C + c] = beta[c] - a * mean;
         }
     }
 }
@@ -306,8 +319,9 @@ cudaError_t launch_conv(const ConvParams& p, int B, cudaStream_t st, int* nparts
 }
 
 cudaError_t launch_stats_finalize(const double* partials, int nparts, double count, float eps, int mode,
-                                  float* out, int B, cudaStream_t st) {
-    stats_finalize_kernel<<<B, 256, 0, st>>>(partials, nparts, count, eps, mode, out);
+                                  float* out, int B, cudaStream_t st, const float* gamma, const float* beta, int C,
+                                  float* coef) {
+    stats_finalize_kernel<<<B, 256, 0, st>>>(partials, nparts, count, eps, mode, out, gamma, beta, C, coef);
     return cudaGetLastError();
 }
 

@@ -8,14 +8,20 @@
 // GEMM view (channels-last makes both operands K-major):
 //     D[t (M = 128 time rows), co (N = n_tile)] = sum_{tap k} sum_{ci} X[t*S + k - pad_l][ci] * W[k][ci][co]
 //   * A (activations): one "unit" = (32-channel chunk, stride phase p): the rows {(t0+u)*S + p - pad_l}
-//     are transformed by 4 producer warps and written (hi and lo slabs) into the canonical SWIZZLE_128B
+//     are transformed by a producer group and written (hi and lo slabs) into the canonical SWIZZLE_128B
 //     K-major layout; every tap k = q*S + p of that phase is then just a ROW-SHIFTED view (start address
 //     + q*128 B; the hardware swizzle works on absolute address bits) of the same slab -- no im2col copy.
-//   * B (weights): pre-split, pre-swizzled slab images in HBM (engine.cu pack_tc_weights), one
-//     cp.async.bulk (TMA engine, 1-D) per (chunk, tap) into a 3-stage ring, completion on an mbarrier.
-//   * warp roles: warps 0-3 producers, then epilogue (TMEM lane == time row; tcgen05.ld 32 columns at a
-//     time -> bias -> coalesced channels-last store -> statistics); warp 4 weight copies + TMEM alloc;
-//     warp 5 lane 0 issues tcgen05.mma and frees ring slots with tcgen05.commit.
+//   * B (weights): pre-split, pre-swizzled slab images in HBM (engine.cu pack_tc), one cp.async.bulk
+//     (TMA engine, 1-D) per (chunk, tap) into a ring, completion on an mbarrier.
+//   * PERSISTENT CTAs (one per SM) walk a static list of (clip, n-tile, time-tile) tiles; every role keeps
+//     running across tile boundaries, so the next tile's loads overlap the previous tile's MMAs and epilogue.
+//   * warp roles (14 warps): 0-3 / 4-7 two producer groups taking alternate units (two units of global
+//     loads in flight); 8 weight copies + TMEM alloc; 9 MMA issuer; 10-13 accumulator warps.
+//   * the tensor core adds into its fp32 accumulator with truncation, so a TMEM-resident chain loses
+//     ~1 ulp per MMA (measured 5e-5 relative after 384 chained MMAs): chains are cut every ~48 MMAs, the MMA
+//     warp ping-pongs between two TMEM accumulators and the accumulator warps fold each finished group into
+//     a third TMEM region (running totals) with round-to-nearest CUDA-core adds, then run the epilogue
+//     (bias, channels-last store, GroupNorm partial sums) on the last group.
 // Roofline: tensor pipe (3 MMAs per fp32-equivalent product) for C_in*K >= 128; HBM for the C <= 64 layers.
 #include "common.cuh"
 #include "kernels.h"
@@ -25,32 +31,29 @@ namespace fcb {
 
 using namespace tc;
 
-constexpr int TC_M = 128;          // time rows per CTA
+constexpr int TC_M = 128;          // time rows per tile
 constexpr int TC_KC = 32;          // channels per chunk (one 128-byte swizzle row)
-constexpr int TC_NA = 2;           // A ring depth
-constexpr int TC_THREADS = 320;    // 4 producer warps, 1 copy warp, 1 MMA warp, 4 accumulator/epilogue warps
+constexpr int TC_THREADS = 448;    // 8 producer warps, copy warp, MMA warp, 4 accumulator warps
 constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TMEM before the fp32 fold
 
 struct TcSmemLayout {
     int a_rows;        // rows per A slab (multiple of 8)
     int a_stage;       // bytes per A stage (hi + lo)
     int b_stage;       // bytes per B stage (hi + lo)
-    int nb;            // B ring depth
-    int off_b, off_coef, off_bar, total;
+    int na, nb;        // ring depths
+    int off_b, off_bar, total;
 };
 
-__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int C_in, int n_tile, bool has1, int nb) {
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb) {
     TcSmemLayout L;
     const int qmax = (K - 1) / S;
     L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
     L.a_stage = 2 * L.a_rows * 128;
     L.b_stage = 2 * n_tile * 128;
-    L.nb = nb;
-    L.off_b = TC_NA * L.a_stage;
-    L.off_coef = L.off_b + nb * L.b_stage;
-    L.off_bar = L.off_coef + C_in * 4 * (has1 ? 4 : 2);
-    L.off_bar = (L.off_bar + 15) & ~15;
-    L.total = L.off_bar + 8 * (2 * TC_NA + 2 * nb + 4) + 16;
+    L.na = na; L.nb = nb;
+    L.off_b = na * L.a_stage;
+    L.off_bar = L.off_b + nb * L.b_stage;
+    L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
     return L;
 }
 
@@ -61,263 +64,276 @@ __host__ __device__ inline int tc_units_per_group(int K, int S) {
     return g < 1 ? 1 : g;
 }
 
-// The tensor core adds into its fp32 accumulator with truncation, so the error of a TMEM-resident chain grows
-// linearly with the number of chained MMAs (measured: ~5e-5 relative after 384 MMAs).  Chains are therefore cut
-// every ~48 MMAs: the MMA warp ping-pongs between two TMEM accumulators and the accumulator warps fold each
-// finished group into fp32 registers with round-to-nearest adds.
+struct TcTile { int b, nt, tt; };
+
+__device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
+    TcTile t;
+    t.nt = id % n_nt;                  // n-tile fastest: concurrent CTAs share the activation rows in L2
+    const int r = id / n_nt;
+    t.tt = r % n_tt;
+    t.b = r / n_tt;
+    return t;
+}
+
 template <int N_TILE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int nb_stages) {
-    constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator buffer
-    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                 // power of two >= 64
+__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
+                                                                 const int n_tiles) {
+    constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
+    constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int t0 = blockIdx.x * TC_M;
-    const int nt = blockIdx.y;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, C_in, N_TILE, has1, nb_stages);
+    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
     const int n_chunks = C_in / TC_KC;
     const int n_units = n_chunks * S;
     const int upg = tc_units_per_group(K, S);
     const int n_groups = (n_units + upg - 1) / upg;
+    const int n_tt = (p.T_out + TC_M - 1) / TC_M;
+    const int n_nt = p.C_out / N_TILE;
 
     uint8_t* smA = smem_raw;
     uint8_t* smB = smem_raw + L.off_b;
-    float* coefA0 = reinterpret_cast<float*>(smem_raw + L.off_coef);
-    float* coefB0 = coefA0 + C_in;
-    float* coefA1 = coefB0 + C_in;
-    float* coefB1 = coefA1 + (has1 ? C_in : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
-    uint64_t* a_full = bars;                       // [TC_NA]   128 producer arrivals
-    uint64_t* a_empty = a_full + TC_NA;            // [TC_NA]   tcgen05.commit
-    uint64_t* b_full = a_empty + TC_NA;            // [nb]      expect_tx
-    uint64_t* b_empty = b_full + nb_stages;        // [nb]      tcgen05.commit
-    uint64_t* acc_full = b_empty + nb_stages;      // [2]       tcgen05.commit
-    uint64_t* acc_empty = acc_full + 2;            // [2]       128 accumulator-warp arrivals
+    uint64_t* a_full = bars;                       // [na]   128 producer arrivals (one group)
+    uint64_t* a_empty = a_full + na_stages;        // [na]   tcgen05.commit
+    uint64_t* b_full = a_empty + na_stages;        // [nb]   expect_tx
+    uint64_t* b_empty = b_full + nb_stages;        // [nb]   tcgen05.commit
+    uint64_t* acc_full = b_empty + nb_stages;      // [2]    tcgen05.commit
+    uint64_t* acc_empty = acc_full + 2;            // [2]    128 accumulator-warp arrivals
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    double* red = reinterpret_cast<double*>(tmem_ptr + 2);       // [4][2] statistics scratch
 
     if (tid == 0) {
-        for (int i = 0; i < TC_NA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, TMEM_COLS);
-    // per-clip GroupNorm coefficients of the input view(s)
-    {
-        float mean0 = 0.f, rstd0 = 1.f, mean1 = 0.f, rstd1 = 1.f;
-        if (p.in0.stats) { mean0 = p.in0.stats[2 * b]; rstd0 = p.in0.stats[2 * b + 1]; }
-        if (has1 && p.in1.stats) { mean1 = p.in1.stats[2 * b]; rstd1 = p.in1.stats[2 * b + 1]; }
-        for (int c = tid; c < C_in; c += TC_THREADS) {
-            float a = 1.f, bb = 0.f;
-            if (p.in0.stats) { a = rstd0 * p.in0.gamma[c]; bb = p.in0.beta[c] - a * mean0; }
-            coefA0[c] = a; coefB0[c] = bb;
-            if (has1) {
-                a = 1.f; bb = 0.f;
-                if (p.in1.stats) { a = rstd1 * p.in1.gamma[c]; bb = p.in1.beta[c] - a * mean1; }
-                coefA1[c] = a; coefB1[c] = bb;
-            }
-        }
-    }
+    if (warp == 8) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =========================================================== producers: transformed A slabs
-        const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
-        const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
+        const int grp = warp >> 2;                  // this group takes the units with (global unit index) % 2 == grp
+        const int ptid = tid & 127;
+        const int jchunk = ptid & 7;                // 16-byte chunk (4 channels) inside the 128-byte row
+        const int rsub = ptid >> 3;                 // 16 rows per pass
         const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
-        const int jchunk = tid & 7;                 // 16-byte chunk (4 channels) inside the 128-byte row
-        const int rsub = tid >> 3;                  // 16 rows per pass
-        for (int unit = 0; unit < n_units; ++unit) {
-            const int chunk = unit / S, ph = unit - chunk * S;
-            const int as = unit % TC_NA;
-            const uint32_t par = ((unit / TC_NA) & 1) ^ 1;
-            uint8_t* hi = smA + as * L.a_stage;
-            uint8_t* lo = hi + L.a_rows * 128;
-            const int c = chunk * TC_KC + jchunk * 4;
-            const float4 a0 = *reinterpret_cast<const float4*>(coefA0 + c);
-            const float4 b0 = *reinterpret_cast<const float4*>(coefB0 + c);
-            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
-            if (has1) { a1 = *reinterpret_cast<const float4*>(coefA1 + c); b1 = *reinterpret_cast<const float4*>(coefB1 + c); }
-            // all row loads of the unit are issued before the ring slot is waited for: one exposed memory latency
-            // per unit instead of one per row
-            constexpr int NR = 9;                      // a_rows <= 144
-            float4 xa[NR], xb[NR];
-            bool okr[NR];
+        long long ucount = 0;                       // global unit counter (across tiles)
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const TcTile tl = tc_tile(tile, n_nt, n_tt);
+            const int b = tl.b, t0 = tl.tt * TC_M;
+            const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
+            const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
+            const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
+            const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
+            for (int unit = 0; unit < n_units; ++unit, ++ucount) {
+                if ((int)(ucount & 1) != grp) continue;
+                const int chunk = unit / S, ph = unit - chunk * S;
+                const int as = (int)(ucount % na_stages);
+                const uint32_t par = (uint32_t)((ucount / na_stages) & 1) ^ 1;
+                uint8_t* hi = smA + as * L.a_stage;
+                uint8_t* lo = hi + L.a_rows * 128;
+                const int c = chunk * TC_KC + jchunk * 4;
+                float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+                if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
+                if (cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
+                // all row loads of the unit are issued before the ring slot is waited for
+                constexpr int NR = 9;                      // a_rows <= 144
+                float4 xa[NR], xb[NR];
+                bool okr[NR];
 #pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const int u = rsub + 16 * i;
-                const int gt = (t0 + u) * S + ph - p.pad_l;
-                bool ok = u < L.a_rows && gt <= gt_max;
-                int src = gt;
-                if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
-                else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
-                okr[i] = ok;
-                xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[i] = xa[i];
-                if (ok) {
-                    const long long off = (long long)src * C_in + c;
-                    xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
-                    if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                }
-            }
-            mbar_wait(a_empty + as, par);
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const int u = rsub + 16 * i;
-                if (u < L.a_rows) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (okr[i]) {
-                        const float4 xv = xa[i];
-                        v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
-                        v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
-                        if (has1) {
-                            const float4 yv = xb[i];
-                            v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
-                            v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
-                        }
-                        if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                for (int i = 0; i < NR; ++i) {
+                    const int u = rsub + 16 * i;
+                    const int gt = (t0 + u) * S + ph - p.pad_l;
+                    bool ok = u < L.a_rows && gt <= gt_max;
+                    int src = gt;
+                    if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
+                    else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
+                    okr[i] = ok;
+                    xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[i] = xa[i];
+                    if (ok) {
+                        const long long off = (long long)src * C_in + c;
+                        xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
+                        if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
                     }
-                    float4 h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
-                    *reinterpret_cast<float4*>(hi + o) = h;
-                    *reinterpret_cast<float4*>(lo + o) = l;
                 }
+                mbar_wait(a_empty + as, par);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int u = rsub + 16 * i;
+                    if (u < L.a_rows) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (okr[i]) {
+                            const float4 xv = xa[i];
+                            v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
+                            v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
+                            if (has1) {
+                                const float4 yv = xb[i];
+                                v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
+                                v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
+                            }
+                            if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                        }
+                        float4 h, l;
+                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                        const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
+                        *reinterpret_cast<float4*>(hi + o) = h;
+                        *reinterpret_cast<float4*>(lo + o) = l;
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(a_full + as);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(a_full + as);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // =========================================================== weight slabs via the bulk-copy engine
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)L.b_stage;
-            const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)nt * n_chunks * K * bytes;
-            int it = 0;
-            for (int unit = 0; unit < n_units; ++unit) {
-                const int chunk = unit / S, ph = unit - chunk * S;
-                for (int k = ph; k < K; k += S, ++it) {
-                    const int bs = it % nb_stages;
-                    const uint32_t par = ((it / nb_stages) & 1) ^ 1;
-                    mbar_wait(b_empty + bs, par);
-                    mbar_arrive_expect_tx(b_full + bs, bytes);
-                    bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+            long long it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const TcTile tl = tc_tile(tile, n_nt, n_tt);
+                const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)tl.nt * n_chunks * K * bytes;
+                for (int unit = 0; unit < n_units; ++unit) {
+                    const int chunk = unit / S, ph = unit - chunk * S;
+                    for (int k = ph; k < K; k += S, ++it) {
+                        const int bs = (int)(it % nb_stages);
+                        const uint32_t par = (uint32_t)((it / nb_stages) & 1) ^ 1;
+                        mbar_wait(b_empty + bs, par);
+                        mbar_arrive_expect_tx(b_full + bs, bytes);
+                        bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+                    }
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, N_TILE);
             const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
-            int it = 0;
-            for (int g = 0; g < n_groups; ++g) {
-                const int buf = g & 1;
-                mbar_wait(acc_empty + buf, ((g >> 1) & 1) ^ 1);
-                tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BUF_COLS);
-                uint32_t accum = 0;
-                const int u_end = min(n_units, (g + 1) * upg);
-                for (int unit = g * upg; unit < u_end; ++unit) {
-                    const int ph = unit % S;
-                    const int as = unit % TC_NA;
-                    mbar_wait(a_full + as, (unit / TC_NA) & 1);
+            long long it = 0, ucount = 0, gcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int g = 0; g < n_groups; ++g, ++gcount) {
+                    const int buf = (int)(gcount & 1);
+                    mbar_wait(acc_empty + buf, (uint32_t)((gcount >> 1) & 1) ^ 1);
                     tc_fence_after_sync();
-                    const uint32_t a_hi0 = a_base + as * L.a_stage;
-                    const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
-                    int q = 0;
-                    for (int k = ph; k < K; k += S, ++it, ++q) {
-                        const int bs = it % nb_stages;
-                        mbar_wait(b_full + bs, (it / nb_stages) & 1);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BUF_COLS);
+                    uint32_t accum = 0;
+                    const int u_end = min(n_units, (g + 1) * upg);
+                    for (int unit = g * upg; unit < u_end; ++unit, ++ucount) {
+                        const int ph = unit % S;
+                        const int as = (int)(ucount % na_stages);
+                        mbar_wait(a_full + as, (uint32_t)((ucount / na_stages) & 1));
                         tc_fence_after_sync();
-                        const uint32_t b_hi0 = b_base + bs * L.b_stage;
-                        const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
+                        const uint32_t a_hi0 = a_base + as * L.a_stage;
+                        const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
+                        int q = 0;
+                        for (int k = ph; k < K; k += S, ++it, ++q) {
+                            const int bs = (int)(it % nb_stages);
+                            mbar_wait(b_full + bs, (uint32_t)((it / nb_stages) & 1));
+                            tc_fence_after_sync();
+                            const uint32_t b_hi0 = b_base + bs * L.b_stage;
+                            const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
-                            const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
-                            const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
-                            const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
-                            mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, accum);
-                            accum = 1;
-                            mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
-                            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
+                                const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
+                                const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
+                                const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
+                                mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, accum);
+                                accum = 1;
+                                mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
+                                mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
+                            }
+                            mma_commit(b_empty + bs);
                         }
-                        mma_commit(b_empty + bs);
+                        mma_commit(a_empty + as);
                     }
-                    mma_commit(a_empty + as);
+                    mma_commit(acc_full + buf);
                 }
-                mma_commit(acc_full + buf);
             }
         }
     } else {
-        // =========================================================== accumulator warps: fold groups, then epilogue
-        const int ew = warp - 6;                       // TMEM lanes [32*ew, 32*ew + 32): warp id % 4 == ew + 2 ... see note
-        float tot[N_TILE];
+        // =========================================================== accumulator warps: fold groups, epilogue
+        const int quad = warp & 3;                                   // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(2 * BUF_COLS);
+        long long gcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const TcTile tl = tc_tile(tile, n_nt, n_tt);
+            const int t = tl.tt * TC_M + quad * 32 + lane;
+            const bool row_ok = t < p.T_out;
+            float* orow = p.out + (long long)tl.b * p.out_clip_stride + (long long)t * p.C_out + (long long)tl.nt * N_TILE;
+            const float* bias = p.bias + tl.nt * N_TILE;
+            float s = 0.f, ss = 0.f;
+            for (int g = 0; g < n_groups; ++g, ++gcount) {
+                const int buf = (int)(gcount & 1);
+                const bool last = (g == n_groups - 1);
+                mbar_wait(acc_full + buf, (uint32_t)((gcount >> 1) & 1));
+                tc_fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < N_TILE; ++j) tot[j] = 0.f;
-        const uint32_t lane_base = (uint32_t)(((warp & 3) * 32)) << 16;   // a warp may only touch lanes 32*(warp%4)..+31
-        for (int g = 0; g < n_groups; ++g) {
-            const int buf = g & 1;
-            mbar_wait(acc_full + buf, (g >> 1) & 1);
-            tc_fence_after_sync();
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_base + (uint32_t)(buf * BUF_COLS + c0), v);
+                    if (g > 0) {
+                        uint32_t tv[32];
+                        tmem_ld_32x32b_x32(tot_base + (uint32_t)c0, tv);
+                        tmem_ld_wait();
 #pragma unroll
-            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_base + (uint32_t)(buf * BUF_COLS + c0), v);
-                tmem_ld_wait();
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(tv[j]) + __uint_as_float(v[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    if (!last) {
+                        tmem_st_32x32b_x32(tot_base + (uint32_t)c0, v);
+                    } else if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < N_TILE) tot[c0 + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            if (c0 + j < N_TILE) {
+                                float4 o;
+                                o.x = __uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0);
+                                o.y = __uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1);
+                                o.z = __uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2);
+                                o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
+                                s += (o.x + o.y) + (o.z + o.w);
+                                ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
+                                *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                            }
+                        }
+                    }
+                }
+                if (!last) tmem_st_wait();
+                tc_fence_before_sync();
+                mbar_arrive(acc_empty + buf);
             }
-            tc_fence_before_sync();
-            mbar_arrive(acc_empty + buf);
-        }
-        (void)ew;
-        const int t = t0 + (warp & 3) * 32 + lane;
-        const bool row_ok = t < p.T_out;
-        float* orow = p.out + (long long)b * p.out_clip_stride + (long long)t * p.C_out + (long long)nt * N_TILE;
-        const float* bias = p.bias + nt * N_TILE;
-        float s = 0.f, ss = 0.f;
-        if (row_ok) {
+            if (p.partials) {
+                double ds = (double)s, dss = (double)ss;
 #pragma unroll
-            for (int j = 0; j < N_TILE; j += 4) {
-                float4 o;
-                o.x = tot[j + 0] + __ldg(bias + j + 0);
-                o.y = tot[j + 1] + __ldg(bias + j + 1);
-                o.z = tot[j + 2] + __ldg(bias + j + 2);
-                o.w = tot[j + 3] + __ldg(bias + j + 3);
-                s += (o.x + o.y) + (o.z + o.w);
-                ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
-                *reinterpret_cast<float4*>(orow + j) = o;
-            }
-        }
-        if (p.partials) {
-            double ds = (double)s, dss = (double)ss;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ds += __shfl_xor_sync(0xffffffffu, ds, o);
-                dss += __shfl_xor_sync(0xffffffffu, dss, o);
-            }
-            double* red = reinterpret_cast<double*>(smA);     // A slabs are dead (all MMAs committed)
-            if (lane == 0) { red[(warp - 6) * 2] = ds; red[(warp - 6) * 2 + 1] = dss; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 6 * 32) {
-                const int nparts = gridDim.x * gridDim.y;
-                double* dst = p.partials + ((long long)b * nparts + blockIdx.y * gridDim.x + blockIdx.x) * 2;
-                dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
-                dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
+                for (int o = 16; o > 0; o >>= 1) {
+                    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's reader is done with `red`
+                if (lane == 0) { red[quad * 2] = ds; red[quad * 2 + 1] = dss; }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (quad == 0 && lane == 0) {
+                    const int nparts = n_nt * n_tt;
+                    double* dst = p.partials + ((long long)tl.b * nparts + tl.nt * n_tt + tl.tt) * 2;
+                    dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
+                    dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
+                }
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -339,8 +355,10 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
     return ((T_out + TC_M - 1) / TC_M) * (C_out_eff / conv_tc_n_tile(C_out_eff));
 }
 
+static int g_num_sms = 0;
+
 template <int N_TILE>
-static cudaError_t launch_tc_n(const ConvParams& p, int B, cudaStream_t st, int nb, int smem, dim3 grid) {
+static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles) {
     auto kern = conv1d_tc_kernel<N_TILE>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -348,23 +366,34 @@ static cudaError_t launch_tc_n(const ConvParams& p, int B, cudaStream_t st, int 
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    kern<<<grid, TC_THREADS, smem, st>>>(p, nb);
+    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
-    const bool has1 = p.in1.x != nullptr;
-    int nb = 3;
-    TcSmemLayout L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb);
-    if (L.total > 225 * 1024) { nb = 2; L = tc_layout(p.K, p.S, p.C_in, p.n_tile, has1, nb); }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    // ring depths: as deep as shared memory allows (A even: the two producer groups alternate slots)
+    int na = 4, nb = 4;
+    TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, nb);
+    if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+    if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+    if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
     if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
-    dim3 grid((p.T_out + TC_M - 1) / TC_M, p.C_out / p.n_tile, B);
-    *nparts = grid.x * grid.y;
+    const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
+    *nparts = n_tt * n_nt;
+    const int n_tiles = n_tt * n_nt * B;
     switch (p.n_tile) {
-        case 16: return launch_tc_n<16>(p, B, st, nb, L.total, grid);
-        case 32: return launch_tc_n<32>(p, B, st, nb, L.total, grid);
-        case 64: return launch_tc_n<64>(p, B, st, nb, L.total, grid);
-        case 128: return launch_tc_n<128>(p, B, st, nb, L.total, grid);
+        case 16: return launch_tc_n<16>(p, st, na, nb, L.total, n_tiles);
+        case 32: return launch_tc_n<32>(p, st, na, nb, L.total, n_tiles);
+        case 64: return launch_tc_n<64>(p, st, na, nb, L.total, n_tiles);
+        case 128: return launch_tc_n<128>(p, st, na, nb, L.total, n_tiles);
         default: return cudaErrorInvalidConfiguration;
     }
 }

@@ -55,6 +55,7 @@ struct Act {
     long long clip_stride = 0;
     int row_off = 0;
     float* stats = nullptr;          // [B][2] or nullptr (plain tensor)
+    float* coef = nullptr;           // [B][2][C] per-channel affine of the deferred GroupNorm (with stats)
     const float* gamma = nullptr;
     const float* beta = nullptr;
     bool owned = false;              // p (and stats) were allocated from the pool by the engine
@@ -278,6 +279,7 @@ int release(Run& r, Act& a) {
     if (a.owned) {
         if (a.p) FCB_CK(cudaFreeAsync(a.p, r.st));
         if (a.stats) FCB_CK(cudaFreeAsync(a.stats, r.st));
+        if (a.coef) FCB_CK(cudaFreeAsync(a.coef, r.st));
     }
     a = Act();
     return FCB_OK;
@@ -301,7 +303,7 @@ int phase_end(Run& r) {
 
 InView view_of(const Act& a) {
     InView v;
-    v.x = a.p; v.stats = a.stats; v.gamma = a.gamma; v.beta = a.beta;
+    v.x = a.p; v.stats = a.stats; v.gamma = a.gamma; v.beta = a.beta; v.coef = a.coef;
     v.clip_stride = a.clip_stride; v.row_off = a.row_off;
     return v;
 }
@@ -356,6 +358,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     if (want_norm) {
         FCB_CK(cudaMallocAsync((void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double), r.st));
         FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
+        FCB_TRY(alloc_f(r, &o.coef, (size_t)r.B * 2 * o.C));
         o.gamma = L.gamma; o.beta = L.beta;
     }
     p.partials = partials;
@@ -365,7 +368,8 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     h->launches++;
     if (want_norm) {
         if (np2 != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch");
-        FCB_CK(launch_stats_finalize(partials, nparts, (double)p.T_out * p.C_out, h->cfg.gn_eps, 0, o.stats, r.B, r.st));
+        FCB_CK(launch_stats_finalize(partials, nparts, (double)p.T_out * p.C_out, h->cfg.gn_eps, 0, o.stats, r.B, r.st,
+                                     L.gamma, L.beta, o.C, o.coef));
         h->launches++;
         FCB_CK(cudaFreeAsync(partials, r.st));
     }

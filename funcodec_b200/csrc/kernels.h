@@ -11,7 +11,8 @@ void conv_pick_tile(int T_out, int C_out, int C_in, int K, int B, int* tx, int* 
 int conv_num_parts(int T_out, int C_out, int C_in, int K, int B);
 cudaError_t launch_conv(const ConvParams& p, int B, cudaStream_t st, int* nparts);
 cudaError_t launch_stats_finalize(const double* partials, int nparts, double count, float eps, int mode,
-                                  float* out, int B, cudaStream_t st);
+                                  float* out, int B, cudaStream_t st, const float* gamma = nullptr,
+                                  const float* beta = nullptr, int C = 0, float* coef = nullptr);
 int sumsq_num_parts(int L);
 cudaError_t launch_sumsq_partials(const float* x, int B, int L, double* partials, int* nparts, cudaStream_t st);
 
