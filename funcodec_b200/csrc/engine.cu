@@ -77,6 +77,7 @@ struct fcb_handle {
     LstmW enc_lstm, dec_lstm;
     float* embed = nullptr;   // [n_q][K][D]
     float* cnorm = nullptr;   // [n_q][K]
+    float* embed_tc = nullptr; // tensor-core image of the codebooks (rvq_tc.cu)
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
@@ -139,13 +140,12 @@ int need(fcb_handle* h, const std::string& name, std::vector<int64_t> shape, con
 // Tensor-core weight image (conv_tc.cu): for every (n-tile, 32-channel chunk, tap) one hi slab and one lo
 // slab of [n_tile rows (output channels) x 32 tf32] in the canonical K-major SWIZZLE_128B layout, so that a
 // single 1-D bulk copy drops it into shared memory ready for tcgen05.mma.  hi/lo = 3xTF32 split.
-int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, ConvW* o) {
-    o->n_tile = 0;
-    if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, 1)) return FCB_OK;
-    const int n_tile = conv_tc_n_tile(cout_eff);
+void build_tc_image(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, int n_tile,
+                    std::vector<float>* img_out) {
     const int n_chunks = cin / 32, n_nt = cout_eff / n_tile;
     const size_t slab = (size_t)n_tile * 32;                 // floats per hi (or lo) slab
-    std::vector<float> img((size_t)n_nt * n_chunks * K * 2 * slab);
+    std::vector<float>& img = *img_out;
+    img.assign((size_t)n_nt * n_chunks * K * 2 * slab, 0.f);
     for (int nt = 0; nt < n_nt; ++nt)
         for (int c = 0; c < n_chunks; ++c)
             for (int k = 0; k < K; ++k) {
@@ -164,6 +164,14 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
                         lo[off] = x - xh;
                     }
             }
+}
+
+int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, ConvW* o) {
+    o->n_tile = 0;
+    if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, 1)) return FCB_OK;
+    const int n_tile = conv_tc_n_tile(cout_eff);
+    std::vector<float> img;
+    build_tc_image(wp, K, cin, cout_eff, n_tile, &img);
     FCB_TRY(upload(h, img, &o->w_tc));
     o->n_tile = n_tile;
     return FCB_OK;
@@ -538,9 +546,22 @@ int do_encode(fcb_handle* h, const float* wav, int B, int L, int n_q, int64_t* c
     q.embed = h->embed; q.cnorm = h->cnorm;
     q.B = B; q.T = f.T; q.D = h->cfg.dimension; q.K = h->cfg.codebook_size; q.n_q = n_q;
     q.codes = reinterpret_cast<long long*>(codes);
-    q.quant = quant; q.sub_quants = sub_quants; q.enc_out = encoder_out;
-    FCB_CK(launch_rvq(q, st));
-    h->launches++;
+    q.sub_quants = sub_quants; q.enc_out = encoder_out;
+    q.embed_tc = h->embed_tc;
+    if (h->use_tc && h->embed_tc) {
+        q.quant = nullptr;
+        FCB_CK(launch_rvq_tc(q, st));
+        h->launches++;
+        if (quant) {   // quantized_out = ((0 + q_0) + q_1) + ... rebuilt from the codes (ddp_core_vq.py:408 order)
+            FCB_CK(launch_embed_sum(q.codes, 1, h->embed, B, f.T, n_q, h->cfg.codebook_size, h->cfg.dimension, quant,
+                                    h->err_flag, st));
+            h->launches++;
+        }
+    } else {
+        q.quant = quant;
+        FCB_CK(launch_rvq(q, st));
+        h->launches++;
+    }
     FCB_TRY(release(r, f));
     FCB_TRY(phase_end(r));
     return FCB_OK;
@@ -631,12 +652,24 @@ int fcb_finalize(fcb_handle* h) {
     const HostTensor* emb;
     FCB_TRY(need(h, "quantizer.rq.model.embed", {c.num_quantizers, c.codebook_size, D}, &emb));
     FCB_TRY(upload(h, emb->data, &h->embed));
+    if (h->use_tc && rvq_tc_supported(D, c.codebook_size)) {
+        // per stage: [1][D][K] "weights" (codeword = output channel) -> slab images, stages concatenated
+        std::vector<float> all, wp((size_t)D * c.codebook_size), img;
+        for (int q = 0; q < c.num_quantizers; ++q) {
+            const float* e = emb->data.data() + (size_t)q * c.codebook_size * D;
+            for (int k = 0; k < c.codebook_size; ++k)
+                for (int d = 0; d < D; ++d) wp[(size_t)d * c.codebook_size + k] = e[(size_t)k * D + d];
+            build_tc_image(wp, 1, D, c.codebook_size, 128, &img);
+            all.insert(all.end(), img.begin(), img.end());
+        }
+        FCB_TRY(upload(h, all, &h->embed_tc));
+    }
     FCB_CK(cudaMalloc((void**)&h->cnorm, (size_t)c.num_quantizers * c.codebook_size * sizeof(float)));
     h->dev_allocs.push_back(h->cnorm);
     FCB_CK(cudaMalloc((void**)&h->err_flag, sizeof(int)));
     h->dev_allocs.push_back(h->err_flag);
     FCB_CK(cudaMemset(h->err_flag, 0, sizeof(int)));
-    FCB_CK(cudaMalloc((void**)&h->lstm_barrier, sizeof(unsigned)));
+    FCB_CK(cudaMalloc((void**)&h->lstm_barrier, 64 * sizeof(unsigned)));
     h->dev_allocs.push_back(h->lstm_barrier);
     FCB_CK(launch_code_norms(h->embed, h->cnorm, c.num_quantizers * c.codebook_size, D, 0));
     h->launches++;
@@ -715,7 +748,7 @@ int fcb_decode_codes(fcb_handle* h, const int64_t* codes, int32_t B, int32_t n_f
     const size_t n = (size_t)B * n_frames * h->cfg.dimension;
     if (!emb) FCB_TRY(alloc_f(r, &emb, n));
     FCB_TRY(phase_begin(r, FCB_PHASE_RVQ));
-    FCB_CK(launch_embed_sum(reinterpret_cast<const long long*>(codes), h->embed, B, n_frames, n_q, h->cfg.codebook_size,
+    FCB_CK(launch_embed_sum(reinterpret_cast<const long long*>(codes), 0, h->embed, B, n_frames, n_q, h->cfg.codebook_size,
                             h->cfg.dimension, emb, h->err_flag, st));
     h->launches++;
     FCB_TRY(phase_end(r));

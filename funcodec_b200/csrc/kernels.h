@@ -40,6 +40,7 @@ struct RvqParams {
     InView in;            // encoder output view [B][T'][D] (normalised on load)
     const float* embed;   // [n_q_max][K][D]
     const float* cnorm;   // [n_q_max][K]  |c|^2
+    const float* embed_tc; // tensor-core image of the codebooks (rvq_tc.cu) or nullptr
     int B, T, D, K, n_q;
     long long* codes;     // [n_q][B][T]
     float* quant;         // [B][T][D] or nullptr
@@ -47,8 +48,10 @@ struct RvqParams {
     float* enc_out;       // [B][T][D] or nullptr
 };
 cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
+bool rvq_tc_supported(int D, int K);
+cudaError_t launch_rvq_tc(const RvqParams& p, cudaStream_t st);
 cudaError_t launch_code_norms(const float* embed, float* cnorm, int rows, int D, cudaStream_t st);
-cudaError_t launch_embed_sum(const long long* codes_btq, const float* embed, int B, int T, int n_q, int K, int D,
+cudaError_t launch_embed_sum(const long long* codes, int q_major, const float* embed, int B, int T, int n_q, int K, int D,
                              float* out, int* err_flag, cudaStream_t st);
 
 // misc.cu

@@ -166,7 +166,8 @@ __global__ void code_norms_kernel(const float* __restrict__ embed, float* __rest
 }
 
 // DistributedResidualVectorQuantization.decode (ddp_core_vq.py:442-453): ((0 + C_0[i0]) + C_1[i1]) + ...
-__global__ void embed_sum_kernel(const long long* __restrict__ codes, const float* __restrict__ embed, long long M,
+// codes layout: q_major ? [n_q][M] (encode side) : [M][n_q] (decode side, codec_basic.py:789)
+__global__ void embed_sum_kernel(const long long* __restrict__ codes, int q_major, const float* __restrict__ embed, long long M,
                                  int n_q, int K, int D, float* __restrict__ out, int* __restrict__ err_flag) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M * D) return;
@@ -174,7 +175,7 @@ __global__ void embed_sum_kernel(const long long* __restrict__ codes, const floa
     const int d = (int)(e - row * D);
     float acc = 0.f;
     for (int q = 0; q < n_q; ++q) {
-        const long long ix = codes[row * n_q + q];
+        const long long ix = q_major ? codes[(long long)q * M + row] : codes[row * n_q + q];
         if (ix < 0 || ix >= K) { if (err_flag) atomicExch(err_flag, 1); continue; }
         acc = acc + __ldg(embed + ((long long)q * K + ix) * D + d);
     }
@@ -201,11 +202,11 @@ cudaError_t launch_code_norms(const float* embed, float* cnorm, int rows, int D,
     return cudaGetLastError();
 }
 
-cudaError_t launch_embed_sum(const long long* codes_btq, const float* embed, int B, int T, int n_q, int K, int D,
+cudaError_t launch_embed_sum(const long long* codes, int q_major, const float* embed, int B, int T, int n_q, int K, int D,
                              float* out, int* err_flag, cudaStream_t st) {
     const long long M = (long long)B * T;
     const long long n = M * D;
-    embed_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(codes_btq, embed, M, n_q, K, D, out, err_flag);
+    embed_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(codes, q_major, embed, M, n_q, K, D, out, err_flag);
     return cudaGetLastError();
 }
 
