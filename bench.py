@@ -285,32 +285,29 @@ def main():
         h2d = B * L * 4
         d2h = hc.numel() * 8 + hr.numel() * 4
     else:
+        from funcodec_b200.parallel import ShardedCodec
         GB = world * B
+
+        def run_shard(w):
+            model._ck(model._lib.fcb_roundtrip(model._h, _ptr(w), w.shape[0], L, n_q, 1, _ptr(codes), None, None, None,
+                                               _ptr(recon), model._stream()), "fcb_roundtrip")
+            return codes, recon
+
+        sharded = ShardedCodec(run_shard)
         if rank == 0:
             hw = (0.1 * torch.randn(GB, L, generator=g)).pin_memory()
-            hc = torch.empty((world, n_q, B, Tf), dtype=torch.int64).pin_memory()
+            hc = torch.empty((n_q, GB, Tf), dtype=torch.int64).pin_memory()
             hr = torch.empty((GB, 1, L), dtype=torch.float32).pin_memory()
             dw = torch.empty((GB, L), dtype=torch.float32, device=dev)
-            gc = torch.empty((world, n_q, B, Tf), dtype=torch.int64, device=dev)
-            gr = torch.empty((GB, 1, L), dtype=torch.float32, device=dev)
-        my = torch.empty((B, L), dtype=torch.float32, device=dev)
 
         def e2e_step():
             if rank == 0:
                 dw.copy_(hw, non_blocking=True)
-                dist.scatter(my, list(dw.view(world, B, L).unbind(0)), src=0)
+                out = sharded(dw, GB, L, dev)
+                hc.copy_(out[0], non_blocking=True)
+                hr.copy_(out[1], non_blocking=True)
             else:
-                dist.scatter(my, None, src=0)
-            model._ck(model._lib.fcb_roundtrip(model._h, _ptr(my), B, L, n_q, 1, _ptr(codes), None, None, None,
-                                               _ptr(recon), model._stream()), "fcb_roundtrip")
-            if rank == 0:
-                dist.gather(codes, list(gc.unbind(0)), dst=0)
-                dist.gather(recon, list(gr.view(world, B, 1, L).unbind(0)), dst=0)
-                hc.copy_(gc, non_blocking=True)
-                hr.copy_(gr, non_blocking=True)
-            else:
-                dist.gather(codes, None, dst=0)
-                dist.gather(recon, None, dst=0)
+                sharded(None, GB, L, dev)
             torch.cuda.synchronize()
 
         for _ in range(2):
@@ -325,7 +322,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         h2d = GB * L * 4
-        d2h = world * n_q * B * Tf * 8 + GB * L * 4
+        d2h = n_q * GB * Tf * 8 + GB * L * 4
     e2e_value = world * B * Tf * e2e_steps / (e2e_ms * 1e-3)
 
     if rank == 0:

@@ -140,7 +140,8 @@ class B200Encodec:
         x = self._prep_speech(speech)
         B, L = x.shape
         Tf = self.num_frames(L)
-        n_q = self.cfg.num_quantizers_for_bandwidth(bit_width)
+        # the reference slices self.layers[:n_q] (ddp_core_vq.py:386): a bandwidth above the maximum uses every stage
+        n_q = min(self.cfg.num_quantizers_for_bandwidth(bit_width), self.cfg.num_quantizers)
         D = self.cfg.dimension
         dev = self.device
         codes = torch.empty((n_q, B, Tf), dtype=torch.int64, device=dev)
@@ -216,7 +217,7 @@ class B200Encodec:
                        bit_width: int = None, use_scale: bool = True):
         """fcb_roundtrip_host: HOST (pinned) buffers in and out, copies inside the call, synchronous."""
         B, L = wav_pinned.shape
-        n_q = self.cfg.num_quantizers_for_bandwidth(bit_width)
+        n_q = min(self.cfg.num_quantizers_for_bandwidth(bit_width), self.cfg.num_quantizers)
         assert codes_pinned.shape == (n_q, B, self.num_frames(L)) and codes_pinned.dtype == torch.int64
         assert recon_pinned.shape[0] == B and recon_pinned.shape[-1] == L
         with torch.cuda.device(self.device):

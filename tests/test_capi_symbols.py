@@ -1,0 +1,44 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/funcodec_b200.h declares
+(no compute calls without a GPU); host-side config logic matches the reference formulas."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from funcodec_b200 import _capi, get_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "funcodec_b200.h")).read()
+    declared = set(re.findall(r"FCB_API\s+[\w\s\*]+?\b(fcb_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.SYMBOLS), (declared ^ set(_capi.SYMBOLS))
+    lib = _capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fcb_version().startswith(b"funcodec_b200")
+
+
+def test_create_without_gpu_fails_loudly_not_silently():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from funcodec_b200.encodec import B200Encodec
+    from funcodec_b200 import init_state_dict
+    cfg = get_config("tiny_ds40")
+    with pytest.raises(Exception):
+        B200Encodec(cfg, init_state_dict(cfg, 0), "cuda:0")
+    with pytest.raises(_capi.FcbError):
+        B200Encodec(cfg, init_state_dict(cfg, 0), "cpu")
+
+
+def test_bandwidth_to_quantizers():
+    """vq.py:105-117 and codec_inference.py:121-125."""
+    cfg = get_config("encodec_16k_n32_ds640")
+    assert cfg.bandwidth_per_quantizer() == 250.0
+    assert [cfg.num_quantizers_for_bandwidth(b) for b in (None, 0, 250, 499, 4000, 8000, 99999)] == [32, 32, 1, 1, 16, 32, 399]
+    cfg = get_config("encodec_16k_n32_ds320")
+    assert cfg.bandwidth_per_quantizer() == 500.0 and cfg.hop_length == 320 and cfg.frames(480000) == 1500
