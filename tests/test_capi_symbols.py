@@ -42,3 +42,24 @@ def test_bandwidth_to_quantizers():
     assert [cfg.num_quantizers_for_bandwidth(b) for b in (None, 0, 250, 499, 4000, 8000, 99999)] == [32, 32, 1, 1, 16, 32, 399]
     cfg = get_config("encodec_16k_n32_ds320")
     assert cfg.bandwidth_per_quantizer() == 500.0 and cfg.hop_length == 320 and cfg.frames(480000) == 1500
+
+
+def test_config_from_reference_like_model():
+    """integration.config_from_reference_model on a duck-typed stand-in for the reference Encodec module."""
+    import types
+    import torch
+    from funcodec_b200 import init_state_dict
+    from funcodec_b200.integration import config_from_reference_model, UnsupportedReferenceModel
+    cfg = get_config("encodec_16k_n32_ds320")
+    sd = init_state_dict(cfg, 0)
+    m = types.SimpleNamespace(
+        encoder=types.SimpleNamespace(ratios=list(reversed(cfg.ratios))), decoder=types.SimpleNamespace(ratios=list(cfg.ratios)),
+        quantizer=types.SimpleNamespace(sampling_rate=16000, encoder_hop_length=320, codebook_size=1024, input_proj=None, input_act=None),
+        audio_normalize=True, segment_dur=None, codec_domain="time", state_dict=lambda: sd)
+    got = config_from_reference_model(m)
+    for f in ("ratios", "n_filters", "dimension", "kernel_size", "last_kernel_size", "residual_kernel_size", "lstm_layers",
+              "codebook_size", "num_quantizers", "sample_rate", "audio_normalize"):
+        assert getattr(got, f) == getattr(cfg, f), f
+    m.segment_dur = 1.0
+    with pytest.raises(UnsupportedReferenceModel):
+        config_from_reference_model(m)
