@@ -15,7 +15,9 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:con
 ncu -i /tmp/conv_${TAG}.ncu-rep --page raw --csv > /tmp/conv_raw_${TAG}.csv 2>/dev/null
 python tools/summarize_ncu_raw.py /tmp/conv_raw_${TAG}.csv > gpurun_out/conv_ncu_${TAG}.txt 2>&1
 # 3. RVQ + one LSTM step
-timeout 600 ncu --set full --clock-control none -k regex:"rvq|lstm" -s ${4:-15} -c 3 -f -o /tmp/rl_${TAG} $BENCH >> gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"rvq_tc|lstm_seq" -s ${4:-15} -c 3 -f -o /tmp/rl_${TAG} $BENCH >> gpurun_out/ncu_full_${TAG}.log 2>&1
 ncu -i /tmp/rl_${TAG}.ncu-rep --page raw --csv > /tmp/rl_raw_${TAG}.csv 2>/dev/null
 python tools/summarize_ncu_raw.py /tmp/rl_raw_${TAG}.csv > gpurun_out/rvq_lstm_ncu_${TAG}.txt 2>&1
+ncu -i /tmp/rl_${TAG}.ncu-rep --page source --csv > /tmp/rl_src_${TAG}.csv 2>/dev/null
+python tools/summarize_ncu_source.py /tmp/rl_src_${TAG}.csv > gpurun_out/rvq_lstm_src_${TAG}.txt 2>&1
 ls -la gpurun_out

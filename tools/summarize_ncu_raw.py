@@ -34,4 +34,9 @@ for row in rd[2:]:
     for key, short in KEYS:
         if key in idx:
             out.append(f"{short}={row[idx[key]]}{units[idx[key]] if short in ('dur', 'dram_rd', 'dram_wr') else ''}")
+    for h_, i_ in idx.items():      # anything tensor-pipe related that is non-zero (tcgen05 shows up under several names)
+        if ("tensor" in h_ or "pipe_tc" in h_ or "tmem" in h_) and h_ not in dict(KEYS):
+            v_ = row[i_]
+            if v_ not in ("0", "0.000000", "", "n/a"):
+                out.append(f"{h_}={v_}")
     print(" ".join(out))
