@@ -20,10 +20,13 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_sm100.cuh"
 
 namespace fcb {
 
 constexpr int LSTM_GB = 8;        // clips per work item (accumulator tile)
+constexpr int LSTM_NBUF = 2;      // h ring depth
+constexpr int LSTM_THREADS = 352; // 8 compute warps, 2 cell warps, 1 loader warp
 constexpr int LSTM_MAX_GROUPS = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -34,61 +37,65 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-// Work item (t, g) = timestep t of clip group g (8 clips).  Clip groups are independent sequences, so items are
-// software-pipelined: while item i is being reduced / finalised, the h_{t-1} rows of item i+1 (another group,
-// published by every CTA at least one item ago) are already in flight from L2 into registers.  Each group has
-// its own release/acquire counter, so the grid barrier latency of one group hides behind the other's math.
+// Work item (t, g) = timestep t of clip group g (8 clips).  Clip groups are independent sequences and each has
+// its own release/acquire counter, so the kernel is warp-specialised around items instead of CTA-wide barriers:
+//   * loader warp (1 lane): waits for a free h ring slot, polls the group's counter until every CTA has published
+//     h_{t-1}, then pulls the 8 rows [H] straight from L2 into shared memory with cp.async.bulk (mbarrier tx);
+//   * 8 compute warps: wait for the slot, accumulate gates = h_{t-1} W_hh^T for the CTA's 4*UNITS columns (K split
+//     over warps/lanes, shuffle-reduced), drop the partials in a double-buffered exchange area;
+//   * 2 cell warps: add the partials and gx (prefetched), run the cell update, store h_t (+ skip output) and publish
+//     the group's counter with a single release-add.
+// The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
+// (B <= 8) the chain is latency-bound by construction.
 template <int UNITS>
-__global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p) {
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
     constexpr int NSLICE = 8 * KS_PER_WARP;    // K slices per CTA (interleaved in groups of 4 k)
-    constexpr int NLD = 8;                     // float4 prefetch registers per thread (H <= 1024)
-    extern __shared__ __align__(16) float smem[];
+    constexpr int NFIN = LSTM_GB * UNITS;      // active cell threads
+    extern __shared__ __align__(128) float smem[];
     const int H = p.H, T = p.T, B = p.B;
-    float* Ws = smem;                               // [H][COLS]
-    float* Hs = Ws + (size_t)H * COLS;              // [2][LSTM_GB][H]
-    float* red = Hs + 2 * LSTM_GB * H;              // [8 warps][LSTM_GB][COLS]
-    float* cS = red + 8 * LSTM_GB * COLS;           // [ng][LSTM_GB][UNITS] cell state
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = lane % UNITS, ks = lane / UNITS;
-    const int slice = warp * KS_PER_WARP + ks;
-    const int j0 = blockIdx.x * UNITS;
+    float* Ws = smem;                                   // [H][COLS]
+    float* Hs = Ws + (size_t)H * COLS;                  // [LSTM_NBUF][LSTM_GB][H]
+    float* red = Hs + LSTM_NBUF * LSTM_GB * H;          // [2][8 warps][LSTM_GB][COLS]
+    float* cS = red + 2 * 8 * LSTM_GB * COLS;           // [ng][LSTM_GB][UNITS] cell state
     const int ng = (B + LSTM_GB - 1) / LSTM_GB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * LSTM_GB * UNITS + 3) & ~3));
+    uint64_t* hs_full = bars;                           // [NBUF] tx
+    uint64_t* hs_empty = hs_full + LSTM_NBUF;           // [NBUF] 8 compute-warp arrivals
+    uint64_t* red_full = hs_empty + LSTM_NBUF;          // [2]    8 compute-warp arrivals
+    uint64_t* red_empty = red_full + 2;                 // [2]    64 cell-thread arrivals
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * UNITS;
     const int n_items = T * ng;
     const unsigned nctas = gridDim.x;
 
-    for (int e = tid; e < H * COLS; e += 256) {
+    for (int e = tid; e < H * COLS; e += LSTM_THREADS) {
         const int k = e / COLS, c = e - k * COLS;
         Ws[e] = __ldg(p.whh + (long long)k * 4 * H + (long long)j0 * 4 + c);
     }
-    for (int e = tid; e < ng * LSTM_GB * UNITS; e += 256) cS[e] = 0.f;
+    for (int e = tid; e < ng * LSTM_GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < LSTM_NBUF; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
+        tc::mbar_fence_init();
+    }
     __syncthreads();
 
-    const bool fin = tid < LSTM_GB * UNITS;
-    const int fbb = tid / UNITS, fu = tid % UNITS;
-    float4 hv[NLD];
-
-    for (int i = 0; i < n_items; ++i) {
-        const int t = i / ng, g = i - t * ng;
-        const int b0 = g * LSTM_GB;
-        const int nb = min(LSTM_GB, B - b0);
-        const float* Hc = Hs + (i & 1) * LSTM_GB * H;
-        const int inext = i + 1;
-        const bool has_next = inext < n_items;
-        const int tn = inext / ng, gn = inext - tn * ng;
-        const bool early = has_next && gn != g;
-
-        float4 gxv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fin && fbb < nb)
-            gxv = __ldcs(reinterpret_cast<const float4*>(p.gx + ((long long)(b0 + fbb) * T + t) * 4 * H + (long long)(j0 + fu) * 4));
-
-        float acc[4][LSTM_GB];
+    if (warp < 8) {
+        // ================================================================ compute warps
+        const int u = lane % UNITS, ks = lane / UNITS;
+        const int slice = warp * KS_PER_WARP + ks;
+        for (int i = ng; i < n_items; ++i) {            // items with t == 0 need no recurrent term
+            const int n = i - ng;
+            const int hb = n % LSTM_NBUF, rb = n & 1;
+            tc::mbar_wait(hs_full + hb, (uint32_t)((n / LSTM_NBUF) & 1));
+            const float* Hc = Hs + hb * LSTM_GB * H;
+            float acc[4][LSTM_GB];
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg)
+            for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-            for (int bb = 0; bb < LSTM_GB; ++bb) acc[gg][bb] = 0.f;
-        if (t > 0) {
+                for (int bb = 0; bb < LSTM_GB; ++bb) acc[gg][bb] = 0.f;
             for (int k0 = slice * 4; k0 < H; k0 += NSLICE * 4) {
                 float4 w[4];
 #pragma unroll
@@ -106,33 +113,8 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p)
                     acc[2][bb] = fmaf(h4.w, w[3].z, acc[2][bb]); acc[3][bb] = fmaf(h4.w, w[3].w, acc[3][bb]);
                 }
             }
-        }
-
-        // ---- prefetch of the next item's h_{t-1} (issued here when it belongs to another clip group)
-        auto fetch_next = [&]() {
-            if (tn > 0) {
-                if (tid == 0) {
-                    while (ld_acquire_u32(p.barrier + gn) < (unsigned)tn * nctas) { }
-                    __threadfence();
-                }
-                __syncthreads();
-                const int bn0 = gn * LSTM_GB;
-#pragma unroll
-                for (int r = 0; r < NLD; ++r) {
-                    const int e = (r * 256 + tid) * 4;
-                    hv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e < LSTM_GB * H) {
-                        const int bb = e / H, k = e - bb * H;
-                        if (bn0 + bb < B)
-                            hv[r] = __ldcg(reinterpret_cast<const float4*>(p.h_seq + ((long long)(bn0 + bb) * T + (tn - 1)) * H + k));
-                    }
-                }
-            }
-        };
-        if (early) fetch_next();
-
-        // ---- reduce the K slices, cell update
-        if (t > 0) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(hs_empty + hb);           // this warp is done with the h slot
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
@@ -142,69 +124,100 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(const LstmSeqParams p)
                     for (int o = UNITS; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     acc[gg][bb] = v;
                 }
+            tc::mbar_wait(red_empty + rb, (uint32_t)((n >> 1) & 1) ^ 1);
             if (ks == 0) {
+                float* rd = red + (size_t)rb * 8 * LSTM_GB * COLS;
 #pragma unroll
                 for (int bb = 0; bb < LSTM_GB; ++bb)
-                    *reinterpret_cast<float4*>(red + (warp * LSTM_GB + bb) * COLS + u * 4) =
+                    *reinterpret_cast<float4*>(rd + (warp * LSTM_GB + bb) * COLS + u * 4) =
                         make_float4(acc[0][bb], acc[1][bb], acc[2][bb], acc[3][bb]);
             }
-            __syncthreads();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(red_full + rb);
         }
-        if (fin && fbb < nb) {
-            const int b = b0 + fbb, j = j0 + fu;
+    } else if (warp < 10) {
+        // ================================================================ cell warps
+        const int ftid = tid - 256;
+        const int fbb = ftid / UNITS, fu = ftid % UNITS;
+        const bool active = ftid < NFIN;
+        for (int i = 0; i < n_items; ++i) {
+            const int t = i / ng, g = i - t * ng;
+            const int b0 = g * LSTM_GB;
+            const int nb = min(LSTM_GB, B - b0);
+            const bool mine = active && fbb < nb;
+            float4 gxv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mine)
+                gxv = __ldcs(reinterpret_cast<const float4*>(p.gx + ((long long)(b0 + fbb) * T + t) * 4 * H + (long long)(j0 + fu) * 4));
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
             if (t > 0) {
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n = i - ng, rb = n & 1;
+                tc::mbar_wait(red_full + rb, (uint32_t)((n >> 1) & 1));
+                if (mine) {
+                    const float* rd = red + (size_t)rb * 8 * LSTM_GB * COLS;
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(red + (w8 * LSTM_GB + fbb) * COLS + fu * 4);
-                    s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
+                    for (int w8 = 0; w8 < 8; ++w8) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rd + (w8 * LSTM_GB + fbb) * COLS + fu * 4);
+                        s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
+                    }
+                    g4[0] += s4.x; g4[1] += s4.y; g4[2] += s4.z; g4[3] += s4.w;
                 }
-                g4[0] += s4.x; g4[1] += s4.y; g4[2] += s4.z; g4[3] += s4.w;
+                tc::mbar_arrive(red_empty + rb);
             }
-            const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
-            float* cp = cS + (g * LSTM_GB + fbb) * UNITS + fu;
-            const float c = fg * (*cp) + ig * gg;
-            *cp = c;
-            const float h = og * tanhf(c);
-            const long long o = ((long long)b * T + t) * H + j;
-            __stcg(p.h_seq + o, h);
-            if (p.y_out) {
-                const long long xo = (long long)b * p.skip.clip_stride + ((long long)(p.skip.row_off + t)) * H + j;
-                float xv = p.skip.x[xo];
-                if (p.skip.stats) {
-                    const float mean = p.skip.stats[2 * b], rstd = p.skip.stats[2 * b + 1];
-                    const float a = rstd * p.skip.gamma[j];
-                    xv = fmaf(xv, a, p.skip.beta[j] - a * mean);
+            if (mine) {
+                const int b = b0 + fbb, j = j0 + fu;
+                const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
+                float* cp = cS + (g * LSTM_GB + fbb) * UNITS + fu;
+                const float c = fg * (*cp) + ig * gg;
+                *cp = c;
+                const float h = og * tanhf(c);
+                const long long o = ((long long)b * T + t) * H + j;
+                __stcg(p.h_seq + o, h);
+                if (p.y_out) {
+                    const long long xo = (long long)b * p.skip.clip_stride + ((long long)(p.skip.row_off + t)) * H + j;
+                    float xv = p.skip.x[xo];
+                    if (p.skip.stats) {
+                        const float mean = p.skip.stats[2 * b], rstd = p.skip.stats[2 * b + 1];
+                        const float a = rstd * p.skip.gamma[j];
+                        xv = fmaf(xv, a, p.skip.beta[j] - a * mean);
+                    }
+                    p.y_out[o] = h + xv;
                 }
-                p.y_out[o] = h + xv;
             }
-            __threadfence();
+            // publish h_t of this group: all cell-thread stores -> named barrier -> one gpu-scope release add
+            asm volatile("bar.sync 3, 64;" ::: "memory");
+            if (ftid == 0 && t + 1 < T)
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier + g), "r"(1u) : "memory");
         }
-        // ---- publish h_t of this group
-        __syncthreads();
-        if (tid == 0 && t + 1 < T) { __threadfence(); atomicAdd(p.barrier + g, 1u); }
-        if (has_next && !early) fetch_next();
-        if (has_next && tn > 0) {
-            float* Hn = Hs + (inext & 1) * LSTM_GB * H;
-#pragma unroll
-            for (int r = 0; r < NLD; ++r) {
-                const int e = (r * 256 + tid) * 4;
-                if (e < LSTM_GB * H) *reinterpret_cast<float4*>(Hn + e) = hv[r];
+    } else {
+        // ================================================================ loader warp
+        if (lane == 0) {
+            for (int i = ng; i < n_items; ++i) {
+                const int t = i / ng, g = i - t * ng;
+                const int n = i - ng, hb = n % LSTM_NBUF;
+                const int b0 = g * LSTM_GB;
+                const int nb = min(LSTM_GB, B - b0);
+                tc::mbar_wait(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1);
+                while (ld_acquire_u32(p.barrier + g) < (unsigned)t * nctas) { }
+                asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
+                tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
+                float* dst = Hs + hb * LSTM_GB * H;
+                for (int bb = 0; bb < nb; ++bb)
+                    tc::bulk_g2s(dst + bb * H, p.h_seq + ((long long)(b0 + bb) * T + (t - 1)) * H, (uint32_t)(H * 4), hs_full + hb);
             }
         }
-        __syncthreads();
     }
 }
 
 size_t lstm_seq_smem_bytes(int H, int B, int units) {
     const int ng = (B + LSTM_GB - 1) / LSTM_GB;
-    return ((size_t)H * 4 * units + (size_t)2 * LSTM_GB * H + 8 * 4 * units * LSTM_GB + (size_t)ng * LSTM_GB * units) * sizeof(float);
+    const size_t cs = ((size_t)ng * LSTM_GB * units + 3) & ~(size_t)3;
+    return ((size_t)H * 4 * units + (size_t)LSTM_NBUF * LSTM_GB * H + 2 * 8 * 4 * units * LSTM_GB + cs) * sizeof(float) +
+           (2 * LSTM_NBUF + 4) * 8 + 64;
 }
 
 int lstm_pick_units(int H) {
     // largest slice that fits shared memory while keeping >= 96 CTAs busy when H allows it
-    if (H > 1024) return 0;                                   // prefetch registers cover 8 clips x 1024
     if (H % 8 == 0 && lstm_seq_smem_bytes(H, 16, 8) <= 220 * 1024 && H / 8 >= 96) return 8;
     if (H % 4 == 0 && lstm_seq_smem_bytes(H, 16, 4) <= 220 * 1024) return 4;
     return 0;
@@ -224,7 +237,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if ((p.B + LSTM_GB - 1) / LSTM_GB > LSTM_MAX_GROUPS) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(p.barrier, 0, LSTM_MAX_GROUPS * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    dim3 grid(p.H / UNITS), block(256);
+    dim3 grid(p.H / UNITS), block(LSTM_THREADS);
     LstmSeqParams pc = p;
     void* args[] = {&pc};
     return cudaLaunchCooperativeKernel((void*)kern, grid, block, args, smem, st);
