@@ -258,6 +258,105 @@ __global__ void sumsq_partials_kernel(const float* __restrict__ x, int L, int ch
     }
 }
 
+// Conv with a single output channel (the decoder's last SConv1d, seanet_decoder.py:160-164): pure HBM streaming
+// (reads C_in floats per sample, writes one).  One thread produces 4 consecutive samples from a transformed input
+// window staged in shared memory; weights are broadcast reads.  Input views must carry precomputed coefficients.
+constexpr int C1_TT = 4, C1_THREADS = 128, C1_TILE = C1_TT * C1_THREADS;
+
+__global__ void __launch_bounds__(C1_THREADS) conv1d_cout1_kernel(const ConvParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int C_in = p.C_in, K = p.K;
+    const int pitch = C_in + 1;
+    const int R = C1_TILE + K - 1;
+    float* Ws = smem;                       // [K][C_in]
+    float* Xs = Ws + ((K * C_in + 3) & ~3); // [R][pitch]
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int t0 = blockIdx.x * C1_TILE;
+    const bool has1 = p.in1.x != nullptr;
+    for (int e = tid; e < K * C_in; e += C1_THREADS) Ws[e] = __ldg(p.w + e);       // packed [k][ci][1]
+    const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
+    const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
+    const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
+    const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
+    const int gt_max = (p.T_out - 1) - p.pad_l + (K - 1);
+    const int nvec = C_in / 4;
+    for (int e = tid; e < R * nvec; e += C1_THREADS) {
+        const int row = e / nvec, c = (e - row * nvec) * 4;
+        const int gt = t0 - p.pad_l + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int src = reflect_index(gt, p.T_ext);
+        if (gt <= gt_max && src >= 0 && src < p.T_in) {
+            const long long off = (long long)src * C_in + c;
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + off));
+            float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cf0) { a = __ldg(reinterpret_cast<const float4*>(cf0 + c)); bb = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
+            v.x = fmaf(xv.x, a.x, bb.x); v.y = fmaf(xv.y, a.y, bb.y); v.z = fmaf(xv.z, a.z, bb.z); v.w = fmaf(xv.w, a.w, bb.w);
+            if (has1) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(x1 + off));
+                a = make_float4(1.f, 1.f, 1.f, 1.f); bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cf1) { a = __ldg(reinterpret_cast<const float4*>(cf1 + c)); bb = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
+                v.x = v.x + fmaf(yv.x, a.x, bb.x); v.y = v.y + fmaf(yv.y, a.y, bb.y);
+                v.z = v.z + fmaf(yv.z, a.z, bb.z); v.w = v.w + fmaf(yv.w, a.w, bb.w);
+            }
+            if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        }
+        float* d = Xs + row * pitch + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    // thread -> samples tid + 128*i (interleaved: conflict-free rows, coalesced stores)
+    float acc[C1_TT];
+#pragma unroll
+    for (int i = 0; i < C1_TT; ++i) acc[i] = 0.f;
+    for (int k = 0; k < K; ++k)
+        for (int c = 0; c < C_in; ++c) {
+            const float w = Ws[k * C_in + c];
+#pragma unroll
+            for (int i = 0; i < C1_TT; ++i) acc[i] = fmaf(Xs[(tid + C1_THREADS * i + k) * pitch + c], w, acc[i]);
+        }
+    const float bias = __ldg(p.bias);
+    float s = 0.f, ss = 0.f;
+    float* outb = p.out + (long long)b * p.out_clip_stride;
+#pragma unroll
+    for (int i = 0; i < C1_TT; ++i) {
+        const int t = t0 + tid + C1_THREADS * i;
+        if (t < p.T_out) {
+            const float o = acc[i] + bias;
+            outb[t] = o;
+            s += o; ss = fmaf(o, o, ss);
+        }
+    }
+    if (p.partials) {
+        __shared__ double red[64];
+        double ds = (double)s, dss = (double)ss;
+        block_reduce_2d(ds, dss, red);
+        if (tid == 0) {
+            double* dst = p.partials + ((long long)b * gridDim.x + blockIdx.x) * 2;
+            dst[0] = ds; dst[1] = dss;
+        }
+    }
+}
+
+bool conv_cout1_supported(const ConvParams& p) {
+    return p.C_out == 1 && p.S == 1 && p.D == 1 && !p.pad_zero && !p.div_scale && p.C_in % 4 == 0 && p.C_in <= 64 &&
+           !(p.in0.stats && !p.in0.coef) && !(p.in1.x && p.in1.stats && !p.in1.coef);
+}
+int conv_cout1_num_parts(int T_out) { return (T_out + C1_TILE - 1) / C1_TILE; }
+
+cudaError_t launch_conv_cout1(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
+    const size_t smem = (((size_t)p.K * p.C_in + 3) & ~(size_t)3) * 4 + (size_t)(C1_TILE + p.K - 1) * (p.C_in + 1) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv1d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(conv_cout1_num_parts(p.T_out), B);
+    *nparts = grid.x;
+    conv1d_cout1_kernel<<<grid, C1_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static size_t conv_smem_bytes(const ConvParams& p, int T_TILE, int CO_TILE) {
     const int R = (T_TILE - 1) * p.S + (p.K - 1) * p.D + 1;

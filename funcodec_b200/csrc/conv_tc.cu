@@ -77,7 +77,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 
 template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles) {
+                                                                 const int n_tiles, const int w_resident) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
     const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
-    const int n_chunks = C_in / TC_KC;
+    const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_units = n_chunks * S;
     const int upg = tc_units_per_group(K, S);
     const int n_groups = (n_units + upg - 1) / upg;
@@ -139,9 +139,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
                 const int c = chunk * TC_KC + jchunk * 4;
+                const bool c_ok = c < C_in;
                 float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
-                if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
-                if (cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
+                if (!c_ok) { a0 = b0; a1 = b0; }
+                else if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
+                if (c_ok && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
                 // all row loads of the unit are issued before the ring slot is waited for
                 constexpr int NR = 9;                      // a_rows <= 144
                 float4 xa[NR], xb[NR];
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 16 * i;
                     const int gt = (t0 + u) * S + ph - p.pad_l;
-                    bool ok = u < L.a_rows && gt <= gt_max;
+                    bool ok = c_ok && u < L.a_rows && gt <= gt_max;
                     int src = gt;
                     if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
                     else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
@@ -161,6 +163,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         const long long off = (long long)src * C_in + c;
                         xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
+                    }
+                }
+                // L2 prefetch of this group's NEXT unit (two units ahead in the global order): one line per row
+                if (jchunk == 0) {
+                    int unit2 = unit + 2, tile2 = tile;
+                    while (unit2 >= n_units && tile2 < n_tiles) { unit2 -= n_units; tile2 += gridDim.x; }
+                    if (tile2 < n_tiles) {
+                        const TcTile t2 = tc_tile(tile2, n_nt, n_tt);
+                        const int chunk2 = unit2 / S, ph2 = unit2 - chunk2 * S;
+                        const float* y0 = p.in0.x + (long long)t2.b * p.in0.clip_stride + (long long)p.in0.row_off * C_in + chunk2 * TC_KC;
+                        const float* y1 = has1 ? p.in1.x + (long long)t2.b * p.in1.clip_stride + (long long)p.in1.row_off * C_in + chunk2 * TC_KC : nullptr;
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int u = rsub + 16 * i;
+                            const int gt = (t2.tt * TC_M + u) * S + ph2 - p.pad_l;
+                            if (u < L.a_rows && gt >= 0 && gt < p.T_in) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(y0 + (long long)gt * C_in));
+                                if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + (long long)gt * C_in));
+                            }
+                        }
                     }
                 }
                 mbar_wait(a_empty + as, par);
@@ -205,7 +227,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     for (int k = ph; k < K; k += S, ++it) {
                         const int bs = (int)(it % nb_stages);
                         const uint32_t par = (uint32_t)((it / nb_stages) & 1) ^ 1;
-                        mbar_wait(b_empty + bs, par);
+                        if (w_resident) { if (it >= nb_stages) continue; }      // whole layer image stays in smem
+                        else mbar_wait(b_empty + bs, par);
                         mbar_arrive_expect_tx(b_full + bs, bytes);
                         bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
                     }
@@ -236,8 +259,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         int q = 0;
                         for (int k = ph; k < K; k += S, ++it, ++q) {
                             const int bs = (int)(it % nb_stages);
-                            mbar_wait(b_full + bs, (uint32_t)((it / nb_stages) & 1));
-                            tc_fence_after_sync();
+                            if (!w_resident || it < nb_stages) {
+                                mbar_wait(b_full + bs, (uint32_t)((it / nb_stages) & 1));
+                                tc_fence_after_sync();
+                            }
                             const uint32_t b_hi0 = b_base + bs * L.b_stage;
                             const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
 #pragma unroll
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
                                 mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
                             }
-                            mma_commit(b_empty + bs);
+                            if (!w_resident) mma_commit(b_empty + bs);
                         }
                         mma_commit(a_empty + as);
                     }
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
 
 // ------------------------------------------------------------------------------------------ host side
 bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D) {
-    return D == 1 && C_in % TC_KC == 0 && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 16;
+    return D == 1 && (C_in % TC_KC == 0 || C_in == 16) && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 16;
 }
 
 int conv_tc_n_tile(int C_out_eff) {
@@ -358,7 +383,7 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 static int g_num_sms = 0;
 
 template <int N_TILE>
-static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles) {
+static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
     auto kern = conv1d_tc_kernel<N_TILE>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -367,7 +392,7 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int
         attr_done = true;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles);
+    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident);
     return cudaGetLastError();
 }
 
@@ -379,21 +404,28 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
     }
-    // ring depths: as deep as shared memory allows (A even: the two producer groups alternate slots)
-    int na = 4, nb = 4;
-    TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, nb);
-    if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-    if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-    if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-    if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
+    // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
+    // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
+    // (A even: the two producer groups alternate slots).
+    const int n_slabs = ((p.C_in + TC_KC - 1) / TC_KC) * p.K;
+    int resident = 0, na = 4, nb = 4;
+    TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
+    if (n_slabs <= 64 && L.total <= 225 * 1024) { resident = 1; nb = n_slabs; }
+    else {
+        L = tc_layout(p.K, p.S, p.n_tile, na, nb);
+        if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
+    }
     const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
     *nparts = n_tt * n_nt;
     const int n_tiles = n_tt * n_nt * B;
     switch (p.n_tile) {
-        case 16: return launch_tc_n<16>(p, st, na, nb, L.total, n_tiles);
-        case 32: return launch_tc_n<32>(p, st, na, nb, L.total, n_tiles);
-        case 64: return launch_tc_n<64>(p, st, na, nb, L.total, n_tiles);
-        case 128: return launch_tc_n<128>(p, st, na, nb, L.total, n_tiles);
+        case 16: return launch_tc_n<16>(p, st, na, nb, L.total, n_tiles, resident);
+        case 32: return launch_tc_n<32>(p, st, na, nb, L.total, n_tiles, resident);
+        case 64: return launch_tc_n<64>(p, st, na, nb, L.total, n_tiles, resident);
+        case 128: return launch_tc_n<128>(p, st, na, nb, L.total, n_tiles, resident);
         default: return cudaErrorInvalidConfiguration;
     }
 }

@@ -142,7 +142,7 @@ int need(fcb_handle* h, const std::string& name, std::vector<int64_t> shape, con
 // single 1-D bulk copy drops it into shared memory ready for tcgen05.mma.  hi/lo = 3xTF32 split.
 void build_tc_image(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, int n_tile,
                     std::vector<float>* img_out) {
-    const int n_chunks = cin / 32, n_nt = cout_eff / n_tile;
+    const int n_chunks = (cin + 31) / 32, n_nt = cout_eff / n_tile;   // a partial last chunk is zero-padded
     const size_t slab = (size_t)n_tile * 32;                 // floats per hi (or lo) slab
     std::vector<float>& img = *img_out;
     img.assign((size_t)n_nt * n_chunks * K * 2 * slab, 0.f);
@@ -153,7 +153,7 @@ void build_tc_image(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, 
                 float* lo = hi + slab;
                 for (int n = 0; n < n_tile; ++n)
                     for (int col = 0; col < 32; ++col) {
-                        const float x = wp[((size_t)k * cin + c * 32 + col) * cout_eff + nt * n_tile + n];
+                        const float x = (c * 32 + col < cin) ? wp[((size_t)k * cin + c * 32 + col) * cout_eff + nt * n_tile + n] : 0.f;
                         uint32_t u;
                         memcpy(&u, &x, 4);
                         u = (u + 0x1000u) & 0xFFFFE000u;
@@ -362,7 +362,9 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     o.owned = true;
     p.out = o.p;
     double* partials = nullptr;
-    const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B);
+    const bool c1 = !tc && conv_cout1_supported(p);
+    const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out)
+                          : (c1 ? conv_cout1_num_parts(p.T_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B));
     if (want_norm) {
         FCB_CK(cudaMallocAsync((void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double), r.st));
         FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
@@ -372,6 +374,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     p.partials = partials;
     int np2 = 0;
     if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
+    else if (c1) FCB_CK(launch_conv_cout1(p, r.B, r.st, &np2));
     else FCB_CK(launch_conv(p, r.B, r.st, &np2));
     h->launches++;
     if (want_norm) {

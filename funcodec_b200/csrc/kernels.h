@@ -13,6 +13,9 @@ cudaError_t launch_conv(const ConvParams& p, int B, cudaStream_t st, int* nparts
 cudaError_t launch_stats_finalize(const double* partials, int nparts, double count, float eps, int mode,
                                   float* out, int B, cudaStream_t st, const float* gamma = nullptr,
                                   const float* beta = nullptr, int C = 0, float* coef = nullptr);
+bool conv_cout1_supported(const ConvParams& p);
+int conv_cout1_num_parts(int T_out);
+cudaError_t launch_conv_cout1(const ConvParams& p, int B, cudaStream_t st, int* nparts);
 int sumsq_num_parts(int L);
 cudaError_t launch_sumsq_partials(const float* x, int B, int L, double* partials, int* nparts, cudaStream_t st);
 

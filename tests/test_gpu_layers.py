@@ -70,6 +70,8 @@ CASES = [  # (layer, C_in, T_in, elu)
     ("decoder.model.0", 128, 250, False), ("decoder.model.3", 1024, 250, True), ("decoder.model.6", 512, 131, True),
     ("decoder.model.9", 256, 140, True), ("decoder.model.12", 128, 257, True), ("decoder.model.15", 64, 300, True),
     ("decoder.model.16.block.1", 32, 515, True), ("encoder.model.18", 1024, 5, True), ("decoder.model.3", 1024, 1, True),
+    ("encoder.model.1.block.3", 16, 700, True), ("decoder.model.18", 32, 1500, True), ("decoder.model.18", 32, 3, True),
+    ("encoder.model.0", 1, 1000, False),
 ]
 
 
