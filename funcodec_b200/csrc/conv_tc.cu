@@ -15,8 +15,9 @@
 //     (TMA engine, 1-D) per (chunk, tap) into a ring, completion on an mbarrier.
 //   * PERSISTENT CTAs (one per SM) walk a static list of (clip, n-tile, time-tile) tiles; every role keeps
 //     running across tile boundaries, so the next tile's loads overlap the previous tile's MMAs and epilogue.
-//   * warp roles (14 warps): 0-3 / 4-7 two producer groups taking alternate units (two units of global
-//     loads in flight); 8 weight copies + TMEM alloc; 9 MMA issuer; 10-13 accumulator warps.
+//   * warp roles (22 warps): 0-7 / 8-15 two producer groups taking alternate units (two units of global
+//     loads in flight; the transform is issue-bound, hence 16 warps); 16 weight copies + TMEM alloc; 17 MMA
+//     issuer; 18-21 accumulator warps.
 //   * the tensor core adds into its fp32 accumulator with truncation, so a TMEM-resident chain loses
 //     ~1 ulp per MMA (measured 5e-5 relative after 384 chained MMAs): chains are cut every ~48 MMAs, the MMA
 //     warp ping-pongs between two TMEM accumulators and the accumulator warps fold each finished group into
@@ -33,8 +34,13 @@ using namespace tc;
 
 constexpr int TC_M = 128;          // time rows per tile
 constexpr int TC_KC = 32;          // channels per chunk (one 128-byte swizzle row)
-constexpr int TC_THREADS = 448;    // 8 producer warps, copy warp, MMA warp, 4 accumulator warps
+constexpr int TC_THREADS = 704;    // 16 producer warps (2 groups), copy warp, MMA warp, 4 accumulator warps
+constexpr int TC_PROD = 256;       // producer threads per group (one unit)
 constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TMEM before the fp32 fold
+
+// ELU with the hardware exponential (ex2.approx): |error| <= ~2e-7 on the (0, 1] range of exp(x), the same order as
+// one fp32 rounding of the reference's exp(x) - 1.  (The SIMT path keeps expf.)
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
 
 struct TcSmemLayout {
     int a_rows;        // rows per A slab (multiple of 8)
@@ -105,23 +111,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     double* red = reinterpret_cast<double*>(tmem_ptr + 2);       // [4][2] statistics scratch
 
     if (tid == 0) {
-        for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, TC_PROD); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_ptr, TMEM_COLS);
+    if (warp == 16) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 8) {
+    if (warp < 16) {
         // =========================================================== producers: transformed A slabs
-        const int grp = warp >> 2;                  // this group takes the units with (global unit index) % 2 == grp
-        const int ptid = tid & 127;
+        const int grp = warp >> 3;                  // this group takes the units with (global unit index) % 2 == grp
+        const int ptid = tid & (TC_PROD - 1);
         const int jchunk = ptid & 7;                // 16-byte chunk (4 channels) inside the 128-byte row
-        const int rsub = ptid >> 3;                 // 16 rows per pass
+        const int rsub = ptid >> 3;                 // 32 rows per pass
         const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
         long long ucount = 0;                       // global unit counter (across tiles)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -145,12 +151,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 else if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
                 if (c_ok && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
                 // all row loads of the unit are issued before the ring slot is waited for
-                constexpr int NR = 9;                      // a_rows <= 144
+                constexpr int NR = 5;                      // a_rows <= 160 = 5 passes of 32 rows
                 float4 xa[NR], xb[NR];
                 bool okr[NR];
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
-                    const int u = rsub + 16 * i;
+                    const int u = rsub + 32 * i;
                     const int gt = (t0 + u) * S + ph - p.pad_l;
                     bool ok = c_ok && u < L.a_rows && gt <= gt_max;
                     int src = gt;
@@ -165,30 +171,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
                     }
                 }
-                // L2 prefetch of this group's NEXT unit (two units ahead in the global order): one line per row
-                if (jchunk == 0) {
-                    int unit2 = unit + 2, tile2 = tile;
-                    while (unit2 >= n_units && tile2 < n_tiles) { unit2 -= n_units; tile2 += gridDim.x; }
-                    if (tile2 < n_tiles) {
-                        const TcTile t2 = tc_tile(tile2, n_nt, n_tt);
-                        const int chunk2 = unit2 / S, ph2 = unit2 - chunk2 * S;
-                        const float* y0 = p.in0.x + (long long)t2.b * p.in0.clip_stride + (long long)p.in0.row_off * C_in + chunk2 * TC_KC;
-                        const float* y1 = has1 ? p.in1.x + (long long)t2.b * p.in1.clip_stride + (long long)p.in1.row_off * C_in + chunk2 * TC_KC : nullptr;
-#pragma unroll
-                        for (int i = 0; i < NR; ++i) {
-                            const int u = rsub + 16 * i;
-                            const int gt = (t2.tt * TC_M + u) * S + ph2 - p.pad_l;
-                            if (u < L.a_rows && gt >= 0 && gt < p.T_in) {
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(y0 + (long long)gt * C_in));
-                                if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + (long long)gt * C_in));
-                            }
-                        }
-                    }
-                }
                 mbar_wait(a_empty + as, par);
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
-                    const int u = rsub + 16 * i;
+                    const int u = rsub + 32 * i;
                     if (u < L.a_rows) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (okr[i]) {
@@ -200,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
                                 v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
                             }
-                            if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+                            if (p.elu) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
                         }
                         float4 h, l;
                         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
@@ -214,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 mbar_arrive(a_full + as);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // =========================================================== weight slabs via the bulk-copy engine
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)L.b_stage;
@@ -235,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // =========================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, N_TILE);
@@ -358,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
