@@ -233,14 +233,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-
-    # ---------------- timed region: device-resident inputs
+    # clocks are sampled from before the warm-up (nvidia-smi needs ~0.3 s to start; the timed region of a short run
+    # would otherwise be over before its first sample) -- same kernels, same load
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    t_load = time.perf_counter()
+    while rank == 0 and len(sampler.rows) < 2 and time.perf_counter() - t_load < 1.5:
+        step(0)                     # keep the GPU under the same load until the sampler has started reporting
+        torch.cuda.synchronize()
+    barrier()
+
+    # ---------------- timed region: device-resident inputs
     model.set_profiling(True)
     launches0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

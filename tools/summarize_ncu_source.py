@@ -31,6 +31,6 @@ for r in rows:
     except Exception:
         continue
 tot = sum(v[0] for v in agg.values()) or 1.0
-print("columns seen:", list(hdr)[:30] if hdr else None)
-for (k, s), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+
+for (k, s), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:55]:
     print(f"{100 * v[0] / tot:5.1f}%  {s}")
