@@ -129,19 +129,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         const int jchunk = ptid & 7;                // 16-byte chunk (4 channels) inside the 128-byte row
         const int rsub = ptid >> 3;                 // 32 rows per pass
         const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
-        long long ucount = 0;                       // global unit counter (across tiles)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // this group's cursor over the CTA's global unit sequence (tile-major); it advances two units at a time and its
+        // ring slot two slots at a time (na is even), so no division / modulo is needed in the loop
+        int tile = blockIdx.x, unit = grp;
+        int as = grp % na_stages;
+        uint32_t aphase = 0;
+        while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+        while (tile < n_tiles) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
             const int b = tl.b, t0 = tl.tt * TC_M;
             const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
             const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
             const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
-            for (int unit = 0; unit < n_units; ++unit, ++ucount) {
-                if ((int)(ucount & 1) != grp) continue;
+            const int cur_tile = tile;
+            for (; unit < n_units && tile == cur_tile; ) {
                 const int chunk = unit / S, ph = unit - chunk * S;
-                const int as = (int)(ucount % na_stages);
-                const uint32_t par = (uint32_t)((ucount / na_stages) & 1) ^ 1;
+                const uint32_t par = aphase ^ 1;
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
                 const int c = chunk * TC_KC + jchunk * 4;
@@ -198,27 +202,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(a_full + as);
+                as += 2;
+                if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
+                unit += 2;
             }
+            while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
         }
     } else if (warp == 16) {
         // =========================================================== weight slabs via the bulk-copy engine
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)L.b_stage;
-            long long it = 0;
+            int bs = 0;
+            uint32_t bphase = 0;
+            bool first = true;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (w_resident && !first) break;                       // whole layer image already resident
                 const TcTile tl = tc_tile(tile, n_nt, n_tt);
                 const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)tl.nt * n_chunks * K * bytes;
+                int chunk = 0, ph = 0;
                 for (int unit = 0; unit < n_units; ++unit) {
-                    const int chunk = unit / S, ph = unit - chunk * S;
-                    for (int k = ph; k < K; k += S, ++it) {
-                        const int bs = (int)(it % nb_stages);
-                        const uint32_t par = (uint32_t)((it / nb_stages) & 1) ^ 1;
-                        if (w_resident) { if (it >= nb_stages) continue; }      // whole layer image stays in smem
-                        else mbar_wait(b_empty + bs, par);
+                    for (int k = ph; k < K; k += S) {
+                        if (!w_resident) mbar_wait(b_empty + bs, bphase ^ 1);
                         mbar_arrive_expect_tx(b_full + bs, bytes);
                         bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+                        if (++bs == nb_stages) { bs = 0; bphase ^= 1; }
                     }
+                    if (++ph == S) { ph = 0; ++chunk; }
                 }
+                first = false;
             }
         }
     } else if (warp == 17) {
@@ -226,27 +237,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, N_TILE);
             const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
-            long long it = 0, ucount = 0, gcount = 0;
+            int as = 0, bs = 0;
+            uint32_t aphase = 0, bphase = 0, gcount = 0;
+            bool first = true;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int ph = 0;
+                if (w_resident) bs = 0;
                 for (int g = 0; g < n_groups; ++g, ++gcount) {
                     const int buf = (int)(gcount & 1);
-                    mbar_wait(acc_empty + buf, (uint32_t)((gcount >> 1) & 1) ^ 1);
+                    mbar_wait(acc_empty + buf, ((gcount >> 1) & 1) ^ 1);
                     tc_fence_after_sync();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BUF_COLS);
                     uint32_t accum = 0;
                     const int u_end = min(n_units, (g + 1) * upg);
-                    for (int unit = g * upg; unit < u_end; ++unit, ++ucount) {
-                        const int ph = unit % S;
-                        const int as = (int)(ucount % na_stages);
-                        mbar_wait(a_full + as, (uint32_t)((ucount / na_stages) & 1));
+                    for (int unit = g * upg; unit < u_end; ++unit) {
+                        mbar_wait(a_full + as, aphase);
                         tc_fence_after_sync();
                         const uint32_t a_hi0 = a_base + as * L.a_stage;
                         const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
                         int q = 0;
-                        for (int k = ph; k < K; k += S, ++it, ++q) {
-                            const int bs = (int)(it % nb_stages);
-                            if (!w_resident || it < nb_stages) {
-                                mbar_wait(b_full + bs, (uint32_t)((it / nb_stages) & 1));
+                        for (int k = ph; k < K; k += S, ++q) {
+                            if (!w_resident || first) {
+                                mbar_wait(b_full + bs, bphase);
                                 tc_fence_after_sync();
                             }
                             const uint32_t b_hi0 = b_base + bs * L.b_stage;
@@ -263,11 +275,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
                             }
                             if (!w_resident) mma_commit(b_empty + bs);
+                            if (++bs == nb_stages) { bs = 0; bphase ^= 1; }
                         }
                         mma_commit(a_empty + as);
+                        if (++as == na_stages) { as = 0; aphase ^= 1; }
+                        if (++ph == S) ph = 0;
                     }
                     mma_commit(acc_full + buf);
                 }
+                first = false;
             }
         }
     } else {
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         const int quad = warp & 3;                                   // a warp may only touch TMEM lanes 32*(warp%4)..+31
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(2 * BUF_COLS);
-        long long gcount = 0;
+        uint32_t gcount = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
             const int t = tl.tt * TC_M + quad * 32 + lane;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             for (int g = 0; g < n_groups; ++g, ++gcount) {
                 const int buf = (int)(gcount & 1);
                 const bool last = (g == n_groups - 1);
-                mbar_wait(acc_full + buf, (uint32_t)((gcount >> 1) & 1));
+                mbar_wait(acc_full + buf, (gcount >> 1) & 1);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -396,7 +412,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     const int n_slabs = ((p.C_in + TC_KC - 1) / TC_KC) * p.K;
     int resident = 0, na = 4, nb = 4;
     TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
-    if (n_slabs <= 64 && L.total <= 225 * 1024) { resident = 1; nb = n_slabs; }
+    if (n_slabs <= 64 && p.C_out == p.n_tile && L.total <= 225 * 1024) { resident = 1; nb = n_slabs; }   // one n-tile only
     else {
         L = tc_layout(p.K, p.S, p.n_tile, na, nb);
         if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
