@@ -82,7 +82,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 }
 
 template <int N_TILE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
+__global__ void __maxnreg__(88) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
                                                                  const int n_tiles, const int w_resident) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
@@ -173,6 +173,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         const long long off = (long long)src * C_in + c;
                         xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
+                    }
+                }
+                // L2 prefetch of this group's next unit (global loads of a unit are latency-bound: ~2-3 us from DRAM
+                // under load vs ~0.4 us from L2); every lane prefetches the address it will load
+                {
+                    int unit2 = unit + 2, tile2 = tile;
+                    while (unit2 >= n_units && tile2 < n_tiles) { unit2 -= n_units; tile2 += gridDim.x; }
+                    if (tile2 < n_tiles && c_ok) {
+                        int b2 = b, tt2 = tl.tt;
+                        if (tile2 != tile) { const TcTile t2 = tc_tile(tile2, n_nt, n_tt); b2 = t2.b; tt2 = t2.tt; }
+                        const int chunk2 = unit2 / S, ph2 = unit2 - chunk2 * S;
+                        const int c2 = chunk2 * TC_KC + jchunk * 4;
+                        const float* y0 = p.in0.x + (long long)b2 * p.in0.clip_stride + (long long)p.in0.row_off * C_in + c2;
+                        const float* y1 = has1 ? p.in1.x + (long long)b2 * p.in1.clip_stride + (long long)p.in1.row_off * C_in + c2 : nullptr;
+                        if (c2 < C_in) {
+#pragma unroll
+                            for (int i = 0; i < NR; ++i) {
+                                const int u = rsub + 32 * i;
+                                int gt = (tt2 * TC_M + u) * S + ph2 - p.pad_l;
+                                gt = gt < 0 ? 0 : (gt >= p.T_in ? p.T_in - 1 : gt);     // clamp: a harmless in-range line
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(y0 + (long long)gt * C_in));
+                                if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + (long long)gt * C_in));
+                            }
+                        }
                     }
                 }
                 mbar_wait(a_empty + as, par);

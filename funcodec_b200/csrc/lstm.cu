@@ -26,7 +26,7 @@ namespace fcb {
 
 constexpr int LSTM_GB = 8;        // clips per work item (accumulator tile)
 constexpr int LSTM_NBUF = 2;      // h ring depth
-constexpr int LSTM_THREADS = 352; // 8 compute warps, 2 cell warps, 1 loader warp
+constexpr int LSTM_THREADS = 416; // 8 compute warps, 2 x 2 cell warps (alternate items), 1 loader warp
 constexpr int LSTM_MAX_GROUPS = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -43,8 +43,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 //     h_{t-1}, then pulls the 8 rows [H] straight from L2 into shared memory with cp.async.bulk (mbarrier tx);
 //   * 8 compute warps: wait for the slot, accumulate gates = h_{t-1} W_hh^T for the CTA's 4*UNITS columns (K split
 //     over warps/lanes, shuffle-reduced), drop the partials in a double-buffered exchange area;
-//   * 2 cell warps: add the partials and gx (prefetched), run the cell update, store h_t (+ skip output) and publish
-//     the group's counter with a single release-add.
+//   * 2 x 2 cell warps (alternate items): add the partials and gx (prefetched one item ahead), run the cell update,
+//     store h_t (+ skip output) and publish the group's counter with a single release-add.
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
 template <int UNITS>
@@ -135,19 +135,29 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(red_full + rb);
         }
-    } else if (warp < 10) {
-        // ================================================================ cell warps
-        const int ftid = tid - 256;
+    } else if (warp < 12) {
+        // ================================================================ cell warps: two pairs take alternate items
+        const int pair = (warp - 8) >> 1;
+        const int ftid = (tid - 256) & 63;
         const int fbb = ftid / UNITS, fu = ftid % UNITS;
         const bool active = ftid < NFIN;
-        for (int i = 0; i < n_items; ++i) {
+        auto load_gx = [&](int i) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_items) {
+                const int t = i / ng, g = i - t * ng;
+                const int b0 = g * LSTM_GB;
+                if (active && b0 + fbb < B)
+                    v = __ldcs(reinterpret_cast<const float4*>(p.gx + ((long long)(b0 + fbb) * T + t) * 4 * H + (long long)(j0 + fu) * 4));
+            }
+            return v;
+        };
+        float4 gxv = load_gx(pair);
+        for (int i = pair; i < n_items; i += 2) {
             const int t = i / ng, g = i - t * ng;
             const int b0 = g * LSTM_GB;
             const int nb = min(LSTM_GB, B - b0);
             const bool mine = active && fbb < nb;
-            float4 gxv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mine)
-                gxv = __ldcs(reinterpret_cast<const float4*>(p.gx + ((long long)(b0 + fbb) * T + t) * 4 * H + (long long)(j0 + fu) * 4));
+            const float4 gx_next = load_gx(i + 2);               // in flight while this item is reduced
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
             if (t > 0) {
                 const int n = i - ng, rb = n & 1;
@@ -184,10 +194,12 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     p.y_out[o] = h + xv;
                 }
             }
-            // publish h_t of this group: all cell-thread stores -> named barrier -> one gpu-scope release add
-            asm volatile("bar.sync 3, 64;" ::: "memory");
+            // publish h_t of this group: the pair's stores -> named barrier -> one gpu-scope release add
+            if (pair == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
             if (ftid == 0 && t + 1 < T)
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier + g), "r"(1u) : "memory");
+            gxv = gx_next;
         }
     } else {
         // ================================================================ loader warp
