@@ -82,7 +82,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 }
 
 template <int N_TILE>
-__global__ void __maxnreg__(88) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
+__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
                                                                  const int n_tiles, const int w_resident) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
