@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_sm100.cuh"
+#include <stdlib.h>
 
 namespace fcb {
 
@@ -64,9 +65,9 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
 }
 
 // units (chunk, phase) chained in one TMEM accumulation group
-__host__ __device__ inline int tc_units_per_group(int K, int S) {
+__host__ __device__ inline int tc_units_per_group(int K, int S, int group_mmas) {
     const int taps = (K + S - 1) / S;                  // max taps of a phase
-    int g = TC_GROUP_MMAS / (12 * taps);
+    int g = group_mmas / (12 * taps);
     return g < 1 ? 1 : g;
 }
 
@@ -83,7 +84,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 
 template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles, const int w_resident) {
+                                                                 const int n_tiles, const int w_resident, const int group_mmas) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_units = n_chunks * S;
-    const int upg = tc_units_per_group(K, S);
+    const int upg = tc_units_per_group(K, S, group_mmas);
     const int n_groups = (n_units + upg - 1) / upg;
     const int n_tt = (p.T_out + TC_M - 1) / TC_M;
     const int n_nt = p.C_out / N_TILE;
@@ -173,30 +174,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         const long long off = (long long)src * C_in + c;
                         xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                    }
-                }
-                // L2 prefetch of this group's next unit (global loads of a unit are latency-bound: ~2-3 us from DRAM
-                // under load vs ~0.4 us from L2); every lane prefetches the address it will load
-                {
-                    int unit2 = unit + 2, tile2 = tile;
-                    while (unit2 >= n_units && tile2 < n_tiles) { unit2 -= n_units; tile2 += gridDim.x; }
-                    if (tile2 < n_tiles && c_ok) {
-                        int b2 = b, tt2 = tl.tt;
-                        if (tile2 != tile) { const TcTile t2 = tc_tile(tile2, n_nt, n_tt); b2 = t2.b; tt2 = t2.tt; }
-                        const int chunk2 = unit2 / S, ph2 = unit2 - chunk2 * S;
-                        const int c2 = chunk2 * TC_KC + jchunk * 4;
-                        const float* y0 = p.in0.x + (long long)b2 * p.in0.clip_stride + (long long)p.in0.row_off * C_in + c2;
-                        const float* y1 = has1 ? p.in1.x + (long long)b2 * p.in1.clip_stride + (long long)p.in1.row_off * C_in + c2 : nullptr;
-                        if (c2 < C_in) {
-#pragma unroll
-                            for (int i = 0; i < NR; ++i) {
-                                const int u = rsub + 32 * i;
-                                int gt = (tt2 * TC_M + u) * S + ph2 - p.pad_l;
-                                gt = gt < 0 ? 0 : (gt >= p.T_in ? p.T_in - 1 : gt);     // clamp: a harmless in-range line
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(y0 + (long long)gt * C_in));
-                                if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(y1 + (long long)gt * C_in));
-                            }
-                        }
                     }
                 }
                 mbar_wait(a_empty + as, par);
@@ -408,6 +385,8 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
+static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0;
+
 template <int N_TILE>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
     auto kern = conv1d_tc_kernel<N_TILE>;
@@ -418,7 +397,7 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int
         attr_done = true;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident);
+    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);
     return cudaGetLastError();
 }
 
@@ -429,6 +408,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
+        // tuning knobs (experiments only; defaults are the shipped configuration)
+        if (const char* v = getenv("FCB_TC_GROUP_MMAS")) g_group_mmas = atoi(v) > 0 ? atoi(v) : TC_GROUP_MMAS;
+        if (const char* v = getenv("FCB_TC_NA")) g_force_na = atoi(v);
+        if (const char* v = getenv("FCB_TC_NB")) g_force_nb = atoi(v);
     }
     // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
@@ -443,6 +426,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
         if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
         if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
+        if (g_force_na > 0 && g_force_nb > 0) {
+            const TcSmemLayout L2 = tc_layout(p.K, p.S, p.n_tile, g_force_na, g_force_nb);
+            if (L2.total <= 225 * 1024 && g_force_na % 2 == 0) { na = g_force_na; nb = g_force_nb; L = L2; }
+        }
     }
     const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
     *nparts = n_tt * n_nt;
