@@ -200,6 +200,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FCB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_name, B, L, bw = WORKLOADS[args.workload]
@@ -339,8 +340,9 @@ def main():
         conv_bytes = algo["conv_bytes_per_10s"] * clip10 * B + algo["weight_bytes"]
         achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
         conv_tflops = 2 * algo["conv_gmac_per_10s"] * clip10 * B / (conv_ms * 1e-3) / 1e3 if conv_ms > 0 else 0.0
-        roofline = dict(bound="hbm", kernel="conv1d_cl_kernel (all SEANet conv/convtr launches of one step, "
-                                            "encoder_conv + decoder_conv phases)",
+        roofline = dict(bound="hbm", kernel="conv1d_tc_kernel<N> (+ conv1d_cl / conv1d_cout1 for the 3 layers that do not fit "
+                                            "the tensor cores): all SEANet conv/convtr launches of one step = "
+                                            "encoder_conv + decoder_conv phases",
                         achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
                         traffic=None, peak_source=peaks["source"], algorithmic_bytes=conv_bytes,
                         kernel_ms_per_step=conv_ms, conv_fp32_tflops=conv_tflops)

@@ -1,0 +1,44 @@
+"""`Speech2Token` mirror (funcodec/bin/codec_inference.py:41-151): the run_mod dispatch the CLI performs on the model,
+on top of B200Encodec.  Same call signature and return tuple, same `decode` bit-width arithmetic."""
+import math
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from .config import CodecConfig
+from .encodec import B200Encodec
+
+
+class Speech2Token:
+    def __init__(self, model: B200Encodec, device: str = "cuda:0"):
+        self.model = model
+        self.device = device
+
+    @classmethod
+    def from_state_dict(cls, cfg: CodecConfig, state_dict, device: str = "cuda:0"):
+        return cls(B200Encodec(cfg, state_dict, device), device)
+
+    @torch.no_grad()
+    def __call__(self, speech: Union[torch.Tensor, np.ndarray], ppg=None, need_recon: bool = True,
+                 bit_width: Optional[int] = None, use_scale: bool = True, run_mod: str = "inference"):
+        """codec_inference.py:86-134.  `ppg` (CodecSemanticAug only) is not supported."""
+        if ppg is not None:
+            raise ValueError("ppg input belongs to codec_semantic_aug models, which are out of scope")
+        if isinstance(speech, np.ndarray):
+            speech = torch.from_numpy(speech)
+        m = self.model
+        if run_mod == "inference":
+            ret = m.inference(speech, need_recon=need_recon, bit_width=bit_width, use_scale=use_scale)
+        elif run_mod == "encode":
+            ret = m.inference_encoding(speech, need_recon=False, bit_width=bit_width)
+        elif run_mod == "decode_emb":
+            ret = m.inference_decoding_emb(speech)
+        else:
+            q = m.quantizer
+            bit_per_quant = (q.sampling_rate // q.encoder_hop_length) * int(math.log2(q.codebook_size))
+            nq = None
+            if bit_width is not None:
+                nq = int(max(bit_width // bit_per_quant, 1))
+            ret = m.inference_decoding(speech[:, :, :nq])
+        return ret["code_indices"], ret["code_embeddings"], ret["recon_speech"], ret["sub_quants"]
