@@ -662,7 +662,7 @@ int fcb_finalize(fcb_handle* h) {
             const float* e = emb->data.data() + (size_t)q * c.codebook_size * D;
             for (int k = 0; k < c.codebook_size; ++k)
                 for (int d = 0; d < D; ++d) wp[(size_t)d * c.codebook_size + k] = e[(size_t)k * D + d];
-            build_tc_image(wp, 1, D, c.codebook_size, 128, &img);
+            build_tc_image(wp, 1, D, c.codebook_size, RVQ_TC_N, &img);
             all.insert(all.end(), img.begin(), img.end());
         }
         FCB_TRY(upload(h, all, &h->embed_tc));

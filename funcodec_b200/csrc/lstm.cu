@@ -70,9 +70,14 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     const int n_items = T * ng;
     const unsigned nctas = gridDim.x;
 
+    // W_hh slice in the FFMA2-friendly layout: for every pair of consecutive k and every unit u two 16-byte records
+    //   rec(kp, half, u) = { W[k][u][2*half], W[k+1][u][2*half], W[k][u][2*half+1], W[k+1][u][2*half+1] }
+    // so that one LDS.128 yields two (w_k, w_{k+1}) register pairs and lanes u = 0..UNITS-1 read consecutive records.
     for (int e = tid; e < H * COLS; e += LSTM_THREADS) {
         const int k = e / COLS, c = e - k * COLS;
-        Ws[e] = __ldg(p.whh + (long long)k * 4 * H + (long long)j0 * 4 + c);
+        const int uu = c >> 2, g = c & 3;
+        const int dst = (((k >> 1) * 2 + (g >> 1)) * UNITS + uu) * 4 + ((g & 1) * 2 + (k & 1));
+        Ws[dst] = __ldg(p.whh + (long long)k * 4 * H + (long long)j0 * 4 + c);
     }
     for (int e = tid; e < ng * LSTM_GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
     if (tid == 0) {
@@ -91,28 +96,37 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             const int hb = n % LSTM_NBUF, rb = n & 1;
             tc::mbar_wait(hs_full + hb, (uint32_t)((n / LSTM_NBUF) & 1));
             const float* Hc = Hs + hb * LSTM_GB * H;
+            // packed fp32 FMAs (FFMA2): even-k and odd-k partial sums live in the two halves of a register pair
+            float2 acc2[4][LSTM_GB];
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+                for (int bb = 0; bb < LSTM_GB; ++bb) acc2[gg][bb] = make_float2(0.f, 0.f);
+            for (int k0 = slice * 4; k0 < H; k0 += NSLICE * 4) {
+                const int kp = k0 >> 1;
+                const float4 wa0 = *reinterpret_cast<const float4*>(Ws + (((kp + 0) * 2 + 0) * UNITS + u) * 4);
+                const float4 wb0 = *reinterpret_cast<const float4*>(Ws + (((kp + 0) * 2 + 1) * UNITS + u) * 4);
+                const float4 wa1 = *reinterpret_cast<const float4*>(Ws + (((kp + 1) * 2 + 0) * UNITS + u) * 4);
+                const float4 wb1 = *reinterpret_cast<const float4*>(Ws + (((kp + 1) * 2 + 1) * UNITS + u) * 4);
+#pragma unroll
+                for (int bb = 0; bb < LSTM_GB; ++bb) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(Hc + bb * H + k0);
+                    const float2 h01 = make_float2(h4.x, h4.y), h23 = make_float2(h4.z, h4.w);
+                    acc2[0][bb] = __ffma2_rn(h01, make_float2(wa0.x, wa0.y), acc2[0][bb]);
+                    acc2[1][bb] = __ffma2_rn(h01, make_float2(wa0.z, wa0.w), acc2[1][bb]);
+                    acc2[2][bb] = __ffma2_rn(h01, make_float2(wb0.x, wb0.y), acc2[2][bb]);
+                    acc2[3][bb] = __ffma2_rn(h01, make_float2(wb0.z, wb0.w), acc2[3][bb]);
+                    acc2[0][bb] = __ffma2_rn(h23, make_float2(wa1.x, wa1.y), acc2[0][bb]);
+                    acc2[1][bb] = __ffma2_rn(h23, make_float2(wa1.z, wa1.w), acc2[1][bb]);
+                    acc2[2][bb] = __ffma2_rn(h23, make_float2(wb1.x, wb1.y), acc2[2][bb]);
+                    acc2[3][bb] = __ffma2_rn(h23, make_float2(wb1.z, wb1.w), acc2[3][bb]);
+                }
+            }
             float acc[4][LSTM_GB];
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) acc[gg][bb] = 0.f;
-            for (int k0 = slice * 4; k0 < H; k0 += NSLICE * 4) {
-                float4 w[4];
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Ws + (k0 + kk) * COLS + u * 4);
-#pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) {
-                    const float4 h4 = *reinterpret_cast<const float4*>(Hc + bb * H + k0);
-                    acc[0][bb] = fmaf(h4.x, w[0].x, acc[0][bb]); acc[1][bb] = fmaf(h4.x, w[0].y, acc[1][bb]);
-                    acc[2][bb] = fmaf(h4.x, w[0].z, acc[2][bb]); acc[3][bb] = fmaf(h4.x, w[0].w, acc[3][bb]);
-                    acc[0][bb] = fmaf(h4.y, w[1].x, acc[0][bb]); acc[1][bb] = fmaf(h4.y, w[1].y, acc[1][bb]);
-                    acc[2][bb] = fmaf(h4.y, w[1].z, acc[2][bb]); acc[3][bb] = fmaf(h4.y, w[1].w, acc[3][bb]);
-                    acc[0][bb] = fmaf(h4.z, w[2].x, acc[0][bb]); acc[1][bb] = fmaf(h4.z, w[2].y, acc[1][bb]);
-                    acc[2][bb] = fmaf(h4.z, w[2].z, acc[2][bb]); acc[3][bb] = fmaf(h4.z, w[2].w, acc[3][bb]);
-                    acc[0][bb] = fmaf(h4.w, w[3].x, acc[0][bb]); acc[1][bb] = fmaf(h4.w, w[3].y, acc[1][bb]);
-                    acc[2][bb] = fmaf(h4.w, w[3].z, acc[2][bb]); acc[3][bb] = fmaf(h4.w, w[3].w, acc[3][bb]);
-                }
-            }
+                for (int bb = 0; bb < LSTM_GB; ++bb) acc[gg][bb] = acc2[gg][bb].x + acc2[gg][bb].y;
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(hs_empty + hb);           // this warp is done with the h slot
 #pragma unroll

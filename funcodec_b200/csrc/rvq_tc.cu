@@ -27,8 +27,8 @@ namespace fcb {
 using namespace tc;
 
 constexpr int RQ_M = 128;           // rows per CTA
-constexpr int RQ_N = 128;           // codewords per MMA tile
-constexpr int RQ_NB = 2;            // codebook slab ring depth
+constexpr int RQ_N = RVQ_TC_N;      // codewords per MMA tile (64: 16 KB slabs -> a 4-deep ring hides the copy latency)
+constexpr int RQ_NB = 4;            // codebook slab ring depth
 constexpr int RQ_THREADS = 192;     // 4 epilogue warps, copy warp, MMA warp
 constexpr float RQ_RESCORE_TOL = 4e-3f;
 
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
         mbar_init(a_ready, 128);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, 256);
+    if (warp == 4) tmem_alloc(tmem_ptr, 2 * RQ_N);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
     __syncthreads();
     if (warp == 4) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 2 * RQ_N);
     }
 }
 
