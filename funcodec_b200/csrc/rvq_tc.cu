@@ -186,29 +186,50 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
             idx_s[myrow] = best;
             if (row0 + myrow < M) p.codes[(long long)q * M + row0 + myrow] = (long long)best;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            // ---- dequantize + residual update (all MMAs of the stage have completed: last acc_full was waited on)
-            for (int ch = 0; ch < n_chunks; ++ch) {
-                uint8_t* hi = smA + (2 * ch) * L.a_slab;
-                uint8_t* lo = hi + L.a_slab;
-                for (int r = rsub; r < RQ_M; r += 16) {
-                    const long long row = row0 + r;
-                    if (row >= M) continue;
-                    const int d = ch * 32 + jchunk * 4;
-                    const float4 cv = __ldg(reinterpret_cast<const float4*>(E + (long long)idx_s[r] * D + d));
-                    const uint32_t o = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
-                    const float4 h0 = *reinterpret_cast<const float4*>(hi + o);
-                    const float4 l0 = *reinterpret_cast<const float4*>(lo + o);
-                    float4 x;
-                    x.x = (h0.x + l0.x) - cv.x; x.y = (h0.y + l0.y) - cv.y; x.z = (h0.z + l0.z) - cv.z; x.w = (h0.w + l0.w) - cv.w;
-                    float4 h, l;
-                    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-                    *reinterpret_cast<float4*>(hi + o) = h;
-                    *reinterpret_cast<float4*>(lo + o) = l;
-                    if (p.sub_quants) {
-                        const int b = (int)(row / T), t = (int)(row - (long long)b * T);
-                        float* sq = p.sub_quants + (((long long)q * p.B + b) * D + d) * T + t;
-                        sq[0] = cv.x; sq[(long long)T] = cv.y; sq[2LL * T] = cv.z; sq[3LL * T] = cv.w;
+            // ---- dequantize + residual update (all MMAs of the stage have completed: last acc_full was waited on).
+            // 8 passes of 16 rows; the codeword reads of pass i+1 (L2 latency) are in flight while pass i is re-split.
+            {
+                constexpr int MAXCH = 4;                       // D <= 128 on this path
+                float4 cv[MAXCH], nv[MAXCH];
+                auto load_c = [&](int r, float4 (&dst)[MAXCH]) {
+#pragma unroll
+                    for (int ch = 0; ch < MAXCH; ++ch) {
+                        dst[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ch < n_chunks && row0 + r < M)
+                            dst[ch] = __ldg(reinterpret_cast<const float4*>(E + (long long)idx_s[r] * D + ch * 32 + jchunk * 4));
                     }
+                };
+                load_c(rsub, cv);
+                for (int r = rsub; r < RQ_M; r += 16) {
+                    if (r + 16 < RQ_M) load_c(r + 16, nv);
+                    const long long row = row0 + r;
+                    if (row < M) {
+                        const uint32_t o = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
+#pragma unroll
+                        for (int ch = 0; ch < MAXCH; ++ch) {
+                            if (ch < n_chunks) {
+                                uint8_t* hi = smA + (2 * ch) * L.a_slab;
+                                uint8_t* lo = hi + L.a_slab;
+                                const float4 h0 = *reinterpret_cast<const float4*>(hi + o);
+                                const float4 l0 = *reinterpret_cast<const float4*>(lo + o);
+                                const float4 c4 = cv[ch];
+                                float4 x;
+                                x.x = (h0.x + l0.x) - c4.x; x.y = (h0.y + l0.y) - c4.y; x.z = (h0.z + l0.z) - c4.z; x.w = (h0.w + l0.w) - c4.w;
+                                float4 h, l;
+                                split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+                                *reinterpret_cast<float4*>(hi + o) = h;
+                                *reinterpret_cast<float4*>(lo + o) = l;
+                                if (p.sub_quants) {
+                                    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+                                    const int d = ch * 32 + jchunk * 4;
+                                    float* sq = p.sub_quants + (((long long)q * p.B + b) * D + d) * T + t;
+                                    sq[0] = c4.x; sq[(long long)T] = c4.y; sq[2LL * T] = c4.z; sq[3LL * T] = c4.w;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < MAXCH; ++ch) cv[ch] = nv[ch];
                 }
             }
         }
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
 }
 
 bool rvq_tc_supported(int D, int K) {
-    return D % 32 == 0 && D >= 32 && K % RQ_N == 0 && rq_layout(D, K).total <= 225 * 1024;
+    return D % 32 == 0 && D >= 32 && D <= 128 && K % RQ_N == 0 && rq_layout(D, K).total <= 225 * 1024;
 }
 
 cudaError_t launch_rvq_tc(const RvqParams& p, cudaStream_t st) {
