@@ -261,8 +261,7 @@ __global__ void sumsq_partials_kernel(const float* __restrict__ x, int L, int ch
 // Conv with a single output channel (the decoder's last SConv1d, seanet_decoder.py:160-164): pure HBM streaming
 // (reads C_in floats per sample, writes one).  One thread produces 4 consecutive samples from a transformed input
 // window staged in shared memory; weights are broadcast reads.  Input views must carry precomputed coefficients.
-constexpr int C1_TT = 7, C1_THREADS = 128, C1_TILE = C1_TT * C1_THREADS;   // 7 consecutive samples per thread:
-// row stride 7*(C_in+1) words is odd for the C_in = 32 case -> conflict-free; each x value is reused by up to K taps
+constexpr int C1_TT = 4, C1_THREADS = 128, C1_TILE = C1_TT * C1_THREADS;
 
 __global__ void __launch_bounds__(C1_THREADS) conv1d_cout1_kernel(const ConvParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -305,40 +304,22 @@ __global__ void __launch_bounds__(C1_THREADS) conv1d_cout1_kernel(const ConvPara
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
-    // thread -> samples [tid*7, tid*7+7): sliding window of 7+K-1 rows per channel, weights broadcast
-    constexpr int KMAX = 8;
+    // thread -> samples tid + 128*i (interleaved: conflict-free rows, coalesced stores)
     float acc[C1_TT];
 #pragma unroll
     for (int i = 0; i < C1_TT; ++i) acc[i] = 0.f;
-    const float* xr = Xs + (tid * C1_TT) * pitch;
-    if (K <= KMAX) {
+    for (int k = 0; k < K; ++k)
         for (int c = 0; c < C_in; ++c) {
-            float xw[C1_TT + KMAX - 1];
+            const float w = Ws[k * C_in + c];
 #pragma unroll
-            for (int i = 0; i < C1_TT + KMAX - 1; ++i) xw[i] = (i < C1_TT + K - 1) ? xr[i * pitch + c] : 0.f;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    const float w = Ws[k * C_in + c];
-#pragma unroll
-                    for (int i = 0; i < C1_TT; ++i) acc[i] = fmaf(xw[i + k], w, acc[i]);
-                }
-            }
+            for (int i = 0; i < C1_TT; ++i) acc[i] = fmaf(Xs[(tid + C1_THREADS * i + k) * pitch + c], w, acc[i]);
         }
-    } else {
-        for (int k = 0; k < K; ++k)
-            for (int c = 0; c < C_in; ++c) {
-                const float w = Ws[k * C_in + c];
-#pragma unroll
-                for (int i = 0; i < C1_TT; ++i) acc[i] = fmaf(xr[(i + k) * pitch + c], w, acc[i]);
-            }
-    }
     const float bias = __ldg(p.bias);
     float s = 0.f, ss = 0.f;
     float* outb = p.out + (long long)b * p.out_clip_stride;
 #pragma unroll
     for (int i = 0; i < C1_TT; ++i) {
-        const int t = t0 + tid * C1_TT + i;
+        const int t = t0 + tid + C1_THREADS * i;
         if (t < p.T_out) {
             const float o = acc[i] + bias;
             outb[t] = o;
