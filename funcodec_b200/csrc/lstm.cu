@@ -24,7 +24,7 @@
 
 namespace fcb {
 
-constexpr int LSTM_GB = 8;        // clips per work item (accumulator tile)
+constexpr int LSTM_GB_MAX = 8;    // clips per work item (accumulator tile): 8, or 4 for small batches (more items in flight)
 constexpr int LSTM_NBUF = 2;      // h ring depth
 constexpr int LSTM_THREADS = 416; // 8 compute warps, 2 x 2 cell warps (alternate items), 1 loader warp
 constexpr int LSTM_MAX_GROUPS = 64;
@@ -47,20 +47,20 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 //     store h_t (+ skip output) and publish the group's counter with a single release-add.
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
-template <int UNITS>
+template <int UNITS, int GB>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
     constexpr int NSLICE = 8 * KS_PER_WARP;    // K slices per CTA (interleaved in groups of 4 k)
-    constexpr int NFIN = LSTM_GB * UNITS;      // active cell threads
+    constexpr int NFIN = GB * UNITS;      // active cell threads
     extern __shared__ __align__(128) float smem[];
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                                   // [H][COLS]
-    float* Hs = Ws + (size_t)H * COLS;                  // [LSTM_NBUF][LSTM_GB][H]
-    float* red = Hs + LSTM_NBUF * LSTM_GB * H;          // [2][8 warps][LSTM_GB][COLS]
-    float* cS = red + 2 * 8 * LSTM_GB * COLS;           // [ng][LSTM_GB][UNITS] cell state
-    const int ng = (B + LSTM_GB - 1) / LSTM_GB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * LSTM_GB * UNITS + 3) & ~3));
+    float* Hs = Ws + (size_t)H * COLS;                  // [LSTM_NBUF][GB][H]
+    float* red = Hs + LSTM_NBUF * GB * H;          // [2][8 warps][GB][COLS]
+    float* cS = red + 2 * 8 * GB * COLS;           // [ng][GB][UNITS] cell state
+    const int ng = (B + GB - 1) / GB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * GB * UNITS + 3) & ~3));
     uint64_t* hs_full = bars;                           // [NBUF] tx
     uint64_t* hs_empty = hs_full + LSTM_NBUF;           // [NBUF] 8 compute-warp arrivals
     uint64_t* red_full = hs_empty + LSTM_NBUF;          // [2]    8 compute-warp arrivals
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         const int dst = (((k >> 1) * 2 + (g >> 1)) * UNITS + uu) * 4 + ((g & 1) * 2 + (k & 1));
         Ws[dst] = __ldg(p.whh + (long long)k * 4 * H + (long long)j0 * 4 + c);
     }
-    for (int e = tid; e < ng * LSTM_GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
+    for (int e = tid; e < ng * GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
     if (tid == 0) {
         for (int i = 0; i < LSTM_NBUF; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
@@ -95,13 +95,13 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             const int n = i - ng;
             const int hb = n % LSTM_NBUF, rb = n & 1;
             tc::mbar_wait(hs_full + hb, (uint32_t)((n / LSTM_NBUF) & 1));
-            const float* Hc = Hs + hb * LSTM_GB * H;
+            const float* Hc = Hs + hb * GB * H;
             // packed fp32 FMAs (FFMA2): even-k and odd-k partial sums live in the two halves of a register pair
-            float2 acc2[4][LSTM_GB];
+            float2 acc2[4][GB];
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) acc2[gg][bb] = make_float2(0.f, 0.f);
+                for (int bb = 0; bb < GB; ++bb) acc2[gg][bb] = make_float2(0.f, 0.f);
             for (int k0 = slice * 4; k0 < H; k0 += NSLICE * 4) {
                 const int kp = k0 >> 1;
                 const float4 wa0 = *reinterpret_cast<const float4*>(Ws + (((kp + 0) * 2 + 0) * UNITS + u) * 4);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 const float4 wa1 = *reinterpret_cast<const float4*>(Ws + (((kp + 1) * 2 + 0) * UNITS + u) * 4);
                 const float4 wb1 = *reinterpret_cast<const float4*>(Ws + (((kp + 1) * 2 + 1) * UNITS + u) * 4);
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) {
+                for (int bb = 0; bb < GB; ++bb) {
                     const float4 h4 = *reinterpret_cast<const float4*>(Hc + bb * H + k0);
                     const float2 h01 = make_float2(h4.x, h4.y), h23 = make_float2(h4.z, h4.w);
                     acc2[0][bb] = __ffma2_rn(h01, make_float2(wa0.x, wa0.y), acc2[0][bb]);
@@ -122,17 +122,17 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     acc2[3][bb] = __ffma2_rn(h23, make_float2(wb1.z, wb1.w), acc2[3][bb]);
                 }
             }
-            float acc[4][LSTM_GB];
+            float acc[4][GB];
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) acc[gg][bb] = acc2[gg][bb].x + acc2[gg][bb].y;
+                for (int bb = 0; bb < GB; ++bb) acc[gg][bb] = acc2[gg][bb].x + acc2[gg][bb].y;
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(hs_empty + hb);           // this warp is done with the h slot
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb) {
+                for (int bb = 0; bb < GB; ++bb) {
                     float v = acc[gg][bb];
 #pragma unroll
                     for (int o = UNITS; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 }
             tc::mbar_wait(red_empty + rb, (uint32_t)((n >> 1) & 1) ^ 1);
             if (ks == 0) {
-                float* rd = red + (size_t)rb * 8 * LSTM_GB * COLS;
+                float* rd = red + (size_t)rb * 8 * GB * COLS;
 #pragma unroll
-                for (int bb = 0; bb < LSTM_GB; ++bb)
-                    *reinterpret_cast<float4*>(rd + (warp * LSTM_GB + bb) * COLS + u * 4) =
+                for (int bb = 0; bb < GB; ++bb)
+                    *reinterpret_cast<float4*>(rd + (warp * GB + bb) * COLS + u * 4) =
                         make_float4(acc[0][bb], acc[1][bb], acc[2][bb], acc[3][bb]);
             }
             __syncwarp();
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n_items) {
                 const int t = i / ng, g = i - t * ng;
-                const int b0 = g * LSTM_GB;
+                const int b0 = g * GB;
                 if (active && b0 + fbb < B)
                     v = __ldcs(reinterpret_cast<const float4*>(p.gx + ((long long)(b0 + fbb) * T + t) * 4 * H + (long long)(j0 + fu) * 4));
             }
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         float4 gxv = load_gx(pair);
         for (int i = pair; i < n_items; i += 2) {
             const int t = i / ng, g = i - t * ng;
-            const int b0 = g * LSTM_GB;
-            const int nb = min(LSTM_GB, B - b0);
+            const int b0 = g * GB;
+            const int nb = min(GB, B - b0);
             const bool mine = active && fbb < nb;
             const float4 gx_next = load_gx(i + 2);               // in flight while this item is reduced
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
@@ -177,11 +177,11 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 const int n = i - ng, rb = n & 1;
                 tc::mbar_wait(red_full + rb, (uint32_t)((n >> 1) & 1));
                 if (mine) {
-                    const float* rd = red + (size_t)rb * 8 * LSTM_GB * COLS;
+                    const float* rd = red + (size_t)rb * 8 * GB * COLS;
                     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int w8 = 0; w8 < 8; ++w8) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(rd + (w8 * LSTM_GB + fbb) * COLS + fu * 4);
+                        const float4 r4 = *reinterpret_cast<const float4*>(rd + (w8 * GB + fbb) * COLS + fu * 4);
                         s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
                     }
                     g4[0] += s4.x; g4[1] += s4.y; g4[2] += s4.z; g4[3] += s4.w;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             if (mine) {
                 const int b = b0 + fbb, j = j0 + fu;
                 const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
-                float* cp = cS + (g * LSTM_GB + fbb) * UNITS + fu;
+                float* cp = cS + (g * GB + fbb) * UNITS + fu;
                 const float c = fg * (*cp) + ig * gg;
                 *cp = c;
                 const float h = og * tanhf(c);
@@ -221,13 +221,13 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             for (int i = ng; i < n_items; ++i) {
                 const int t = i / ng, g = i - t * ng;
                 const int n = i - ng, hb = n % LSTM_NBUF;
-                const int b0 = g * LSTM_GB;
-                const int nb = min(LSTM_GB, B - b0);
+                const int b0 = g * GB;
+                const int nb = min(GB, B - b0);
                 tc::mbar_wait(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1);
                 while (ld_acquire_u32(p.barrier + g) < (unsigned)t * nctas) { }
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
-                float* dst = Hs + hb * LSTM_GB * H;
+                float* dst = Hs + hb * GB * H;
                 for (int bb = 0; bb < nb; ++bb)
                     tc::bulk_g2s(dst + bb * H, p.h_seq + ((long long)(b0 + bb) * T + (t - 1)) * H, (uint32_t)(H * 4), hs_full + hb);
             }
@@ -235,24 +235,27 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
 }
 
-size_t lstm_seq_smem_bytes(int H, int B, int units) {
-    const int ng = (B + LSTM_GB - 1) / LSTM_GB;
-    const size_t cs = ((size_t)ng * LSTM_GB * units + 3) & ~(size_t)3;
-    return ((size_t)H * 4 * units + (size_t)LSTM_NBUF * LSTM_GB * H + 2 * 8 * 4 * units * LSTM_GB + cs) * sizeof(float) +
+size_t lstm_seq_smem_bytes(int H, int B, int units, int gb) {
+    const int ng = (B + gb - 1) / gb;
+    const size_t cs = ((size_t)ng * gb * units + 3) & ~(size_t)3;
+    return ((size_t)H * 4 * units + (size_t)LSTM_NBUF * gb * H + 2 * 8 * 4 * units * gb + cs) * sizeof(float) +
            (2 * LSTM_NBUF + 4) * 8 + 64;
 }
 
+// clip-group size: small batches use 4-clip groups so that >= 4 independent items hide the publish -> poll -> copy chain
+static int lstm_pick_gb(int B) { return B <= 16 ? 4 : 8; }
+
 int lstm_pick_units(int H) {
     // largest slice that fits shared memory while keeping >= 96 CTAs busy when H allows it
-    if (H % 8 == 0 && lstm_seq_smem_bytes(H, 16, 8) <= 220 * 1024 && H / 8 >= 96) return 8;
-    if (H % 4 == 0 && lstm_seq_smem_bytes(H, 16, 4) <= 220 * 1024) return 4;
+    if (H % 8 == 0 && lstm_seq_smem_bytes(H, 16, 8, LSTM_GB_MAX) <= 220 * 1024 && H / 8 >= 96) return 8;
+    if (H % 4 == 0 && lstm_seq_smem_bytes(H, 16, 4, LSTM_GB_MAX) <= 220 * 1024) return 4;
     return 0;
 }
 
-template <int UNITS>
+template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
-    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS);
-    auto kern = lstm_seq_kernel<UNITS>;
+    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB);
+    auto kern = lstm_seq_kernel<UNITS, GB>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
@@ -260,7 +263,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
         attr_done = true;
     }
     if (smem > 225 * 1024) return cudaErrorInvalidConfiguration;
-    if ((p.B + LSTM_GB - 1) / LSTM_GB > LSTM_MAX_GROUPS) return cudaErrorInvalidValue;
+    if ((p.B + GB - 1) / GB > LSTM_MAX_GROUPS) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(p.barrier, 0, LSTM_MAX_GROUPS * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
     dim3 grid(p.H / UNITS), block(LSTM_THREADS);
@@ -272,8 +275,11 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
 cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (p.H % 4 != 0) return cudaErrorInvalidValue;
     const int units = lstm_pick_units(p.H);
-    if (units == 8) return launch_seq<8>(p, st);
-    if (units == 4) return launch_seq<4>(p, st);
+    const int gb = lstm_pick_gb(p.B);
+    if (units == 8 && gb == 8) return launch_seq<8, 8>(p, st);
+    if (units == 8 && gb == 4) return launch_seq<8, 4>(p, st);
+    if (units == 4 && gb == 8) return launch_seq<4, 8>(p, st);
+    if (units == 4 && gb == 4) return launch_seq<4, 4>(p, st);
     return cudaErrorInvalidConfiguration;
 }
 
