@@ -32,6 +32,9 @@ WORKLOADS = {
     "config5": ("encodec_16k_n32_ds640", 64, 160000, None),
 }
 # SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 48 conv launches of ONE config-2 step, from the
+# `ncu --set full` capture summarised in profiles/conv_ncu_r1n.txt (11.74 GB read + 6.98 GB written)
+NCU_CONV_TRAFFIC = {"config2": 18.72e9}
 ALGO = {
     "encodec_16k_n32_ds640": dict(conv_bytes_per_10s=1066.6e6, conv_gmac_per_10s=33.10, lstm_gmac_per_10s=8.39,
                                   rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
@@ -344,7 +347,9 @@ def main():
                                             "the tensor cores): all SEANet conv/convtr launches of one step = "
                                             "encoder_conv + decoder_conv phases",
                         achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                        traffic=None, peak_source=peaks["source"], algorithmic_bytes=conv_bytes,
+                        traffic=NCU_CONV_TRAFFIC.get(args.workload) if not args.batch else None,
+                        traffic_source="profiles/conv_ncu_r1n.txt (ncu --set full, 48 conv launches of one step)",
+                        peak_source=peaks["source"], algorithmic_bytes=conv_bytes,
                         kernel_ms_per_step=conv_ms, conv_fp32_tflops=conv_tflops)
         cpu = None
         if not args.no_cpu_baseline:
