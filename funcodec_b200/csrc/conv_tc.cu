@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
                     }
                 }
-                mbar_wait(a_empty + as, par);
+                mbar_wait_backoff(a_empty + as, par, 64);
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 32 * i;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 int chunk = 0, ph = 0;
                 for (int unit = 0; unit < n_units; ++unit) {
                     for (int k = ph; k < K; k += S) {
-                        if (!w_resident) mbar_wait(b_empty + bs, bphase ^ 1);
+                        if (!w_resident) mbar_wait_backoff(b_empty + bs, bphase ^ 1, 64);
                         mbar_arrive_expect_tx(b_full + bs, bytes);
                         bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
                         if (++bs == nb_stages) { bs = 0; bphase ^= 1; }
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             for (int g = 0; g < n_groups; ++g, ++gcount) {
                 const int buf = (int)(gcount & 1);
                 const bool last = (g == n_groups - 1);
-                mbar_wait(acc_full + buf, (gcount >> 1) & 1);
+                mbar_wait_backoff(acc_full + buf, (gcount >> 1) & 1, 128);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
             if (t > 0) {
                 const int n = i - ng, rb = n & 1;
-                tc::mbar_wait(red_full + rb, (uint32_t)((n >> 1) & 1));
+                tc::mbar_wait_backoff(red_full + rb, (uint32_t)((n >> 1) & 1), 64);
                 if (mine) {
                     const float* rd = red + (size_t)rb * 8 * GB * COLS;
                     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 const int n = i - ng, hb = n % LSTM_NBUF;
                 const int b0 = g * GB;
                 const int nb = min(GB, B - b0);
-                tc::mbar_wait(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1);
+                tc::mbar_wait_backoff(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1, 64);
                 while (ld_acquire_u32(p.barrier + g) < (unsigned)t * nctas) { }
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));

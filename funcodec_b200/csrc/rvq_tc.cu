@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
             int i1 = 0x7fffffff, i2 = 0x7fffffff;
             for (int nt = 0; nt < n_nt; ++nt, ++tcount) {
                 const int buf = (int)(tcount & 1);
-                mbar_wait(acc_full + buf, (uint32_t)((tcount >> 1) & 1));
+                mbar_wait_backoff(acc_full + buf, (uint32_t)((tcount >> 1) & 1), 64);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int c0 = 0; c0 < RQ_N; c0 += 32) {
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
                 for (int nt = 0; nt < n_nt; ++nt)
                     for (int ch = 0; ch < n_chunks; ++ch, ++it) {
                         const int bs = (int)(it % RQ_NB);
-                        mbar_wait(b_empty + bs, (uint32_t)((it / RQ_NB) & 1) ^ 1);
+                        mbar_wait_backoff(b_empty + bs, (uint32_t)((it / RQ_NB) & 1) ^ 1, 64);
                         mbar_arrive_expect_tx(b_full + bs, (uint32_t)slab_bytes);
                         bulk_g2s(smB + bs * slab_bytes, qbase + ((long long)nt * n_chunks + ch) * slab_bytes, (uint32_t)slab_bytes, b_full + bs);
                     }

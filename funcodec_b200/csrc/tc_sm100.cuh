@@ -39,6 +39,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// Same, with a back-off between polls: for waiters that are NOT on the critical path (a spinning warp still takes
+// issue slots away from the producer warps of its SM sub-partition).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try_wait(bar, parity)) { __nanosleep(ns); }
+}
 
 // generic-proxy writes (st.shared by threads) -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
