@@ -1,0 +1,134 @@
+"""Host-side plumbing around the hot path: what `funcodec/bin/codec_inference.py` does between
+the scp files and the model -- wrap-padded variable-length batches, the `codecs.txt` JSONL format, peak-limited PCM16
+output -- so that `encoding_decoding.sh`-style runs work end to end on top of B200Encodec.  Pure host logic (numpy /
+stdlib); no CUDA here.
+
+References: collate with pad_mode="wrap" `funcodec/bin/codec_inference.py:257-261` -> `funcodec/modules/nets_utils.py:65-98`;
+`write_indices` `codec_inference.py:288-299`; `load_codec_json` `funcodec/datasets/iterable_dataset.py:54-58`;
+per-utterance trimming `codec_inference.py:358-367`; `save_audio` `:153-161`.
+"""
+import json
+import os
+import wave
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def wrap_pad_batch(clips: Sequence[np.ndarray]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """pad_list_with_mod(mode="wrap"): short clips are extended by repeating themselves from the start; RMS and
+    GroupNorm then run over the padded length (as in the reference) and outputs are trimmed by `lengths`."""
+    lengths = torch.tensor([int(c.shape[0]) for c in clips], dtype=torch.int64)
+    max_len = int(lengths.max())
+    out = [np.pad(np.asarray(c, dtype=np.float32), (0, max_len - c.shape[0]), mode="wrap") for c in clips]
+    return torch.from_numpy(np.stack(out, axis=0)), lengths
+
+
+def format_indices_line(key: str, code_indices: List[torch.Tensor], batch_id: int, length: int) -> str:
+    """`write_indices`: one line `uttid [[[q0 codes...],[q1 codes...],...]]` (n_frame x n_q x T', n_frame == 1)."""
+    to_write = [x[:, batch_id, :length].cpu().numpy().tolist() for x in code_indices]
+    return key + " " + json.dumps(to_write) + "\n"
+
+
+def parse_indices_line(line: str) -> Tuple[str, np.ndarray]:
+    """Inverse of format_indices_line via the reference's load_codec_json: returns (key, codes [T', n_q])."""
+    key, json_str = line.strip().split(" ", 1)
+    array = np.array(json.loads(json_str))
+    if array.ndim == 3:
+        array = array[0]
+    return key, array.T
+
+
+def peak_limit(wav: torch.Tensor, rescale: bool = True, limit: float = 0.99) -> torch.Tensor:
+    """`save_audio`'s amplitude handling: rescale so that the peak is <= 0.99, or clamp."""
+    mx = wav.abs().max()
+    if rescale:
+        return wav * min(limit / float(mx), 1.0) if float(mx) > 0 else wav
+    return wav.clamp(-limit, limit)
+
+
+def save_wav_pcm16(path: str, wav: torch.Tensor, sample_rate: int, rescale: bool = True) -> None:
+    """16-bit PCM mono wav (the reference calls torchaudio.save(encoding='PCM_S', bits_per_sample=16))."""
+    x = peak_limit(wav.detach().cpu().float().reshape(-1), rescale).numpy()
+    pcm = np.clip(np.round(x * 32768.0), -32768, 32767).astype("<i2")
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(sample_rate)
+        f.writeframes(pcm.tobytes())
+
+
+def load_wav(path: str) -> Tuple[np.ndarray, int]:
+    with wave.open(path, "rb") as f:
+        assert f.getsampwidth() == 2, "only 16-bit PCM is supported by this loader"
+        sr, n, ch = f.getframerate(), f.getnframes(), f.getnchannels()
+        data = np.frombuffer(f.readframes(n), dtype="<i2").astype(np.float32) / 32768.0
+    if ch > 1:
+        data = data.reshape(-1, ch).mean(axis=1)
+    return data, sr
+
+
+def read_scp(path: str) -> List[Tuple[str, str]]:
+    out = []
+    with open(path, "rt", encoding="utf-8") as f:
+        for line in f:
+            line = line.strip()
+            if line:
+                k, v = line.split(maxsplit=1)
+                out.append((k, v))
+    return out
+
+
+def batches(items: Sequence, batch_size: int) -> Iterator[Sequence]:
+    for i in range(0, len(items), batch_size):
+        yield items[i: i + batch_size]
+
+
+def run_encode(s2t, wav_scp: str, output_dir: str, batch_size: int = 16, bit_width: Optional[int] = None,
+               run_mod: str = "encode", use_scale: bool = False, save_recon: bool = False) -> int:
+    """`--run_mod encode|inference`: wav.scp -> codecs.txt (+ reconstructed wavs).  Returns the number of utterances."""
+    os.makedirs(output_dir, exist_ok=True)
+    hop = s2t.model.quantizer.encoder_hop_length
+    sr_model = s2t.model.quantizer.sampling_rate
+    n = 0
+    with open(os.path.join(output_dir, "codecs.txt"), "wt") as fout:
+        for group in batches(read_scp(wav_scp), batch_size):
+            clips = []
+            for key, path in group:
+                x, sr = load_wav(path)
+                if sr != sr_model:
+                    raise ValueError(f"{key}: sample rate {sr} != model rate {sr_model} (resampling is out of scope)")
+                clips.append(x)
+            speech, lengths = wrap_pad_batch(clips)
+            codes, _, recon, _ = s2t(speech, need_recon=True, bit_width=bit_width, use_scale=use_scale, run_mod=run_mod)
+            for i, (key, _) in enumerate(group):
+                ilen = int(lengths[i])
+                codec_len = -(-ilen // hop)
+                fout.write(format_indices_line(key, codes, i, codec_len))
+                if save_recon and recon is not None:
+                    save_wav_pcm16(os.path.join(output_dir, key if key.endswith(".wav") else key + ".wav"),
+                                   recon[i].cpu()[:, :ilen], sr_model, rescale=True)
+                n += 1
+    return n
+
+
+def run_decode(s2t, codecs_txt: str, output_dir: str, batch_size: int = 16, bit_width: Optional[int] = None) -> int:
+    """`--run_mod decode`: codecs.txt -> wavs.  Code sequences of different lengths are wrap-padded like the reference's
+    collate (int arrays) and the output is trimmed to codec_len * hop."""
+    os.makedirs(output_dir, exist_ok=True)
+    hop = s2t.model.quantizer.encoder_hop_length
+    sr_model = s2t.model.quantizer.sampling_rate
+    with open(codecs_txt, "rt") as f:
+        items = [parse_indices_line(line) for line in f if line.strip()]
+    n = 0
+    for group in batches(items, batch_size):
+        lens = [c.shape[0] for _, c in group]
+        tmax = max(lens)
+        toks = np.stack([np.pad(c, ((0, tmax - c.shape[0]), (0, 0)), mode="wrap") for _, c in group], axis=0)
+        _, _, recon, _ = s2t(torch.from_numpy(toks.astype(np.int64)), bit_width=bit_width, run_mod="decode")
+        for i, (key, _) in enumerate(group):
+            save_wav_pcm16(os.path.join(output_dir, key if key.endswith(".wav") else key + ".wav"),
+                           recon[i].cpu()[:, : lens[i] * hop], sr_model, rescale=True)
+            n += 1
+    return n

@@ -1,0 +1,37 @@
+"""Host plumbing (funcodec_b200/pipeline.py) against the reference's formats -- CPU only."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from funcodec_b200 import pipeline as P
+
+
+def test_wrap_pad_matches_numpy_wrap():
+    clips = [np.arange(5, dtype=np.float32), np.arange(12, dtype=np.float32), np.arange(1, dtype=np.float32) + 7]
+    x, lens = P.wrap_pad_batch(clips)
+    assert x.shape == (3, 12) and lens.tolist() == [5, 12, 1]
+    assert x[0].tolist() == [0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 0, 1]       # nets_utils.pad_list_with_mod(mode="wrap")
+    assert x[2].tolist() == [7.0] * 12
+
+
+def test_codecs_txt_roundtrip_matches_reference_loader():
+    g = torch.Generator().manual_seed(0)
+    codes = torch.randint(0, 1024, (4, 3, 9), generator=g)             # [n_q, B, T']
+    line = P.format_indices_line("utt_01", [codes], batch_id=1, length=7)
+    key, js = line.strip().split(" ", 1)
+    assert key == "utt_01" and json.loads(js) == [codes[:, 1, :7].tolist()]
+    k2, arr = P.parse_indices_line(line)                                # == load_codec_json: [T', n_q]
+    assert k2 == "utt_01" and arr.shape == (7, 4) and np.array_equal(arr, codes[:, 1, :7].numpy().T)
+
+
+def test_peak_limit_and_wav_io(tmp_path):
+    w = torch.tensor([[0.5, -2.0, 1.0]])
+    assert torch.allclose(P.peak_limit(w, rescale=True), w * (0.99 / 2.0))
+    assert P.peak_limit(w, rescale=False).abs().max().item() <= 0.99 + 1e-6
+    path = os.path.join(tmp_path, "a.wav")
+    x = torch.sin(torch.arange(1600) / 10.0) * 0.5
+    P.save_wav_pcm16(path, x.view(1, -1), 16000, rescale=True)
+    y, sr = P.load_wav(path)
+    assert sr == 16000 and np.abs(y - x.numpy()).max() <= 1.0 / 32768 + 1e-6
