@@ -345,11 +345,9 @@ int conv_cout1_num_parts(int T_out) { return (T_out + C1_TILE - 1) / C1_TILE; }
 
 cudaError_t launch_conv_cout1(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
     const size_t smem = (((size_t)p.K * p.C_in + 3) & ~(size_t)3) * 4 + (size_t)(C1_TILE + p.K - 1) * (p.C_in + 1) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv1d_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)conv1d_cout1_kernel, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     dim3 grid(conv_cout1_num_parts(p.T_out), B);
     *nparts = grid.x;
@@ -376,11 +374,9 @@ static cudaError_t launch_cfg(ConvParams p, int B, cudaStream_t st, int* nparts_
     const size_t smem = conv_smem_bytes(p, T_TILE, CO_TILE);
     if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = conv1d_cl_kernel<TX, TM, TWO>;
-    static bool attr_done = false;   // one static per template instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)kern, 220 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     dim3 grid((p.T_out + T_TILE - 1) / T_TILE, (p.C_out + CO_TILE - 1) / CO_TILE, B);
     *nparts_out = grid.x * grid.y;

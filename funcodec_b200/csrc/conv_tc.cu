@@ -390,11 +390,9 @@ static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0;
 template <int N_TILE>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
     auto kern = conv1d_tc_kernel<N_TILE>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
     kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);

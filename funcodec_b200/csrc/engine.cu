@@ -269,25 +269,46 @@ int pack_resblock(fcb_handle* h, const std::string& prefix, int dim, ResBlockW* 
 }
 
 // ------------------------------------------------------------------------------------------- run helpers
+// One API call.  Every temporary comes from the stream-ordered pool through pool_alloc and is tracked here, so an
+// early return on an error path cannot leak: whatever is still live is returned to the pool by the destructor.
 struct Run {
     fcb_handle* h;
     int B;
     cudaStream_t st;
     int phase = -1;
+    std::vector<void*> live;
+    Run(fcb_handle* h_, int B_, cudaStream_t st_) : h(h_), B(B_), st(st_) {}
+    Run(const Run&) = delete;
+    Run& operator=(const Run&) = delete;
+    ~Run() {
+        for (void* p : live) cudaFreeAsync(p, st);
+    }
 };
 
-int alloc_f(Run& r, float** p, size_t n) {
+int pool_alloc(Run& r, void** p, size_t bytes) {
     fcb_handle* h = r.h;
-    FCB_CK(cudaMallocAsync((void**)p, n * sizeof(float), r.st));
+    FCB_CK(cudaMallocAsync(p, bytes, r.st));
+    r.live.push_back(*p);
     return FCB_OK;
 }
+
+int pool_free(Run& r, void* p) {
+    fcb_handle* h = r.h;
+    if (!p) return FCB_OK;
+    for (size_t i = 0; i < r.live.size(); ++i)
+        if (r.live[i] == p) { r.live[i] = r.live.back(); r.live.pop_back(); break; }
+    FCB_CK(cudaFreeAsync(p, r.st));
+    return FCB_OK;
+}
+
+int alloc_f(Run& r, float** p, size_t n) { return pool_alloc(r, (void**)p, n * sizeof(float)); }
 
 int release(Run& r, Act& a) {
     fcb_handle* h = r.h;
     if (a.owned) {
-        if (a.p) FCB_CK(cudaFreeAsync(a.p, r.st));
-        if (a.stats) FCB_CK(cudaFreeAsync(a.stats, r.st));
-        if (a.coef) FCB_CK(cudaFreeAsync(a.coef, r.st));
+        FCB_TRY(pool_free(r, a.p));
+        FCB_TRY(pool_free(r, a.stats));
+        FCB_TRY(pool_free(r, a.coef));
     }
     a = Act();
     return FCB_OK;
@@ -366,7 +387,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out)
                           : (c1 ? conv_cout1_num_parts(p.T_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B));
     if (want_norm) {
-        FCB_CK(cudaMallocAsync((void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double), r.st));
+        FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double)));
         FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
         FCB_TRY(alloc_f(r, &o.coef, (size_t)r.B * 2 * o.C));
         o.gamma = L.gamma; o.beta = L.beta;
@@ -382,7 +403,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         FCB_CK(launch_stats_finalize(partials, nparts, (double)p.T_out * p.C_out, h->cfg.gn_eps, 0, o.stats, r.B, r.st,
                                      L.gamma, L.beta, o.C, o.coef));
         h->launches++;
-        FCB_CK(cudaFreeAsync(partials, r.st));
+        FCB_TRY(pool_free(r, partials));
     }
     *out = o;
     return FCB_OK;
@@ -446,12 +467,12 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
     if (h->cfg.audio_normalize) {
         double* partials = nullptr;
         int nparts = sumsq_num_parts(L), np2 = 0;
-        FCB_CK(cudaMallocAsync((void**)&partials, (size_t)B * nparts * 2 * sizeof(double), r.st));
+        FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)B * nparts * 2 * sizeof(double)));
         if (scale_out) scale = scale_out; else { FCB_TRY(alloc_f(r, &scale, B)); scale_owned = true; }
         FCB_CK(launch_sumsq_partials(wav, B, L, partials, &np2, r.st));
         FCB_CK(launch_stats_finalize(partials, nparts, (double)L, 0.f, 1, scale, B, r.st));
         h->launches += 2;
-        FCB_CK(cudaFreeAsync(partials, r.st));
+        FCB_TRY(pool_free(r, partials));
     } else if (scale_out) {
         FCB_CK(launch_fill(scale_out, 1.0f, B, r.st));
         h->launches++;
@@ -460,7 +481,7 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
     x.p = const_cast<float*>(wav); x.T = L; x.C = 1; x.clip_stride = L;
     Act a;
     FCB_TRY(run_conv(r, x, nullptr, false, scale, h->enc_conv0, true, &a));
-    if (scale_owned) FCB_CK(cudaFreeAsync(scale, r.st));
+    if (scale_owned) FCB_TRY(pool_free(r, scale));
     for (size_t i = 0; i < h->enc_rb.size(); ++i) {
         Act sc, blk, d;
         FCB_TRY(run_resblock(r, a, h->enc_rb[i], &sc, &blk));
@@ -492,6 +513,7 @@ int run_decoder(Run& r, const float* emb, int n_frames, const float* scale, floa
     fcb_handle* h = r.h;
     const int hop = h->hop();
     if (out_len > n_frames * hop || out_len <= 0) return fail(h, FCB_E_INVALID, "out_len must be in (0, T'*hop]");
+    if (r.B > 512) return fail(h, FCB_E_INVALID, "decode: at most 512 clips per call (split the batch)");
     Act e;
     e.p = const_cast<float*>(emb); e.T = n_frames; e.C = h->cfg.dimension; e.clip_stride = (long long)n_frames * e.C;
     FCB_TRY(phase_begin(r, FCB_PHASE_DECODER_LSTM));
@@ -540,6 +562,7 @@ int do_encode(fcb_handle* h, const float* wav, int B, int L, int n_q, int64_t* c
               float* sub_quants, float* encoder_out, cudaStream_t st) {
     if (!wav || !codes || B <= 0 || L <= 0) return fail(h, FCB_E_INVALID, "fcb_encode: bad arguments");
     if (n_q <= 0 || n_q > h->cfg.num_quantizers) return fail(h, FCB_E_INVALID, "fcb_encode: n_q out of range");
+    if (B > 512) return fail(h, FCB_E_INVALID, "fcb_encode: at most 512 clips per call (split the batch)");
     Run r{h, B, st};
     Act f;
     FCB_TRY(run_encoder(r, wav, L, scale, &f));
@@ -756,7 +779,7 @@ int fcb_decode_codes(fcb_handle* h, const int64_t* codes, int32_t B, int32_t n_f
     h->launches++;
     FCB_TRY(phase_end(r));
     int rc = run_decoder(r, emb, n_frames, nullptr, wav_out, out_len);
-    if (!emb_out) FCB_CK(cudaFreeAsync(emb, st));
+    if (!emb_out) FCB_TRY(pool_free(r, emb));
     return rc;
 }
 
@@ -777,8 +800,8 @@ int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t
         const bool apply = use_scale && h->cfg.audio_normalize;
         rc = run_decoder(r, q, Tf, apply ? sc : nullptr, recon, L);
     }
-    if (!quant) FCB_CK(cudaFreeAsync(q, st));
-    if (!scale) FCB_CK(cudaFreeAsync(sc, st));
+    if (!quant) FCB_TRY(pool_free(r, q));
+    if (!scale) FCB_TRY(pool_free(r, sc));
     return rc;
 }
 
@@ -794,16 +817,16 @@ int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t 
     int64_t* d_codes;
     FCB_TRY(alloc_f(r, &d_wav, (size_t)B * L));
     FCB_TRY(alloc_f(r, &d_recon, (size_t)B * L));
-    FCB_CK(cudaMallocAsync((void**)&d_codes, (size_t)n_q * B * Tf * sizeof(int64_t), st));
+    FCB_TRY(pool_alloc(r, (void**)&d_codes, (size_t)n_q * B * Tf * sizeof(int64_t)));
     FCB_CK(cudaMemcpyAsync(d_wav, wav_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = fcb_roundtrip(h, d_wav, B, L, n_q, use_scale, d_codes, nullptr, nullptr, nullptr, d_recon, stream);
     if (rc == FCB_OK) {
         FCB_CK(cudaMemcpyAsync(codes_host, d_codes, (size_t)n_q * B * Tf * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         FCB_CK(cudaMemcpyAsync(recon_host, d_recon, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    FCB_CK(cudaFreeAsync(d_wav, st));
-    FCB_CK(cudaFreeAsync(d_recon, st));
-    FCB_CK(cudaFreeAsync(d_codes, st));
+    FCB_TRY(pool_free(r, d_wav));
+    FCB_TRY(pool_free(r, d_recon));
+    FCB_TRY(pool_free(r, d_codes));
     FCB_CK(cudaStreamSynchronize(st));
     return rc;
 }

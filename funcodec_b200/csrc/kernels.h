@@ -6,6 +6,9 @@
 
 namespace fcb {
 
+// misc.cu: opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device); thread-safe.
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
+
 // conv_simt.cu
 void conv_pick_tile(int T_out, int C_out, int C_in, int K, int B, int* tx, int* tm, bool* two);
 int conv_num_parts(int T_out, int C_out, int C_in, int K, int B);

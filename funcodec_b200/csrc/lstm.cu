@@ -256,11 +256,9 @@ template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB);
     auto kern = lstm_seq_kernel<UNITS, GB>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     if (smem > 225 * 1024) return cudaErrorInvalidConfiguration;
     if ((p.B + GB - 1) / GB > LSTM_MAX_GROUPS) return cudaErrorInvalidValue;

@@ -186,11 +186,9 @@ cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st) {
     if (p.D % 4 != 0) return cudaErrorInvalidValue;
     const int pitch = p.D + 4;
     const size_t smem = ((size_t)(2 * RVQ_ROWS + RVQ_CHUNK) * pitch + RVQ_ROWS) * sizeof(float) + RVQ_ROWS * sizeof(int);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)rvq_kernel, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const long long M = (long long)p.B * p.T;
     rvq_kernel<<<(unsigned)((M + RVQ_ROWS - 1) / RVQ_ROWS), 256, smem, st>>>(p);

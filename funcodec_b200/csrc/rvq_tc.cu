@@ -300,11 +300,9 @@ bool rvq_tc_supported(int D, int K) {
 cudaError_t launch_rvq_tc(const RvqParams& p, cudaStream_t st) {
     if (!rvq_tc_supported(p.D, p.K) || !p.embed_tc) return cudaErrorInvalidValue;
     const RqSmem L = rq_layout(p.D, p.K);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    {
+        cudaError_t e = ensure_dynamic_smem((const void*)rvq_tc_kernel, 225 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const long long M = (long long)p.B * p.T;
     rvq_tc_kernel<<<(unsigned)((M + RQ_M - 1) / RQ_M), RQ_THREADS, L.total, st>>>(p);
