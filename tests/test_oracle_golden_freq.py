@@ -1,0 +1,23 @@
+"""Pins the FreqCodec (mag_phase, BASELINE config 4) oracle against vectors produced by the UNMODIFIED reference
+(tools/gen_golden_freq.py).  CPU only.  The CUDA path for this variant is round-2 work; the oracle is ready for it."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.freqcodec_oracle import OracleFreqCodec
+
+
+def test_freqcodec_magphase_oracle_vs_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "freq_magphase_small.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    o = OracleFreqCodec(sd, [tuple(r) for r in z["ratios"]])
+    wav = torch.from_numpy(z["wav"])
+    r = o.inference(wav, want_margin=True)
+    assert r["features"].shape[1:3] == (3, 257)
+    assert np.abs(r["encoder_out"].numpy() - z["encoder_out"]).max() <= 5e-6
+    assert np.array_equal(r["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert np.abs(r["code_embeddings"][0][0].numpy() - z["quant"]).max() <= 5e-6
+    assert np.abs(r["code_embeddings"][0][1].numpy() - z["scale"]).max() <= 1e-7
+    assert r["recon_speech"].shape == z["recon"].shape
+    assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 5e-6

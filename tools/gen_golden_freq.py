@@ -1,0 +1,64 @@
+"""Golden vectors for the FreqCodec (mag_phase) path from the UNMODIFIED reference (build container only).
+Weights: the reference modules' own default init under torch.manual_seed, stored in the fixture for the small config
+(a few hundred KB) so the oracle test needs nothing else."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from ref_harness import import_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def build(n_filters, dimension, K, nq, ratios):
+    import_reference()
+    from funcodec.models import codec_freq
+    codec_freq.check_argument_types = lambda: True
+    from funcodec.models.encoder.seanet_encoder import SEANetEncoder2d
+    from funcodec.models.decoder.seanet_decoder import SEANetDecoder2d
+    from funcodec.models.quantizer.costume_quantizer import CostumeQuantizer
+    torch.manual_seed(5)
+    enc = SEANetEncoder2d(input_size=3, dimension=dimension, n_filters=n_filters, ratios=ratios, norm="time_group_norm",
+                          norm_params={"num_groups": 1}, causal=False, dilation_base=1)
+    dec = SEANetDecoder2d(input_size=dimension, channels=3, n_filters=n_filters, ratios=ratios, norm="time_group_norm",
+                          norm_params={"num_groups": 1}, causal=False, dilation_base=1)
+    q = CostumeQuantizer(input_size=dimension, codebook_size=K, num_quantizers=nq, kmeans_init=False, sampling_rate=16000,
+                         encoder_hop_length=320, use_ddp=True)
+    m = codec_freq.FreqCodec(input_size=3, odim=dimension, encoder=enc, quantizer=q, decoder=dec, discriminator=None,
+                             target_sample_hz=16000, multi_spectral_window_powers_of_two=[], audio_normalize=True,
+                             segment_dur=None, overlap_ratio=None, codec_domain=["mag_phase", "mag_phase"])
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for name, par in m.named_parameters():
+            if name.endswith("norm.weight"):
+                par.copy_(1 + 0.1 * torch.randn(par.shape, generator=g))
+            elif name.endswith("norm.bias"):
+                par.copy_(0.1 * torch.randn(par.shape, generator=g))
+        m.quantizer.rq.model.embed.copy_(torch.randn(nq, K, dimension, generator=g) * (0.6 * 0.9 ** torch.arange(nq).float()).view(nq, 1, 1))
+        m.quantizer.rq.model.inited.fill_(1)
+    return m.eval()
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    ratios = [[4, 1], [4, 1], [4, 2], [4, 1]]
+    m = build(4, 32, 64, 6, ratios)
+    g = torch.Generator().manual_seed(8)
+    wav = 0.1 * torch.randn(2, 3200 + 57, generator=g)
+    with torch.no_grad():
+        r = m.inference(wav, need_recon=True, bit_width=None, use_scale=True)
+        emb, scale = m._encode(wav.unsqueeze(1))[0]
+    out = dict(wav=wav.numpy(), ratios=np.array(ratios), codes=r["code_indices"][0].numpy().astype(np.int16),
+               quant=r["code_embeddings"][0][0].numpy(), scale=r["code_embeddings"][0][1].numpy(),
+               recon=r["recon_speech"].numpy(), encoder_out=emb.numpy())
+    for k, v in m.state_dict().items():
+        if k.startswith(("encoder.", "decoder.")) or k == "quantizer.rq.model.embed":
+            out["sd." + k] = v.numpy()
+    path = os.path.join(OUT, "freq_magphase_small.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", "codes", out["codes"].shape, "recon", out["recon"].shape)
