@@ -30,6 +30,7 @@ WORKLOADS = {
     "config1": ("encodec_16k_n32_ds640", 1, 160000, None),
     "config3": ("encodec_16k_n32_ds320", 64, 480000, None),
     "config5": ("encodec_16k_n32_ds640", 64, 160000, None),
+    "config4": ("freqcodec_magphase_16k_n32_ds320", 32, 160000, None),
 }
 # SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the 48 conv launches of ONE config-2 step, from the
@@ -38,6 +39,8 @@ NCU_CONV_TRAFFIC = {"config2": 18.72e9}
 ALGO = {
     "encodec_16k_n32_ds640": dict(conv_bytes_per_10s=1066.6e6, conv_gmac_per_10s=33.10, lstm_gmac_per_10s=8.39,
                                   rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
+    "freqcodec_magphase_16k_n32_ds320": dict(conv_bytes_per_10s=803.2e6, conv_gmac_per_10s=24.95, lstm_gmac_per_10s=4.20,
+                                             rvq_gflop_per_10s_nq32=2.10, weight_bytes=64.9e6),
     "encodec_16k_n32_ds320": dict(conv_bytes_per_10s=780.1e6, conv_gmac_per_10s=15.67, lstm_gmac_per_10s=4.19,
                                   rvq_gflop_per_10s_nq32=4.19, weight_bytes=59.4e6),
 }
@@ -241,14 +244,21 @@ def main():
     codes = torch.empty((n_q, B, Tf), dtype=torch.int64, device=dev)
     quant = torch.empty((B, Tf, cfg.dimension), dtype=torch.float32, device=dev)
     scale = torch.empty((B, 1), dtype=torch.float32, device=dev)
-    recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+    Lr = min(L, cfg.decoded_length(Tf))
+    recon = torch.empty((B, 1, Lr), dtype=torch.float32, device=dev)
     import ctypes
     from funcodec_b200.encodec import _ptr
 
     def step(i):
         x = wavs[i % n_rot]
-        model._ck(model._lib.fcb_roundtrip(model._h, _ptr(x), B, L, n_q, 1, _ptr(codes), _ptr(quant), _ptr(scale),
-                                           None, _ptr(recon), model._stream()), "fcb_roundtrip")
+        if Lr == L:
+            model._ck(model._lib.fcb_roundtrip(model._h, _ptr(x), B, L, n_q, 1, _ptr(codes), _ptr(quant), _ptr(scale),
+                                               None, _ptr(recon), model._stream()), "fcb_roundtrip")
+        else:   # FreqCodec clip whose iSTFT is shorter than L: encode + decode of what exists
+            model._ck(model._lib.fcb_encode(model._h, _ptr(x), B, L, n_q, _ptr(codes), _ptr(quant), _ptr(scale), None, None,
+                                            model._stream()), "fcb_encode")
+            model._ck(model._lib.fcb_decode_emb(model._h, _ptr(quant), B, Tf, _ptr(scale), _ptr(recon), Lr, model._stream()),
+                      "fcb_decode_emb")
 
     def barrier():
         if world > 1:

@@ -20,7 +20,8 @@ class FcbConfig(Structure):
                 ("dimension", c_int32), ("kernel_size", c_int32), ("last_kernel_size", c_int32),
                 ("residual_kernel_size", c_int32), ("lstm_layers", c_int32), ("codebook_size", c_int32),
                 ("num_quantizers", c_int32), ("sample_rate", c_int32), ("audio_normalize", c_int32),
-                ("gn_eps", c_float)]
+                ("gn_eps", c_float), ("arch", c_int32), ("ratios_f", c_int32 * FCB_MAX_RATIOS), ("n_fft", c_int32),
+                ("stft_hop", c_int32)]
 
 
 class FcbError(RuntimeError):
@@ -34,6 +35,7 @@ SYMBOLS = {
     "fcb_set_tensor": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, POINTER(c_int64)]),
     "fcb_finalize": (c_int32, [c_void_p]),
     "fcb_num_frames": (c_int32, [c_void_p, c_int32]),
+    "fcb_decoded_length": (c_int32, [c_void_p, c_int32]),
     "fcb_num_quantizers_for_bandwidth": (c_int32, [c_void_p, c_double]),
     "fcb_encode": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p]),

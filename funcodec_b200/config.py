@@ -26,17 +26,32 @@ class CodecConfig:
     sample_rate: int = 16000                     # quantizer_conf.sampling_rate / target_sample_hz
     audio_normalize: bool = True                 # model_conf.audio_normalize
     gn_eps: float = 1e-5                         # nn.GroupNorm default
+    # FreqCodec variant (funcodec/models/codec_freq.py, codec_domain ['mag_phase', 'mag_phase']): arch = 1, `ratios` are then
+    # the TIME ratios and `ratios_f` the FREQUENCY ratios of encoder_conf.ratios [[f, t], ...]
+    arch: int = 0
+    ratios_f: Tuple[int, ...] = ()
+    n_fft: int = 512
+    stft_hop: int = 160
 
     @property
     def hop_length(self) -> int:
-        return int(math.prod(self.ratios))
+        h = int(math.prod(self.ratios))
+        return h * self.stft_hop if self.arch == 1 else h
 
     @property
     def top_channels(self) -> int:
         return self.n_filters * (2 ** len(self.ratios))
 
     def frames(self, length: int) -> int:
+        if self.arch == 1:                       # STFT frames (center=True) then the encoder's time strides
+            ts, tp = 1 + length // self.stft_hop, int(math.prod(self.ratios))
+            return -(-ts // tp)
         return -(-length // self.hop_length)
+
+    def decoded_length(self, n_frames: int) -> int:
+        if self.arch == 1:                       # torch.istft(center=True, length=None)
+            return self.stft_hop * (n_frames * int(math.prod(self.ratios)) - 1)
+        return n_frames * self.hop_length
 
     def bandwidth_per_quantizer(self) -> float:
         """ResidualVectorQuantizer.get_bandwidth_per_quantizer (funcodec/modules/quantization/vq.py:114-117)."""
@@ -61,6 +76,12 @@ PRESETS: Dict[str, CodecConfig] = {
     # small shapes for parity tests (same topology, every kernel family exercised)
     "tiny_ds40": CodecConfig(name="tiny_ds40", ratios=(5, 4, 2), n_filters=8, dimension=32,
                              codebook_size=64, num_quantizers=8),
+    # BASELINE.json config 4: repo YAML conf/freqcodec_mag_phase_16k_n32_600k_step.yaml (ratios [[4,1],[4,1],[4,2],[4,1]],
+    # conv groups = 1 -- the hub model's gr8 grouping is not in the repository)
+    "freqcodec_magphase_16k_n32_ds320": CodecConfig(name="freqcodec_magphase_16k_n32_ds320", arch=1, ratios=(1, 1, 2, 1),
+                                                    ratios_f=(4, 4, 4, 4)),
+    "freq_small": CodecConfig(name="freq_small", arch=1, ratios=(1, 1, 2, 1), ratios_f=(4, 4, 4, 4), n_filters=4,
+                              dimension=32, codebook_size=64, num_quantizers=6),
     "small_ds320": CodecConfig(name="small_ds320", ratios=(8, 5, 4, 2), n_filters=8, dimension=64,
                                codebook_size=256, num_quantizers=8),
 }

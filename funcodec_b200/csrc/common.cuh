@@ -44,6 +44,30 @@ struct ConvParams {
     int cic;                 // input-channel chunk staged per iteration
 };
 
+// ---- FreqCodec 2-D path (conv2d_simt.cu): raw activations are channels-last [B][F_raw][T_raw][C]
+struct InView2 {
+    const float* x;          // nullptr => view unused
+    const float* coef;       // [B][2][C] deferred-GroupNorm affine or nullptr (plain tensor)
+    int F_raw, T_raw;        // allocated extents
+    int f_off, t_off;        // first logical frequency row / time column (transposed-conv trim, conv.py:430-445)
+};
+
+struct Conv2dParams {
+    InView2 in0, in1;
+    int elu;
+    int B, F_in, T_in, C_in; // logical input extents
+    int KF, KT, SF, ST;      // taps and strides per axis (dilation 1)
+    int pad_f, pad_t;        // leading padding per axis (time: incl. the extra padding, conv.py:368)
+    int pad_zero;            // 1: transposed conv as 2x2-tap zero-padded conv; 0: reflect
+    const float* w;          // packed [KT][KF*C_in][C_out_eff]
+    const float* bias;       // [C_out_eff]
+    float* out;              // raw [B][F_out*FR][T_out*TR][Cc]
+    int F_out, T_out, C_out_eff;
+    int FR, TR, Cc;          // phase scatter of a transposed conv (C_out_eff = FR*TR*Cc); plain conv: 1, 1, C_out
+    double* partials;        // [B*F_out][n_parts][2] or nullptr
+    int cic;
+};
+
 __device__ __forceinline__ float elu1(float v) {
     // ATen CPU ELU: x <= 0 ? (exp(x) - 1) : x   (alpha = 1)
     return v > 0.f ? v : (expf(v) - 1.0f);

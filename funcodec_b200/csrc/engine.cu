@@ -84,12 +84,25 @@ struct fcb_handle {
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
 
+    // FreqCodec (arch 1) layers
+    struct Conv2W {
+        int cin = 0, cout = 0, kf = 0, kt = 0, sf = 1, st = 1;
+        bool transposed = false;
+        float* w = nullptr; float* bias = nullptr; float* gamma = nullptr; float* beta = nullptr;
+    };
+    struct ResBlock2W { Conv2W c1, c2, sc; };
+    Conv2W f_enc_conv0, f_dec_final;
+    std::vector<ResBlock2W> f_enc_rb, f_dec_rb;
+    std::vector<Conv2W> f_enc_down, f_dec_up;
+
     bool profiling = false;
     cudaEvent_t ev[FCB_NUM_PHASES + 1][2]{};
     bool ev_used[FCB_NUM_PHASES]{};
     bool ev_created = false;
 
-    int hop() const { int h = 1; for (int i = 0; i < cfg.n_ratios; ++i) h *= cfg.ratios[i]; return h; }
+    int tprod() const { int h = 1; for (int i = 0; i < cfg.n_ratios; ++i) h *= cfg.ratios[i]; return h; }
+    // samples per codec frame: prod(ratios), times the STFT hop for the FreqCodec variant
+    int hop() const { return cfg.arch == 1 ? tprod() * cfg.stft_hop : tprod(); }
     int top_channels() const { return cfg.n_filters << cfg.n_ratios; }
 };
 
@@ -509,7 +522,9 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
 }
 
 // SEANetDecoder.forward + Encodec._decode_frame (codec_basic.py:398-408) + trim (:711).
-int run_decoder(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
+int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len);
+
+int run_decoder_time(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
     fcb_handle* h = r.h;
     const int hop = h->hop();
     if (out_len > n_frames * hop || out_len <= 0) return fail(h, FCB_E_INVALID, "out_len must be in (0, T'*hop]");
@@ -549,6 +564,326 @@ int run_decoder(Run& r, const float* emb, int n_frames, const float* scale, floa
     return FCB_OK;
 }
 
+// =============================================================================================== FreqCodec (arch 1)
+typedef fcb_handle::Conv2W Conv2W;
+typedef fcb_handle::ResBlock2W ResBlock2W;
+
+// SConv2d weight [cout][cin][kf][kt] -> [kt][kf*cin + ci][cout]
+int pack_conv2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int kf, int kt, int sf, int st, Conv2W* o) {
+    const HostTensor *w, *b, *g, *be;
+    FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, kf, kt}, &w));
+    FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
+    FCB_TRY(need(h, prefix + ".conv.norm.weight", {cout}, &g));
+    FCB_TRY(need(h, prefix + ".conv.norm.bias", {cout}, &be));
+    std::vector<float> p((size_t)kt * kf * cin * cout);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int a = 0; a < kf; ++a)
+                for (int c = 0; c < kt; ++c)
+                    p[(((size_t)c * kf + a) * cin + ci) * cout + co] = w->data[(((size_t)co * cin + ci) * kf + a) * kt + c];
+    o->cin = cin; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = sf; o->st = st; o->transposed = false;
+    FCB_TRY(upload(h, p, &o->w));
+    FCB_TRY(upload(h, b->data, &o->bias));
+    FCB_TRY(upload(h, g->data, &o->gamma));
+    FCB_TRY(upload(h, be->data, &o->beta));
+    return FCB_OK;
+}
+
+// SConvTranspose2d (k = 2s per axis) weight [cin][cout][2fr][2tr] -> 2x2-tap conv, C_out' = fr*tr*cout:
+// packed[kti][kfi*cin + ci][(pf*tr + pt)*cout + co] = W[ci][co][pf + (1-kfi)*fr][pt + (1-kti)*tr]
+// (tap index 0 <-> the previous input row / column, as in pack_convtr).
+int pack_convtr2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int fr, int tr, Conv2W* o) {
+    const int kf = 2 * fr, kt = 2 * tr;
+    const HostTensor *w, *b, *g, *be;
+    FCB_TRY(need(h, prefix + ".convtr.convtr.weight", {cin, cout, kf, kt}, &w));
+    FCB_TRY(need(h, prefix + ".convtr.convtr.bias", {cout}, &b));
+    FCB_TRY(need(h, prefix + ".convtr.norm.weight", {cout}, &g));
+    FCB_TRY(need(h, prefix + ".convtr.norm.bias", {cout}, &be));
+    const int ce = fr * tr * cout;
+    std::vector<float> p((size_t)2 * 2 * cin * ce), bias(ce);
+    for (int kti = 0; kti < 2; ++kti)
+        for (int kfi = 0; kfi < 2; ++kfi)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int pf = 0; pf < fr; ++pf)
+                    for (int pt = 0; pt < tr; ++pt)
+                        for (int co = 0; co < cout; ++co)
+                            p[(((size_t)kti * 2 + kfi) * cin + ci) * ce + (pf * tr + pt) * cout + co] =
+                                w->data[(((size_t)ci * cout + co) * kf + pf + (1 - kfi) * fr) * kt + pt + (1 - kti) * tr];
+    for (int ph = 0; ph < fr * tr; ++ph)
+        for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
+    o->cin = cin; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = fr; o->st = tr; o->transposed = true;
+    FCB_TRY(upload(h, p, &o->w));
+    FCB_TRY(upload(h, bias, &o->bias));
+    FCB_TRY(upload(h, g->data, &o->gamma));
+    FCB_TRY(upload(h, be->data, &o->beta));
+    return FCB_OK;
+}
+
+int pack_resblock2d(fcb_handle* h, const std::string& prefix, int dim, ResBlock2W* o) {
+    const int rk = h->cfg.residual_kernel_size;
+    FCB_TRY(pack_conv2d(h, prefix + ".block.1", dim, dim / 2, rk, rk, 1, 1, &o->c1));
+    FCB_TRY(pack_conv2d(h, prefix + ".block.3", dim / 2, dim, 1, 1, 1, 1, &o->c2));
+    FCB_TRY(pack_conv2d(h, prefix + ".shortcut", dim, dim, 1, 1, 1, 1, &o->sc));
+    return FCB_OK;
+}
+
+// A raw 2-D activation [B][F_raw][T_raw][C] plus its deferred GroupNorm and logical window.
+struct Act2 {
+    float* p = nullptr;
+    int F_raw = 0, T_raw = 0, f_off = 0, t_off = 0;
+    int F = 0, T = 0, C = 0;
+    float* stats = nullptr;
+    float* coef = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    bool owned = false;
+};
+
+int release2(Run& r, Act2& a) {
+    if (a.owned) {
+        FCB_TRY(pool_free(r, a.p));
+        FCB_TRY(pool_free(r, a.stats));
+        FCB_TRY(pool_free(r, a.coef));
+    }
+    a = Act2();
+    return FCB_OK;
+}
+
+InView2 view2_of(const Act2& a) {
+    InView2 v;
+    v.x = a.p; v.coef = a.coef; v.F_raw = a.F_raw; v.T_raw = a.T_raw; v.f_off = a.f_off; v.t_off = a.t_off;
+    return v;
+}
+
+// SConv2d / SConvTranspose2d (non-causal).  out_padding = {{f_l, f_r}, {t_l, t_r}} of the transposed conv.
+int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W& L, const int (*out_pad)[2], Act2* out) {
+    fcb_handle* h = r.h;
+    if (in0.C != L.cin) return fail(h, FCB_E_INVALID, "internal: 2-D channel mismatch");
+    Conv2dParams p{};
+    p.in0 = view2_of(in0);
+    if (in1) p.in1 = view2_of(*in1); else p.in1.x = nullptr;
+    p.elu = elu ? 1 : 0;
+    p.B = r.B; p.F_in = in0.F; p.T_in = in0.T; p.C_in = in0.C;
+    p.w = L.w; p.bias = L.bias;
+    Act2 o;
+    if (!L.transposed) {
+        const int pt_f = (L.kf - 1) - (L.sf - 1), pt_t = (L.kt - 1) - (L.st - 1);
+        const int num = in0.T - L.kt + pt_t;
+        const int n_frames_ceil = (num >= 0 ? (num + L.st - 1) / L.st : -((-num) / L.st)) + 1;
+        const int extra = (n_frames_ceil - 1) * L.st + (L.kt - pt_t) - in0.T;
+        const int f_after = pt_f / 2, f_before = pt_f - f_after;
+        const int t_after = pt_t / 2, t_before = pt_t - t_after + extra;     // extra on the LEFT in 2-D (conv.py:368)
+        if (in0.F <= (f_before > f_after ? f_before : f_after) || in0.T <= (t_before > t_after ? t_before : t_after))
+            return fail(h, FCB_E_INVALID, "2-D conv: input smaller than its reflect padding is not supported");
+        p.KF = L.kf; p.KT = L.kt; p.SF = L.sf; p.ST = L.st; p.pad_f = f_before; p.pad_t = t_before; p.pad_zero = 0;
+        p.F_out = (in0.F + pt_f - L.kf) / L.sf + 1;
+        p.T_out = (in0.T + pt_t + extra - L.kt) / L.st + 1;
+        p.C_out_eff = L.cout; p.FR = 1; p.TR = 1; p.Cc = L.cout;
+        o.F_raw = o.F = p.F_out; o.T_raw = o.T = p.T_out;
+    } else {
+        const int fr = L.sf, tr = L.st;
+        p.KF = 2; p.KT = 2; p.SF = 1; p.ST = 1; p.pad_f = 1; p.pad_t = 1; p.pad_zero = 1;
+        p.F_out = in0.F + 1; p.T_out = in0.T + 1;
+        p.C_out_eff = fr * tr * L.cout; p.FR = fr; p.TR = tr; p.Cc = L.cout;
+        o.F_raw = p.F_out * fr; o.T_raw = p.T_out * tr;
+        const int pf = L.kf - fr, ptt = L.kt - tr;                            // conv.py:410-445
+        const int pf_r = pf / 2, pf_l = pf - pf_r, pt_r = ptt / 2, pt_l = ptt - pt_r;
+        const int fo_l = out_pad ? out_pad[0][0] : 0, fo_r = out_pad ? out_pad[0][1] : 0;
+        const int to_l = out_pad ? out_pad[1][0] : 0, to_r = out_pad ? out_pad[1][1] : 0;
+        const int fl = pf_l - fo_l > 0 ? pf_l - fo_l : 0, frr = pf_r - fo_r > 0 ? pf_r - fo_r : 0;
+        const int tl = pt_l - to_l > 0 ? pt_l - to_l : 0, trr = pt_r - to_r > 0 ? pt_r - to_r : 0;
+        o.f_off = fl; o.t_off = tl;
+        o.F = o.F_raw - fl - frr; o.T = o.T_raw - tl - trr;
+    }
+    o.C = L.cout;
+    const size_t per_clip = (size_t)o.F_raw * o.T_raw * o.C;
+    FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * per_clip));
+    o.owned = true;
+    p.out = o.p;
+    const int nparts = conv2d_num_parts(p);
+    double* partials = nullptr;
+    FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * p.F_out * nparts * 2 * sizeof(double)));
+    FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
+    FCB_TRY(alloc_f(r, &o.coef, (size_t)r.B * 2 * o.C));
+    o.gamma = L.gamma; o.beta = L.beta;
+    p.partials = partials;
+    FCB_CK(launch_conv2d(p, r.st));
+    FCB_CK(launch_stats_finalize(partials, p.F_out * nparts, (double)per_clip, h->cfg.gn_eps, 0, o.stats, r.B, r.st, L.gamma,
+                                 L.beta, o.C, o.coef));
+    h->launches += 2;
+    FCB_TRY(pool_free(r, partials));
+    *out = o;
+    return FCB_OK;
+}
+
+int run_resblock2d(Run& r, const Act2& x, const ResBlock2W& W, Act2* sc_out, Act2* blk_out) {
+    Act2 h1, h2, sc;
+    FCB_TRY(run_conv2d(r, x, nullptr, true, W.c1, nullptr, &h1));
+    FCB_TRY(run_conv2d(r, h1, nullptr, true, W.c2, nullptr, &h2));
+    FCB_TRY(release2(r, h1));
+    FCB_TRY(run_conv2d(r, x, nullptr, false, W.sc, nullptr, &sc));
+    *sc_out = sc; *blk_out = h2;
+    return FCB_OK;
+}
+
+int stft_frames(const fcb_handle* h, int L) { return 1 + L / h->cfg.stft_hop; }
+
+// FreqCodec._encode_frame (mag_phase) + SEANetEncoder2d.forward; returns the final conv1d's raw output view.
+int run_encoder_freq(Run& r, const float* wav, int L, float* scale_out, Act* out) {
+    fcb_handle* h = r.h;
+    const int B = r.B;
+    const fcb_config& c = h->cfg;
+    if (L <= c.n_fft / 2) return fail(h, FCB_E_INVALID, "clip shorter than n_fft/2 (reflect padding of the STFT)");
+    FCB_TRY(phase_begin(r, FCB_PHASE_ENCODER_CONV));
+    float* scale = nullptr;
+    bool scale_owned = false;
+    if (c.audio_normalize) {
+        double* partials = nullptr;
+        int nparts = sumsq_num_parts(L), np2 = 0;
+        FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)B * nparts * 2 * sizeof(double)));
+        if (scale_out) scale = scale_out; else { FCB_TRY(alloc_f(r, &scale, B)); scale_owned = true; }
+        FCB_CK(launch_sumsq_partials(wav, B, L, partials, &np2, r.st));
+        FCB_CK(launch_stats_finalize(partials, nparts, (double)L, 0.f, 1, scale, B, r.st));
+        h->launches += 2;
+        FCB_TRY(pool_free(r, partials));
+    } else if (scale_out) {
+        FCB_CK(launch_fill(scale_out, 1.0f, B, r.st));
+        h->launches++;
+    }
+    const int n_bins = c.n_fft / 2 + 1, Ts = stft_frames(h, L);
+    Act2 a;
+    FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * 3));
+    a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = 3;
+    FCB_CK(launch_stft_magphase(wav, scale, B, L, c.n_fft, c.stft_hop, Ts, a.p, r.st));
+    h->launches++;
+    if (scale_owned) FCB_TRY(pool_free(r, scale));
+    Act2 x;
+    FCB_TRY(run_conv2d(r, a, nullptr, false, h->f_enc_conv0, nullptr, &x));
+    FCB_TRY(release2(r, a));
+    for (size_t i = 0; i < h->f_enc_rb.size(); ++i) {
+        Act2 sc, blk, d;
+        FCB_TRY(run_resblock2d(r, x, h->f_enc_rb[i], &sc, &blk));
+        FCB_TRY(release2(r, x));
+        FCB_TRY(run_conv2d(r, sc, &blk, true, h->f_enc_down[i], nullptr, &d));
+        FCB_TRY(release2(r, sc));
+        FCB_TRY(release2(r, blk));
+        x = d;
+    }
+    if (x.F != 1) return fail(h, FCB_E_INVALID, "FreqCodec encoder: frequency axis did not reduce to 1 (check ratios / n_fft)");
+    FCB_TRY(phase_end(r));
+    // squeeze (ReshapeModule, seanet_encoder.py:326): [B][1][T][C] is already a 1-D channels-last tensor
+    Act y1;
+    y1.p = x.p; y1.T = x.T; y1.C = x.C; y1.clip_stride = (long long)x.T * x.C; y1.stats = x.stats; y1.coef = x.coef;
+    y1.gamma = x.gamma; y1.beta = x.beta; y1.owned = true;
+    FCB_TRY(phase_begin(r, FCB_PHASE_ENCODER_LSTM));
+    if (c.lstm_layers > 0) {
+        Act y;
+        FCB_TRY(run_lstm(r, y1, h->enc_lstm, &y));
+        FCB_TRY(release(r, y1));
+        y1 = y;
+    }
+    Act f;
+    FCB_TRY(run_conv(r, y1, nullptr, true, nullptr, h->enc_final, true, &f));
+    FCB_TRY(release(r, y1));
+    FCB_TRY(phase_end(r));
+    *out = f;
+    return FCB_OK;
+}
+
+// SEANetDecoder2d.forward + FreqCodec._decode_frame (mag_phase) + iSTFT + trim.
+int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
+    fcb_handle* h = r.h;
+    const fcb_config& c = h->cfg;
+    if (out_len <= 0 || out_len > fcb_decoded_length(h, n_frames))
+        return fail(h, FCB_E_INVALID, "out_len must be in (0, fcb_decoded_length]");
+    Act e;
+    e.p = const_cast<float*>(emb); e.T = n_frames; e.C = c.dimension; e.clip_stride = (long long)n_frames * e.C;
+    FCB_TRY(phase_begin(r, FCB_PHASE_DECODER_LSTM));
+    Act a;
+    FCB_TRY(run_conv(r, e, nullptr, false, nullptr, h->dec_conv0, true, &a));
+    if (c.lstm_layers > 0) {
+        Act y;
+        FCB_TRY(run_lstm(r, a, h->dec_lstm, &y));
+        FCB_TRY(release(r, a));
+        a = y;
+    }
+    FCB_TRY(phase_end(r));
+    FCB_TRY(phase_begin(r, FCB_PHASE_DECODER_CONV));
+    // unsqueeze (seanet_decoder.py:235-241)
+    Act2 sc, blk;
+    sc.p = a.p; sc.F_raw = sc.F = 1; sc.T_raw = sc.T = a.T; sc.C = a.C; sc.stats = a.stats; sc.coef = a.coef;
+    sc.gamma = a.gamma; sc.beta = a.beta; sc.owned = true;
+    bool have_blk = false;
+    static const int last_out_pad[2][2] = {{0, 1}, {0, 0}};      // SEANetDecoder2d last_out_padding default
+    for (size_t i = 0; i < h->f_dec_up.size(); ++i) {
+        Act2 u;
+        const bool last = (i + 1 == h->f_dec_up.size());
+        FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_up[i], last ? last_out_pad : nullptr, &u));
+        FCB_TRY(release2(r, sc));
+        if (have_blk) FCB_TRY(release2(r, blk));
+        FCB_TRY(run_resblock2d(r, u, h->f_dec_rb[i], &sc, &blk));
+        FCB_TRY(release2(r, u));
+        have_blk = true;
+    }
+    Act2 f;
+    FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_final, nullptr, &f));
+    FCB_TRY(release2(r, sc));
+    if (have_blk) FCB_TRY(release2(r, blk));
+    const int n_bins = c.n_fft / 2 + 1;
+    if (f.F != n_bins || f.C != 3) return fail(h, FCB_E_INVALID, "FreqCodec decoder: output is not [n_fft/2+1 bins x 3 channels]");
+    float* frames = nullptr;
+    FCB_TRY(alloc_f(r, &frames, (size_t)r.B * f.T * c.n_fft));
+    FCB_CK(launch_istft(f.p, f.coef, r.B, f.F_raw, f.T_raw, c.n_fft, c.stft_hop, f.T, scale, frames, wav_out, out_len, r.st));
+    h->launches += 2;
+    FCB_TRY(pool_free(r, frames));
+    FCB_TRY(release2(r, f));
+    FCB_TRY(phase_end(r));
+    return FCB_OK;
+}
+
+int finalize_freq(fcb_handle* h) {
+    const fcb_config& c = h->cfg;
+    const int nf = c.n_filters, D = c.dimension, nr = c.n_ratios;
+    FCB_TRY(pack_conv2d(h, "encoder.model.0", 3, nf, c.kernel_size, c.kernel_size, 1, 1, &h->f_enc_conv0));
+    int n = 1, mult = 1;
+    for (int i = nr - 1; i >= 0; --i) {               // encoder applies the ratios reversed (seanet_encoder.py:288)
+        const int fr = c.ratios_f[i], tr = c.ratios[i];
+        ResBlock2W rb; Conv2W down;
+        FCB_TRY(pack_resblock2d(h, "encoder.model." + std::to_string(n), mult * nf, &rb));
+        FCB_TRY(pack_conv2d(h, "encoder.model." + std::to_string(n + 2), mult * nf, 2 * mult * nf, 2 * fr, 2 * tr, fr, tr, &down));
+        h->f_enc_rb.push_back(rb); h->f_enc_down.push_back(down);
+        mult *= 2; n += 3;
+    }
+    n += 1;                                             // ReshapeModule
+    if (c.lstm_layers > 0) {
+        FCB_TRY(pack_lstm(h, "encoder.model." + std::to_string(n), mult * nf, c.lstm_layers, &h->enc_lstm));
+        n += 1;
+    }
+    FCB_TRY(pack_conv(h, "encoder.model." + std::to_string(n + 1), mult * nf, D, c.last_kernel_size, 1, &h->enc_final));
+    FCB_TRY(pack_conv(h, "decoder.model.0", D, mult * nf, c.kernel_size, 1, &h->dec_conv0));
+    n = 1;
+    if (c.lstm_layers > 0) {
+        FCB_TRY(pack_lstm(h, "decoder.model.1", mult * nf, c.lstm_layers, &h->dec_lstm));
+        n = 2;
+    }
+    n += 1;                                             // ReshapeModule
+    for (int i = 0; i < nr; ++i) {
+        const int fr = c.ratios_f[i], tr = c.ratios[i];
+        Conv2W up; ResBlock2W rb;
+        FCB_TRY(pack_convtr2d(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, fr, tr, &up));
+        FCB_TRY(pack_resblock2d(h, "decoder.model." + std::to_string(n + 2), mult * nf / 2, &rb));
+        h->f_dec_up.push_back(up); h->f_dec_rb.push_back(rb);
+        mult /= 2; n += 3;
+    }
+    FCB_TRY(pack_conv2d(h, "decoder.model." + std::to_string(n + 1), nf, 3, c.last_kernel_size, c.last_kernel_size, 1, 1, &h->f_dec_final));
+    return FCB_OK;
+}
+
+int run_decoder(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
+    return r.h->cfg.arch == 1 ? run_decoder_freq(r, emb, n_frames, scale, wav_out, out_len)
+                              : run_decoder_time(r, emb, n_frames, scale, wav_out, out_len);
+}
+
 int check_ready(fcb_handle* h) {
     if (!h) return FCB_E_INVALID;
     if (!h->finalized) return fail(h, FCB_E_STATE, "fcb_finalize has not been called");
@@ -565,7 +900,8 @@ int do_encode(fcb_handle* h, const float* wav, int B, int L, int n_q, int64_t* c
     if (B > 512) return fail(h, FCB_E_INVALID, "fcb_encode: at most 512 clips per call (split the batch)");
     Run r{h, B, st};
     Act f;
-    FCB_TRY(run_encoder(r, wav, L, scale, &f));
+    if (h->cfg.arch == 1) FCB_TRY(run_encoder_freq(r, wav, L, scale, &f));
+    else FCB_TRY(run_encoder(r, wav, L, scale, &f));
     FCB_TRY(phase_begin(r, FCB_PHASE_RVQ));
     RvqParams q{};
     q.in = view_of(f);
@@ -608,6 +944,12 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
         return FCB_E_INVALID;
     for (int i = 0; i < cfg->n_ratios; ++i)
         if (cfg->ratios[i] < 1) return FCB_E_INVALID;
+    if (cfg->arch != 0 && cfg->arch != 1) return FCB_E_INVALID;
+    if (cfg->arch == 1) {
+        if (cfg->n_fft < 16 || cfg->n_fft % 2 != 0 || cfg->stft_hop < 1 || cfg->stft_hop > cfg->n_fft) return FCB_E_INVALID;
+        for (int i = 0; i < cfg->n_ratios; ++i)
+            if (cfg->ratios_f[i] < 1) return FCB_E_INVALID;
+    }
     fcb_handle* h = new (std::nothrow) fcb_handle();
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
@@ -643,6 +985,9 @@ int fcb_finalize(fcb_handle* h) {
     if (h->finalized) return fail(h, FCB_E_STATE, "already finalized");
     const fcb_config& c = h->cfg;
     const int nf = c.n_filters, D = c.dimension;
+    if (c.arch == 1) {
+        FCB_TRY(finalize_freq(h));
+    } else {
     FCB_TRY(pack_conv(h, "encoder.model.0", 1, nf, c.kernel_size, 1, &h->enc_conv0));
     int n = 1, mult = 1;
     for (int i = c.n_ratios - 1; i >= 0; --i) {      // encoder applies the ratios reversed (seanet_encoder.py:102)
@@ -674,6 +1019,7 @@ int fcb_finalize(fcb_handle* h) {
         mult /= 2; n += 3;
     }
     FCB_TRY(pack_conv(h, "decoder.model." + std::to_string(n + 1), nf, 1, c.last_kernel_size, 1, &h->dec_final));
+    }
 
     const HostTensor* emb;
     FCB_TRY(need(h, "quantizer.rq.model.embed", {c.num_quantizers, c.codebook_size, D}, &emb));
@@ -701,7 +1047,7 @@ int fcb_finalize(fcb_handle* h) {
     h->launches++;
     FCB_CK(cudaDeviceSynchronize());
     h->host.clear();
-    {   // name map for fcb_debug_conv1d (vectors are final now: pointers stay valid)
+    if (h->cfg.arch == 0) {   // name map for fcb_debug_conv1d (vectors are final now: pointers stay valid)
         const fcb_config& cc = h->cfg;
         h->by_name["encoder.model.0"] = &h->enc_conv0;
         int nn = 1;
@@ -734,8 +1080,18 @@ int fcb_finalize(fcb_handle* h) {
 
 int fcb_num_frames(const fcb_handle* h, int32_t L) {
     if (!h || L <= 0) return FCB_E_INVALID;
+    if (h->cfg.arch == 1) {          // STFT frames (center=True): 1 + L / hop, then the encoder's time strides
+        const int ts = 1 + L / h->cfg.stft_hop, tp = h->tprod();
+        return (ts + tp - 1) / tp;
+    }
     const int hop = h->hop();
     return (L + hop - 1) / hop;
+}
+
+int fcb_decoded_length(const fcb_handle* h, int32_t n_frames) {
+    if (!h || n_frames <= 0) return FCB_E_INVALID;
+    if (h->cfg.arch == 1) return h->cfg.stft_hop * (n_frames * h->tprod() - 1);   // torch.istft(center=True, length=None)
+    return n_frames * h->hop();
 }
 
 int fcb_num_quantizers_for_bandwidth(const fcb_handle* h, double bandwidth) {

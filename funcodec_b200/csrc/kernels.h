@@ -28,6 +28,14 @@ int conv_tc_n_tile(int C_out_eff);
 int conv_tc_num_parts(int T_out, int C_out_eff);
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts);
 
+// conv2d_simt.cu (FreqCodec 2-D path)
+int conv2d_num_parts(const Conv2dParams& p);
+cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st);
+cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, int L, int n_fft, int hop, int n_frames,
+                                 float* feats, cudaStream_t st);
+cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,
+                         const float* scale, float* frames, float* out, int out_len, cudaStream_t st);
+
 // lstm.cu
 struct LstmSeqParams {
     const float* gx;      // [B][T][4H] input projection incl. both biases, columns packed unit-major (n' = 4*j + gate)

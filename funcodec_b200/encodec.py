@@ -55,6 +55,9 @@ class B200Encodec:
         c.kernel_size, c.last_kernel_size, c.residual_kernel_size = cfg.kernel_size, cfg.last_kernel_size, cfg.residual_kernel_size
         c.lstm_layers, c.codebook_size, c.num_quantizers = cfg.lstm_layers, cfg.codebook_size, cfg.num_quantizers
         c.sample_rate, c.audio_normalize, c.gn_eps = cfg.sample_rate, int(cfg.audio_normalize), cfg.gn_eps
+        c.arch, c.n_fft, c.stft_hop = cfg.arch, cfg.n_fft, cfg.stft_hop
+        for i, r in enumerate(cfg.ratios_f):
+            c.ratios_f[i] = r
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             rc = self._lib.fcb_create(ctypes.byref(c), ctypes.byref(self._h))
@@ -150,8 +153,11 @@ class B200Encodec:
         sub = torch.empty((n_q, B, D, Tf), dtype=torch.float32, device=dev) if need_sub_quants else None
         enc = torch.empty((B, Tf, D), dtype=torch.float32, device=dev) if need_encoder_out else None
         recon = None
+        # FreqCodec: the iSTFT yields stft_hop * (T_s - 1) samples, possibly fewer than L (the reference's [:, :, :L] slice
+        # then simply returns what exists, codec_freq.py:709)
+        Lr = min(L, self.cfg.decoded_length(Tf))
         with torch.cuda.device(dev):
-            if need_recon and not need_encoder_out:
+            if need_recon and not need_encoder_out and Lr == L:
                 recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
                 self._ck(self._lib.fcb_roundtrip(self._h, _ptr(x), B, L, n_q, int(use_scale), _ptr(codes), _ptr(quant),
                                                  _ptr(scale), _ptr(sub), _ptr(recon), self._stream()), "fcb_roundtrip")
@@ -159,9 +165,9 @@ class B200Encodec:
                 self._ck(self._lib.fcb_encode(self._h, _ptr(x), B, L, n_q, _ptr(codes), _ptr(quant), _ptr(scale),
                                               _ptr(sub), _ptr(enc), self._stream()), "fcb_encode")
                 if need_recon:
-                    recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+                    recon = torch.empty((B, 1, Lr), dtype=torch.float32, device=dev)
                     sc = scale if (use_scale and self.audio_normalize) else None
-                    self._ck(self._lib.fcb_decode_emb(self._h, _ptr(quant), B, Tf, _ptr(sc), _ptr(recon), L,
+                    self._ck(self._lib.fcb_decode_emb(self._h, _ptr(quant), B, Tf, _ptr(sc), _ptr(recon), Lr,
                                                       self._stream()), "fcb_decode_emb")
         ret_scale = scale if (use_scale and self.audio_normalize) else None
         out = dict(recon_speech=recon, code_indices=[codes], code_embeddings=[(quant, ret_scale)],
@@ -185,11 +191,11 @@ class B200Encodec:
             raise ValueError("token_idx must be [B, T', n_q]")
         tok = token_idx.to(self.device, torch.int64).contiguous()
         B, Tf, n_q = tok.shape
-        D, hop = self.cfg.dimension, self.cfg.hop_length
+        D, Lo = self.cfg.dimension, self.cfg.decoded_length(Tf)
         emb = torch.empty((B, Tf, D), dtype=torch.float32, device=self.device)
-        recon = torch.empty((B, 1, Tf * hop), dtype=torch.float32, device=self.device)
+        recon = torch.empty((B, 1, Lo), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            self._ck(self._lib.fcb_decode_codes(self._h, _ptr(tok), B, Tf, n_q, _ptr(emb), _ptr(recon), Tf * hop,
+            self._ck(self._lib.fcb_decode_codes(self._h, _ptr(tok), B, Tf, n_q, _ptr(emb), _ptr(recon), Lo,
                                                 self._stream()), "fcb_decode_codes")
         return dict(recon_speech=recon if need_recon else None, code_indices=None,
                     code_embeddings=[(emb, None)], sub_quants=None)
@@ -202,12 +208,12 @@ class B200Encodec:
             raise ValueError("token_idx must be [B, T', D] embeddings")
         emb = token_idx.to(self.device, torch.float32).contiguous()
         B, Tf, _ = emb.shape
-        hop = self.cfg.hop_length
+        Lo = self.cfg.decoded_length(Tf)
         recon = None
         if need_recon:
-            recon = torch.empty((B, 1, Tf * hop), dtype=torch.float32, device=self.device)
+            recon = torch.empty((B, 1, Lo), dtype=torch.float32, device=self.device)
             with torch.cuda.device(self.device):
-                self._ck(self._lib.fcb_decode_emb(self._h, _ptr(emb), B, Tf, None, _ptr(recon), Tf * hop,
+                self._ck(self._lib.fcb_decode_emb(self._h, _ptr(emb), B, Tf, None, _ptr(recon), Lo,
                                                   self._stream()), "fcb_decode_emb")
         return dict(recon_speech=recon, code_indices=None, code_embeddings=[(emb, None)], sub_quants=None)
 

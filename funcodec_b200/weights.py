@@ -49,7 +49,60 @@ def conv_specs(cfg: CodecConfig) -> List[Dict]:
     return specs
 
 
+def _freq_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
+    """SEANetEncoder2d / SEANetDecoder2d parameter names and shapes (seanet_encoder.py:252-363, seanet_decoder.py:244-360),
+    conv groups = 1."""
+    sh: Dict[str, Tuple[int, ...]] = {}
+    nf, D, rk = cfg.n_filters, cfg.dimension, cfg.residual_kernel_size
+
+    def conv2(name, cin, cout, kf, kt):
+        sh[name + ".conv.conv.weight"] = (cout, cin, kf, kt); sh[name + ".conv.conv.bias"] = (cout,)
+        sh[name + ".conv.norm.weight"] = (cout,); sh[name + ".conv.norm.bias"] = (cout,)
+
+    def conv1(name, cin, cout, k):
+        sh[name + ".conv.conv.weight"] = (cout, cin, k); sh[name + ".conv.conv.bias"] = (cout,)
+        sh[name + ".conv.norm.weight"] = (cout,); sh[name + ".conv.norm.bias"] = (cout,)
+
+    def rb(name, dim):
+        conv2(name + ".block.1", dim, dim // 2, rk, rk); conv2(name + ".block.3", dim // 2, dim, 1, 1)
+        conv2(name + ".shortcut", dim, dim, 1, 1)
+
+    def lstm(name, H):
+        for l in range(cfg.lstm_layers):
+            sh[f"{name}.lstm.weight_ih_l{l}"] = (4 * H, H); sh[f"{name}.lstm.weight_hh_l{l}"] = (4 * H, H)
+            sh[f"{name}.lstm.bias_ih_l{l}"] = (4 * H,); sh[f"{name}.lstm.bias_hh_l{l}"] = (4 * H,)
+
+    conv2("encoder.model.0", 3, nf, cfg.kernel_size, cfg.kernel_size)
+    n, mult = 1, 1
+    for fr, tr in reversed(list(zip(cfg.ratios_f, cfg.ratios))):
+        rb(f"encoder.model.{n}", mult * nf)
+        conv2(f"encoder.model.{n + 2}", mult * nf, 2 * mult * nf, 2 * fr, 2 * tr)
+        mult *= 2; n += 3
+    n += 1
+    if cfg.lstm_layers > 0:
+        lstm(f"encoder.model.{n}", mult * nf); n += 1
+    conv1(f"encoder.model.{n + 1}", mult * nf, D, cfg.last_kernel_size)
+    conv1("decoder.model.0", D, mult * nf, cfg.kernel_size)
+    n = 1
+    if cfg.lstm_layers > 0:
+        lstm("decoder.model.1", mult * nf); n = 2
+    n += 1
+    for fr, tr in zip(cfg.ratios_f, cfg.ratios):
+        name = f"decoder.model.{n + 1}"
+        sh[name + ".convtr.convtr.weight"] = (mult * nf, mult * nf // 2, 2 * fr, 2 * tr); sh[name + ".convtr.convtr.bias"] = (mult * nf // 2,)
+        sh[name + ".convtr.norm.weight"] = (mult * nf // 2,); sh[name + ".convtr.norm.bias"] = (mult * nf // 2,)
+        rb(f"decoder.model.{n + 2}", mult * nf // 2)
+        mult //= 2; n += 3
+    conv2(f"decoder.model.{n + 1}", nf, 3, cfg.last_kernel_size, cfg.last_kernel_size)
+    nq, K = cfg.num_quantizers, cfg.codebook_size
+    sh["quantizer.rq.model.inited"] = (nq, 1); sh["quantizer.rq.model.cluster_size"] = (nq, K)
+    sh["quantizer.rq.model.embed"] = (nq, K, D); sh["quantizer.rq.model.embed_avg"] = (nq, K, D)
+    return sh
+
+
 def state_dict_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
+    if cfg.arch == 1:
+        return _freq_shapes(cfg)
     shapes: Dict[str, Tuple[int, ...]] = {}
     for sp in conv_specs(cfg):
         n = sp["name"]
@@ -99,11 +152,8 @@ def init_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
         elif ".lstm." in name:
             H = shape[-1] if len(shape) == 2 else shape[0] // 4
             sd[name] = uni(shape, 1.0 / math.sqrt(H))
-        elif name.endswith("convtr.weight"):
-            fan_in = shape[1] * shape[2]          # torch: fan_in of [Cin, Cout, k] uses dim 1
-            sd[name] = uni(shape, 1.0 / math.sqrt(fan_in))
-        elif name.endswith("conv.weight"):
-            fan_in = shape[1] * shape[2]
+        elif name.endswith("convtr.weight") or name.endswith("conv.weight"):
+            fan_in = shape[1] * int(math.prod(shape[2:]))     # torch: fan_in uses dim 1 (also for [Cin, Cout, k...])
             sd[name] = uni(shape, 1.0 / math.sqrt(fan_in))
         else:  # conv / convtr bias
             sd[name] = uni(shape, 0.1)

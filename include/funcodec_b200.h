@@ -60,6 +60,12 @@ typedef struct fcb_config {
     int32_t sample_rate;            /* 16000 */
     int32_t audio_normalize;        /* model_conf.audio_normalize */
     float   gn_eps;                 /* nn.GroupNorm eps, 1e-5 */
+    /* FreqCodec variant (funcodec/models/codec_freq.py, codec_domain ['mag_phase','mag_phase']): arch = 1.  ratios[] then
+     * holds the TIME ratios and ratios_f[] the FREQUENCY ratios of encoder_conf.ratios [[f, t], ...]; in_channels = 3. */
+    int32_t arch;                   /* 0: time-domain Encodec (codec_basic.py); 1: FreqCodec mag_phase (codec_freq.py) */
+    int32_t ratios_f[FCB_MAX_RATIOS];
+    int32_t n_fft;                  /* 512 */
+    int32_t stft_hop;               /* 160 */
 } fcb_config;
 
 typedef struct fcb_handle fcb_handle;
@@ -84,6 +90,9 @@ FCB_API int fcb_finalize(fcb_handle* h);
 
 /* T' for a clip of L samples: ceil(L / hop). */
 FCB_API int fcb_num_frames(const fcb_handle* h, int32_t L);
+/* Samples the decoder produces for n_frames codec frames: T'*hop (arch 0) or stft_hop*(T'*prod(time ratios) - 1)
+ * (arch 1, torch.istft with center=True).  fcb_decode_* accept out_len <= this. */
+FCB_API int fcb_decoded_length(const fcb_handle* h, int32_t n_frames);
 /* n_q for a target bandwidth (<=0: all), ResidualVectorQuantizer.get_num_quantizers_for_bandwidth
  * (funcodec/modules/quantization/vq.py:105-112). */
 FCB_API int fcb_num_quantizers_for_bandwidth(const fcb_handle* h, double bandwidth);
