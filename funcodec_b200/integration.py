@@ -1,5 +1,5 @@
 """Glue for the drop-in: derive a CodecConfig from an already-built reference `Encodec`
-module (funcodec/models/codec_basic.py:119) and wrap it with the CUDA-backed B200Encodec.
+(funcodec/models/codec_basic.py:119) or mag_phase `FreqCodec` (funcodec/models/codec_basic.py FreqCodec) module and wrap it with the CUDA-backed B200Encodec.
 
 Only the configurations of DESIGN.md §9 are accepted; anything else raises (no silent fallback to the PyTorch path).
 """
@@ -18,9 +18,21 @@ def config_from_reference_model(model) -> CodecConfig:
     """Reads the attributes SEANetEncoder / SEANetDecoder / CostumeQuantizer / Encodec keep
     (seanet_encoder.py:98-106, seanet_decoder.py:100-106, costume_quantizer.py:49-53, codec_basic.py:249-254)."""
     enc, dec, q = model.encoder, model.decoder, model.quantizer
-    ratios = tuple(int(r) for r in dec.ratios)
-    if tuple(reversed(ratios)) != tuple(int(r) for r in enc.ratios):
-        raise UnsupportedReferenceModel("encoder/decoder ratios differ")
+    domain = getattr(model, "codec_domain", "time")
+    freq = isinstance(domain, (list, tuple)) and list(domain) == ["mag_phase", "mag_phase"]
+    if freq:        # FreqCodec (codec_freq.py): ratios are [freq, time] pairs
+        pairs = [tuple(int(v) for v in r) for r in dec.ratios]
+        if list(reversed(pairs)) != [tuple(int(v) for v in r) for r in enc.ratios]:
+            raise UnsupportedReferenceModel("encoder/decoder ratios differ")
+        ratios = tuple(p[1] for p in pairs)
+        ratios_f = tuple(p[0] for p in pairs)
+    else:
+        if domain not in ("time", None) and not (isinstance(domain, (list, tuple)) and list(domain) == ["time", "time"]):
+            raise UnsupportedReferenceModel(f"codec_domain {domain} is not supported (time, or ['mag_phase', 'mag_phase'])")
+        ratios = tuple(int(r) for r in dec.ratios)
+        ratios_f = ()
+        if tuple(reversed(ratios)) != tuple(int(r) for r in enc.ratios):
+            raise UnsupportedReferenceModel("encoder/decoder ratios differ")
     sd: Dict[str, torch.Tensor] = model.state_dict()
     if any(k.endswith("weight_g") or k.endswith("weight_v") for k in sd):
         raise UnsupportedReferenceModel("weight_norm parametrisation is not supported (norm must be time_group_norm)")
@@ -32,14 +44,17 @@ def config_from_reference_model(model) -> CodecConfig:
         raise UnsupportedReferenceModel("quantizer projections / codec_range are not supported")
     if "quantizer.rq.model.embed" not in sd:
         raise UnsupportedReferenceModel("quantizer must use use_ddp: true (stacked codebook buffers)")
-    if getattr(model, "codec_domain", "time") not in ("time", None):
-        raise UnsupportedReferenceModel("only the time-domain Encodec is supported")
     embed = sd["quantizer.rq.model.embed"]
     w0 = sd["encoder.model.0.conv.conv.weight"]
     n_lstm = len([k for k in sd if k.startswith("decoder.model.1.lstm.weight_ih_l")])
     last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.model."))
     rb_k = sd["encoder.model.1.block.1.conv.conv.weight"].shape[-1]
-    cfg = CodecConfig(name="from_reference", ratios=ratios, n_filters=int(w0.shape[0]), dimension=int(embed.shape[2]),
+    if freq and sd["encoder.model.1.block.1.conv.conv.weight"].shape[1] != sd["encoder.model.0.conv.conv.weight"].shape[0]:
+        raise UnsupportedReferenceModel("grouped 2-D convs (conv_group_ratio > 0) are not supported")
+    dconf = getattr(model, "domain_conf", None) or {}
+    cfg = CodecConfig(name="from_reference", ratios=ratios, arch=1 if freq else 0, ratios_f=ratios_f,
+                      n_fft=int(dconf.get("n_fft", 512)), stft_hop=int(dconf.get("hop_length", 160)),
+                      n_filters=int(w0.shape[0]), dimension=int(embed.shape[2]),
                       kernel_size=int(w0.shape[-1]),
                       last_kernel_size=int(sd[f"decoder.model.{last_idx}.conv.conv.weight"].shape[-1]),
                       residual_kernel_size=int(rb_k), lstm_layers=n_lstm, codebook_size=int(embed.shape[1]),

@@ -63,3 +63,26 @@ def test_config_from_reference_like_model():
     m.segment_dur = 1.0
     with pytest.raises(UnsupportedReferenceModel):
         config_from_reference_model(m)
+
+
+def test_config_from_reference_like_freqcodec():
+    """Same, for a mag_phase FreqCodec (codec_freq.py:118-215): [freq, time] ratio pairs, domain_conf."""
+    import types
+    from funcodec_b200 import init_state_dict
+    from funcodec_b200.integration import config_from_reference_model, UnsupportedReferenceModel
+    cfg = get_config("freq_small")
+    sd = init_state_dict(cfg, 0)
+    pairs = [[f, t] for f, t in zip(cfg.ratios_f, cfg.ratios)]
+    m = types.SimpleNamespace(
+        encoder=types.SimpleNamespace(ratios=list(reversed(pairs))), decoder=types.SimpleNamespace(ratios=pairs),
+        quantizer=types.SimpleNamespace(sampling_rate=cfg.sample_rate, encoder_hop_length=cfg.hop_length,
+                                        codebook_size=cfg.codebook_size, input_proj=None, input_act=None),
+        audio_normalize=True, segment_dur=None, codec_domain=["mag_phase", "mag_phase"],
+        domain_conf={"n_fft": cfg.n_fft, "hop_length": cfg.stft_hop}, state_dict=lambda: sd)
+    got = config_from_reference_model(m)
+    for f in ("arch", "ratios", "ratios_f", "n_fft", "stft_hop", "n_filters", "dimension", "kernel_size", "last_kernel_size",
+              "residual_kernel_size", "lstm_layers", "codebook_size", "num_quantizers"):
+        assert getattr(got, f) == getattr(cfg, f), f
+    m.codec_domain = ["stft", "stft"]
+    with pytest.raises(UnsupportedReferenceModel):
+        config_from_reference_model(m)
