@@ -50,6 +50,8 @@ SYMBOLS = {
     "fcb_set_option": (c_int32, [c_void_p, c_char_p, c_int32]),
     "fcb_debug_conv1d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,
                                    POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "fcb_debug_conv2d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,
+                                   POINTER(c_int32), c_void_p]),
     "fcb_last_error": (c_char_p, [c_void_p]),
     "fcb_destroy": (None, [c_void_p]),
 }

@@ -24,6 +24,18 @@ struct InView {
     int row_off;             // first logical row (transposed-conv trim, conv.py:299-303)
 };
 
+// conv_tc.cu, FreqCodec 2-D mode (KF > 0): every (clip, output frequency row) is a pseudo-clip of a conv along time
+// whose input channels are the KF frequency taps x cin channels, gathered from KF input rows [B][F_raw][T_raw][cin].
+struct Freq2d {
+    int KF, SF, pad_f;       // frequency taps, stride, leading padding (KF == 0: plain 1-D conv)
+    int F_in, F_out;         // logical input rows, output rows (= pseudo-clips per clip)
+    int cin;                 // channels of the stored input (ConvParams::C_in is the gathered KF*cin)
+    int T_raw0, T_raw1;      // allocated time extents of in0 / in1 (InView::row_off = first logical column)
+    int f_off0, f_off1;      // first logical frequency row of in0 / in1
+    int FR, TR, Cc;          // transposed conv phase scatter: output channel co -> phase co / Cc = pf*TR + pt
+    int c_store;             // channels per stored output element (== Cc unless the weight image pads C_out)
+};
+
 struct ConvParams {
     InView in0, in1;         // input = f(in0) [+ f(in1)]   (resblock: shortcut + block)
     const float* div_scale;  // [B] or nullptr: input = x / scale[b]  (codec_basic.py:366-371)
@@ -42,6 +54,7 @@ struct ConvParams {
     long long out_clip_stride;
     double* partials;        // [B][n_parts][2] (sum, sum of squares) or nullptr
     int cic;                 // input-channel chunk staged per iteration
+    Freq2d fq;               // tensor-core 2-D mode (zero-initialised for 1-D layers)
 };
 
 // ---- FreqCodec 2-D path (conv2d_simt.cu): raw activations are channels-last [B][F_raw][T_raw][C]

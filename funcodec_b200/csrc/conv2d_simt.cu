@@ -192,11 +192,12 @@ cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st) {
 
 // =============================================================================================== STFT front end
 // One CTA = 8 frames of one clip.  X[k] = sum_n (x[n]/scale) w[n] e^{-2 pi i k n / N}, then the mag_phase features
-// (codec_freq.py:365-373) written channels-last as [B][N/2+1][T_s][3] = (log max(|X|,1e-6), Re X/max(|X|,1e-6), Im ...).
+// (codec_freq.py:365-373) written channels-last as [B][N/2+1][T_s][cpad] = (log max(|X|,1e-6), Re X/max(|X|,1e-6), Im ...)
+// followed by cpad - 3 zero channels (cpad = 4: one element is one aligned 16-byte load for the first conv).
 constexpr int STFT_FR = 8;
 
 __global__ void __launch_bounds__(256) stft_magphase_kernel(const float* __restrict__ wav, const float* __restrict__ scale, int L,
-                                                            int n_fft, int hop, int n_frames, float* __restrict__ feats) {
+                                                            int n_fft, int hop, int n_frames, int cpad, float* __restrict__ feats) {
     extern __shared__ __align__(16) float smem[];
     float* cs = smem;                 // [n_fft] cos(2 pi j / N)
     float* sn = cs + n_fft;           // [n_fft] sin(2 pi j / N)
@@ -237,19 +238,21 @@ __global__ void __launch_bounds__(256) stft_magphase_kernel(const float* __restr
         }
         const float mag = hypotf(re, im);
         const float cl = fmaxf(mag, 1e-6f);
-        float* dst = feats + (((long long)b * n_bins + k) * n_frames + m) * 3;
+        float* dst = feats + (((long long)b * n_bins + k) * n_frames + m) * cpad;
         dst[0] = logf(cl);
         dst[1] = re / cl;
         dst[2] = im / cl;
+        for (int c = 3; c < cpad; ++c) dst[c] = 0.f;
     }
 }
 
 cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, int L, int n_fft, int hop, int n_frames,
-                                 float* feats, cudaStream_t st) {
+                                 int cpad, float* feats, cudaStream_t st) {
+    if (cpad < 3) return cudaErrorInvalidValue;
     const size_t smem = ((size_t)4 * n_fft + (STFT_FR - 1) * hop) * sizeof(float);
     cudaError_t e = ensure_dynamic_smem((const void*)stft_magphase_kernel, 100 * 1024);
     if (e != cudaSuccess) return e;
-    stft_magphase_kernel<<<dim3((n_frames + STFT_FR - 1) / STFT_FR, B), 256, smem, st>>>(wav, scale, L, n_fft, hop, n_frames, feats);
+    stft_magphase_kernel<<<dim3((n_frames + STFT_FR - 1) / STFT_FR, B), 256, smem, st>>>(wav, scale, L, n_fft, hop, n_frames, cpad, feats);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,13 @@
 //     a third TMEM region (running totals) with round-to-nearest CUDA-core adds, then run the epilogue
 //     (bias, channels-last store, GroupNorm partial sums) on the last group.
 // Roofline: tensor pipe (3 MMAs per fp32-equivalent product) for C_in*K >= 128; HBM for the C <= 64 layers.
+//
+// FREQ = true is the FreqCodec 2-D mode (SConv2d / SConvTranspose2d, conv.py:317-447): a "clip" of the tile list is a
+// pseudo-clip (clip b, output frequency row f_out) and the gathered input channel cg = kf*cin + c of a chunk comes from
+// frequency row f_out*SF + kf - pad_f (reflect / zero indexed) of the [B][F][T][cin] input, so a 32-channel chunk holds
+// 32/cin frequency taps (cin < 32) or a 32-channel slice of one tap; everything downstream of the producers (weight
+// slabs [tap kt][cg][co], MMA issue, folding) is the 1-D machinery.  The epilogue scatters the phases of a transposed
+// conv (co -> (pf, pt, channel)) and can store fewer channels than the padded n-tile (the 32 -> 3 output conv).
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_sm100.cuh"
@@ -82,7 +89,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
     return t;
 }
 
-template <int N_TILE>
+template <int N_TILE, bool FREQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
                                                                  const int n_tiles, const int w_resident, const int group_mmas) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
@@ -138,23 +145,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
         while (tile < n_tiles) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
-            const int b = tl.b, t0 = tl.tt * TC_M;
-            const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
-            const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
-            const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
-            const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
+            const int t0 = tl.tt * TC_M;
+            int b = tl.b, f_out = 0;
+            if (FREQ) { b = tl.b / p.fq.F_out; f_out = tl.b - b * p.fq.F_out; }
+            const int pitch = FREQ ? p.fq.cin : C_in;          // channels per stored input row
+            const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * pitch;
+            const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * pitch : nullptr;
+            const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
+            const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
             for (; unit < n_units && tile == cur_tile; ) {
                 const int chunk = unit / S, ph = unit - chunk * S;
                 const uint32_t par = aphase ^ 1;
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
-                const int c = chunk * TC_KC + jchunk * 4;
-                const bool c_ok = c < C_in;
+                int c = chunk * TC_KC + jchunk * 4;
+                bool c_ok = c < C_in;
+                const float* xu0 = x0;
+                const float* xu1 = x1;
+                if (FREQ) {
+                    // gathered channel -> (frequency tap, stored channel); the tap selects the input row of this thread
+                    const int kf = c / pitch;
+                    c -= kf * pitch;
+                    int f_src = f_out * p.fq.SF + kf - p.fq.pad_f;
+                    if (p.pad_zero) c_ok = c_ok && f_src >= 0 && f_src < p.fq.F_in;
+                    else f_src = reflect_index(f_src, p.fq.F_in);
+                    if (!c_ok) f_src = 0;
+                    xu0 = x0 + (long long)(p.fq.f_off0 + f_src) * p.fq.T_raw0 * pitch;
+                    if (has1) xu1 = x1 + (long long)(p.fq.f_off1 + f_src) * p.fq.T_raw1 * pitch;
+                }
                 float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
                 if (!c_ok) { a0 = b0; a1 = b0; }
-                else if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
-                if (c_ok && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
+                else if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
+                if (c_ok && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
                 // all row loads of the unit are issued before the ring slot is waited for
                 constexpr int NR = 5;                      // a_rows <= 160 = 5 passes of 32 rows
                 float4 xa[NR], xb[NR];
@@ -171,9 +194,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xb[i] = xa[i];
                     if (ok) {
-                        const long long off = (long long)src * C_in + c;
-                        xa[i] = __ldg(reinterpret_cast<const float4*>(x0 + off));
-                        if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(x1 + off));
+                        const long long off = (long long)src * pitch + c;
+                        xa[i] = __ldg(reinterpret_cast<const float4*>(xu0 + off));
+                        if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(xu1 + off));
                     }
                 }
                 mbar_wait_backoff(a_empty + as, par, 64);
@@ -299,6 +322,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const bool row_ok = t < p.T_out;
             float* orow = p.out + (long long)tl.b * p.out_clip_stride + (long long)t * p.C_out + (long long)tl.nt * N_TILE;
             const float* bias = p.bias + tl.nt * N_TILE;
+            long long frow = 0;                                       // FREQ: element row of (clip, f_out*FR, t*TR)
+            if (FREQ) {
+                const int fb = tl.b / p.fq.F_out, ff = tl.b - fb * p.fq.F_out;
+                frow = ((long long)fb * p.fq.F_out * p.fq.FR + (long long)ff * p.fq.FR) * ((long long)p.T_out * p.fq.TR) + (long long)t * p.fq.TR;
+            }
             float s = 0.f, ss = 0.f;
             for (int g = 0; g < n_groups; ++g, ++gcount) {
                 const int buf = (int)(gcount & 1);
@@ -321,6 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     if (!last) {
                         tmem_st_32x32b_x32(tot_base + (uint32_t)c0, v);
                     } else if (row_ok) {
+                        int ph = 0, cch = 0;                          // FREQ: phase and channel of output column c0 + j
+                        if (FREQ) {
+                            const int co = tl.nt * N_TILE + c0;
+                            ph = co / p.fq.Cc;
+                            cch = co - ph * p.fq.Cc;
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             if (c0 + j < N_TILE) {
@@ -331,7 +365,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
                                 s += (o.x + o.y) + (o.z + o.w);
                                 ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
-                                *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                                if (!FREQ) {
+                                    *reinterpret_cast<float4*>(orow + c0 + j) = o;
+                                } else {
+                                    // phase (pf, pt) of a transposed conv lands on row f_out*FR + pf, column t*TR + pt
+                                    const int pf = ph / p.fq.TR, pt = ph - pf * p.fq.TR;
+                                    float* dst = p.out + (frow + (long long)pf * p.T_out * p.fq.TR + pt) * p.fq.c_store + cch;
+                                    if ((p.fq.c_store & 3) == 0) {
+                                        if (cch < p.fq.c_store) *reinterpret_cast<float4*>(dst) = o;   // (padded columns: no store)
+                                    } else {                          // padded n-tile: only the real channels exist in HBM
+                                        if (cch + 0 < p.fq.c_store) dst[0] = o.x;
+                                        if (cch + 1 < p.fq.c_store) dst[1] = o.y;
+                                        if (cch + 2 < p.fq.c_store) dst[2] = o.z;
+                                        if (cch + 3 < p.fq.c_store) dst[3] = o.w;
+                                    }
+                                    cch += 4;
+                                    if (cch >= p.fq.Cc) { cch = 0; ++ph; }
+                                }
                             }
                         }
                     }
@@ -372,6 +422,12 @@ bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D) {
     return D == 1 && (C_in % TC_KC == 0 || C_in == 16) && C_out_eff % 16 == 0 && K >= 1 && S >= 1 && ((K - 1) / S) <= 16;
 }
 
+// 2-D mode: cin stored channels per input element, C_out_eff output columns of the (possibly n-tile padded) weight image
+bool conv_tc_supported_2d(int cin, int C_out_eff, int KT, int ST) {
+    const bool cin_ok = cin % 4 == 0 && (cin % TC_KC == 0 || TC_KC % cin == 0);   // a thread's 4 channels share one tap
+    return cin_ok && C_out_eff % 16 == 0 && KT >= 1 && ST >= 1 && ((KT - 1) / ST) <= 16;
+}
+
 int conv_tc_n_tile(int C_out_eff) {
     if (C_out_eff >= 128 && C_out_eff % 128 == 0) return 128;
     if (C_out_eff % 64 == 0) return 64;
@@ -387,9 +443,9 @@ static int g_num_sms = 0;
 
 static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0;
 
-template <int N_TILE>
+template <int N_TILE, bool FREQ>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
-    auto kern = conv1d_tc_kernel<N_TILE>;
+    auto kern = conv1d_tc_kernel<N_TILE, FREQ>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
@@ -432,11 +488,12 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
     *nparts = n_tt * n_nt;
     const int n_tiles = n_tt * n_nt * B;
+    const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
     switch (p.n_tile) {
-        case 16: return launch_tc_n<16>(p, st, na, nb, L.total, n_tiles, resident);
-        case 32: return launch_tc_n<32>(p, st, na, nb, L.total, n_tiles, resident);
-        case 64: return launch_tc_n<64>(p, st, na, nb, L.total, n_tiles, resident);
-        case 128: return launch_tc_n<128>(p, st, na, nb, L.total, n_tiles, resident);
+        case 16: return freq ? launch_tc_n<16, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<16, false>(p, st, na, nb, L.total, n_tiles, resident);
+        case 32: return freq ? launch_tc_n<32, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<32, false>(p, st, na, nb, L.total, n_tiles, resident);
+        case 64: return freq ? launch_tc_n<64, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<64, false>(p, st, na, nb, L.total, n_tiles, resident);
+        case 128: return freq ? launch_tc_n<128, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<128, false>(p, st, na, nb, L.total, n_tiles, resident);
         default: return cudaErrorInvalidConfiguration;
     }
 }

@@ -81,19 +81,27 @@ struct fcb_handle {
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
+    int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
 
     // FreqCodec (arch 1) layers
     struct Conv2W {
         int cin = 0, cout = 0, kf = 0, kt = 0, sf = 1, st = 1;
+        int kf_eff = 0, kt_eff = 0;   // taps of the conv actually executed (2 x 2 for a transposed conv)
         bool transposed = false;
         float* w = nullptr; float* bias = nullptr; float* gamma = nullptr; float* beta = nullptr;
+        // tensor-core image (conv_tc.cu 2-D mode) of [kt][kf*cin][cout_tc]; cout_tc = C_out_eff rounded up to 16
+        float* w_tc = nullptr; float* bias_tc = nullptr;
+        int n_tile = 0, cout_tc = 0;
+        int tc_class = 0;    // 1: cin % 32 == 0; 2: cin < 32 (several frequency taps per chunk); 4: padded C_out
+        int out_pad[2][2] = {{0, 0}, {0, 0}};   // transposed conv out_padding {{f_l, f_r}, {t_l, t_r}} (conv.py:410-445)
     };
     struct ResBlock2W { Conv2W c1, c2, sc; };
     Conv2W f_enc_conv0, f_dec_final;
     std::vector<ResBlock2W> f_enc_rb, f_dec_rb;
     std::vector<Conv2W> f_enc_down, f_dec_up;
+    std::map<std::string, const Conv2W*> by_name2; // same for the 2-D layers (fcb_debug_conv2d)
 
     bool profiling = false;
     cudaEvent_t ev[FCB_NUM_PHASES + 1][2]{};
@@ -568,24 +576,56 @@ int run_decoder_time(Run& r, const float* emb, int n_frames, const float* scale,
 typedef fcb_handle::Conv2W Conv2W;
 typedef fcb_handle::ResBlock2W ResBlock2W;
 
-// SConv2d weight [cout][cin][kf][kt] -> [kt][kf*cin + ci][cout]
-int pack_conv2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int kf, int kt, int sf, int st, Conv2W* o) {
+// Tensor-core image of a packed 2-D layer wp = [kt][kf*cin][cout_eff] (the 1-D slab format with C_in = kf*cin gathered
+// channels); C_out_eff is zero-padded to a multiple of 16 (the 32 -> 3 output conv), bias alike.
+int pack_tc2d(fcb_handle* h, const std::vector<float>& wp, const std::vector<float>& bias, int cout_eff, Conv2W* o) {
+    o->n_tile = 0; o->tc_class = 0;
+    const int ck = o->kf_eff * o->cin, kt = o->kt_eff;
+    const int cout_tc = (cout_eff + 15) / 16 * 16;
+    if (!h->use_tc || !conv_tc_supported_2d(o->cin, cout_tc, kt, o->transposed ? 1 : o->st)) return FCB_OK;
+    if (cout_tc != cout_eff && o->transposed) return FCB_OK;
+    std::vector<float> img;
+    const int n_tile = conv_tc_n_tile(cout_tc);
+    if (cout_tc == cout_eff) {
+        build_tc_image(wp, kt, ck, cout_eff, n_tile, &img);
+        o->bias_tc = nullptr;
+    } else {
+        std::vector<float> wpad((size_t)kt * ck * cout_tc, 0.f), bpad(cout_tc, 0.f);
+        for (size_t r = 0; r < (size_t)kt * ck; ++r)
+            for (int co = 0; co < cout_eff; ++co) wpad[r * cout_tc + co] = wp[r * cout_eff + co];
+        for (int co = 0; co < cout_eff; ++co) bpad[co] = bias[co];
+        build_tc_image(wpad, kt, ck, cout_tc, n_tile, &img);
+        FCB_TRY(upload(h, bpad, &o->bias_tc));
+    }
+    FCB_TRY(upload(h, img, &o->w_tc));
+    o->n_tile = n_tile; o->cout_tc = cout_tc;
+    o->tc_class = cout_tc != cout_eff ? 4 : (o->cin % 32 == 0 ? 1 : 2);
+    return FCB_OK;
+}
+
+// SConv2d weight [cout][cin][kf][kt] -> [kt][kf*cin_store + ci][cout]; cin_store >= cin pads the stored input channels
+// with zero weights (the 3-channel mag_phase features are kept as 4 channels so that a frequency tap is one 16-byte load).
+int pack_conv2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int kf, int kt, int sf, int st, Conv2W* o,
+                int cin_store = 0) {
+    if (cin_store < cin) cin_store = cin;
     const HostTensor *w, *b, *g, *be;
     FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, kf, kt}, &w));
     FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
     FCB_TRY(need(h, prefix + ".conv.norm.weight", {cout}, &g));
     FCB_TRY(need(h, prefix + ".conv.norm.bias", {cout}, &be));
-    std::vector<float> p((size_t)kt * kf * cin * cout);
+    std::vector<float> p((size_t)kt * kf * cin_store * cout, 0.f);
     for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
             for (int a = 0; a < kf; ++a)
                 for (int c = 0; c < kt; ++c)
-                    p[(((size_t)c * kf + a) * cin + ci) * cout + co] = w->data[(((size_t)co * cin + ci) * kf + a) * kt + c];
-    o->cin = cin; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = sf; o->st = st; o->transposed = false;
+                    p[(((size_t)c * kf + a) * cin_store + ci) * cout + co] = w->data[(((size_t)co * cin + ci) * kf + a) * kt + c];
+    o->cin = cin_store; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = sf; o->st = st; o->transposed = false;
+    o->kf_eff = kf; o->kt_eff = kt;
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, b->data, &o->bias));
     FCB_TRY(upload(h, g->data, &o->gamma));
     FCB_TRY(upload(h, be->data, &o->beta));
+    FCB_TRY(pack_tc2d(h, p, b->data, cout, o));
     return FCB_OK;
 }
 
@@ -612,10 +652,12 @@ int pack_convtr2d(fcb_handle* h, const std::string& prefix, int cin, int cout, i
     for (int ph = 0; ph < fr * tr; ++ph)
         for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
     o->cin = cin; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = fr; o->st = tr; o->transposed = true;
+    o->kf_eff = 2; o->kt_eff = 2;
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, bias, &o->bias));
     FCB_TRY(upload(h, g->data, &o->gamma));
     FCB_TRY(upload(h, be->data, &o->beta));
+    FCB_TRY(pack_tc2d(h, p, bias, ce, o));
     return FCB_OK;
 }
 
@@ -655,8 +697,8 @@ InView2 view2_of(const Act2& a) {
     return v;
 }
 
-// SConv2d / SConvTranspose2d (non-causal).  out_padding = {{f_l, f_r}, {t_l, t_r}} of the transposed conv.
-int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W& L, const int (*out_pad)[2], Act2* out) {
+// SConv2d / SConvTranspose2d (non-causal).
+int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W& L, Act2* out) {
     fcb_handle* h = r.h;
     if (in0.C != L.cin) return fail(h, FCB_E_INVALID, "internal: 2-D channel mismatch");
     Conv2dParams p{};
@@ -688,8 +730,7 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
         o.F_raw = p.F_out * fr; o.T_raw = p.T_out * tr;
         const int pf = L.kf - fr, ptt = L.kt - tr;                            // conv.py:410-445
         const int pf_r = pf / 2, pf_l = pf - pf_r, pt_r = ptt / 2, pt_l = ptt - pt_r;
-        const int fo_l = out_pad ? out_pad[0][0] : 0, fo_r = out_pad ? out_pad[0][1] : 0;
-        const int to_l = out_pad ? out_pad[1][0] : 0, to_r = out_pad ? out_pad[1][1] : 0;
+        const int fo_l = L.out_pad[0][0], fo_r = L.out_pad[0][1], to_l = L.out_pad[1][0], to_r = L.out_pad[1][1];
         const int fl = pf_l - fo_l > 0 ? pf_l - fo_l : 0, frr = pf_r - fo_r > 0 ? pf_r - fo_r : 0;
         const int tl = pt_l - to_l > 0 ? pt_l - to_l : 0, trr = pt_r - to_r > 0 ? pt_r - to_r : 0;
         o.f_off = fl; o.t_off = tl;
@@ -700,14 +741,42 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * per_clip));
     o.owned = true;
     p.out = o.p;
-    const int nparts = conv2d_num_parts(p);
+    // tensor-core path (conv_tc.cu, 2-D mode) when the layer has a slab image and its class is enabled
+    const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && (h->use_tc2d & L.tc_class) != 0;
+    const int nparts = tc ? conv_tc_num_parts(p.T_out, L.cout_tc) : conv2d_num_parts(p);
     double* partials = nullptr;
     FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * p.F_out * nparts * 2 * sizeof(double)));
     FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
     FCB_TRY(alloc_f(r, &o.coef, (size_t)r.B * 2 * o.C));
     o.gamma = L.gamma; o.beta = L.beta;
     p.partials = partials;
-    FCB_CK(launch_conv2d(p, r.st));
+    if (tc) {
+        ConvParams q{};
+        q.in0.x = in0.p; q.in0.coef = in0.coef; q.in0.row_off = in0.t_off;
+        q.in0.clip_stride = (long long)in0.F_raw * in0.T_raw * in0.C;
+        if (in1) {
+            q.in1.x = in1->p; q.in1.coef = in1->coef; q.in1.row_off = in1->t_off;
+            q.in1.clip_stride = (long long)in1->F_raw * in1->T_raw * in1->C;
+        }
+        q.elu = p.elu;
+        q.T_in = in0.T; q.C_in = p.KF * in0.C;
+        q.K = p.KT; q.S = p.ST; q.D = 1; q.pad_l = p.pad_t; q.T_ext = in0.T; q.pad_zero = p.pad_zero;
+        q.w_tc = L.w_tc; q.n_tile = L.n_tile; q.bias = L.bias_tc ? L.bias_tc : L.bias;
+        q.out = o.p; q.T_out = p.T_out; q.C_out = L.cout_tc;
+        q.out_clip_stride = (long long)p.T_out * L.cout_tc;
+        q.partials = partials;
+        q.fq.KF = p.KF; q.fq.SF = p.SF; q.fq.pad_f = p.pad_f; q.fq.F_in = in0.F; q.fq.F_out = p.F_out; q.fq.cin = in0.C;
+        q.fq.T_raw0 = in0.T_raw; q.fq.f_off0 = in0.f_off;
+        q.fq.T_raw1 = in1 ? in1->T_raw : 0; q.fq.f_off1 = in1 ? in1->f_off : 0;
+        q.fq.FR = p.FR; q.fq.TR = p.TR;
+        q.fq.Cc = L.tc_class == 4 ? L.cout_tc : p.Cc;      // padded image: one phase of cout_tc columns, Cc real ones stored
+        q.fq.c_store = p.Cc;
+        int np2 = 0;
+        FCB_CK(launch_conv_tc(q, r.B * p.F_out, r.st, &np2));
+        if (np2 != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch (2-D)");
+    } else {
+        FCB_CK(launch_conv2d(p, r.st));
+    }
     FCB_CK(launch_stats_finalize(partials, p.F_out * nparts, (double)per_clip, h->cfg.gn_eps, 0, o.stats, r.B, r.st, L.gamma,
                                  L.beta, o.C, o.coef));
     h->launches += 2;
@@ -718,10 +787,10 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
 
 int run_resblock2d(Run& r, const Act2& x, const ResBlock2W& W, Act2* sc_out, Act2* blk_out) {
     Act2 h1, h2, sc;
-    FCB_TRY(run_conv2d(r, x, nullptr, true, W.c1, nullptr, &h1));
-    FCB_TRY(run_conv2d(r, h1, nullptr, true, W.c2, nullptr, &h2));
+    FCB_TRY(run_conv2d(r, x, nullptr, true, W.c1, &h1));
+    FCB_TRY(run_conv2d(r, h1, nullptr, true, W.c2, &h2));
     FCB_TRY(release2(r, h1));
-    FCB_TRY(run_conv2d(r, x, nullptr, false, W.sc, nullptr, &sc));
+    FCB_TRY(run_conv2d(r, x, nullptr, false, W.sc, &sc));
     *sc_out = sc; *blk_out = h2;
     return FCB_OK;
 }
@@ -752,19 +821,20 @@ int run_encoder_freq(Run& r, const float* wav, int L, float* scale_out, Act* out
     }
     const int n_bins = c.n_fft / 2 + 1, Ts = stft_frames(h, L);
     Act2 a;
-    FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * 3));
-    a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = 3;
-    FCB_CK(launch_stft_magphase(wav, scale, B, L, c.n_fft, c.stft_hop, Ts, a.p, r.st));
+    const int cfe = h->f_enc_conv0.cin;                 // 3 mag_phase features stored as 4 channels (pack_conv2d)
+    FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * cfe));
+    a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = cfe;
+    FCB_CK(launch_stft_magphase(wav, scale, B, L, c.n_fft, c.stft_hop, Ts, cfe, a.p, r.st));
     h->launches++;
     if (scale_owned) FCB_TRY(pool_free(r, scale));
     Act2 x;
-    FCB_TRY(run_conv2d(r, a, nullptr, false, h->f_enc_conv0, nullptr, &x));
+    FCB_TRY(run_conv2d(r, a, nullptr, false, h->f_enc_conv0, &x));
     FCB_TRY(release2(r, a));
     for (size_t i = 0; i < h->f_enc_rb.size(); ++i) {
         Act2 sc, blk, d;
         FCB_TRY(run_resblock2d(r, x, h->f_enc_rb[i], &sc, &blk));
         FCB_TRY(release2(r, x));
-        FCB_TRY(run_conv2d(r, sc, &blk, true, h->f_enc_down[i], nullptr, &d));
+        FCB_TRY(run_conv2d(r, sc, &blk, true, h->f_enc_down[i], &d));
         FCB_TRY(release2(r, sc));
         FCB_TRY(release2(r, blk));
         x = d;
@@ -814,11 +884,9 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
     sc.p = a.p; sc.F_raw = sc.F = 1; sc.T_raw = sc.T = a.T; sc.C = a.C; sc.stats = a.stats; sc.coef = a.coef;
     sc.gamma = a.gamma; sc.beta = a.beta; sc.owned = true;
     bool have_blk = false;
-    static const int last_out_pad[2][2] = {{0, 1}, {0, 0}};      // SEANetDecoder2d last_out_padding default
     for (size_t i = 0; i < h->f_dec_up.size(); ++i) {
         Act2 u;
-        const bool last = (i + 1 == h->f_dec_up.size());
-        FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_up[i], last ? last_out_pad : nullptr, &u));
+        FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_up[i], &u));
         FCB_TRY(release2(r, sc));
         if (have_blk) FCB_TRY(release2(r, blk));
         FCB_TRY(run_resblock2d(r, u, h->f_dec_rb[i], &sc, &blk));
@@ -826,7 +894,7 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
         have_blk = true;
     }
     Act2 f;
-    FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_final, nullptr, &f));
+    FCB_TRY(run_conv2d(r, sc, have_blk ? &blk : nullptr, true, h->f_dec_final, &f));
     FCB_TRY(release2(r, sc));
     if (have_blk) FCB_TRY(release2(r, blk));
     const int n_bins = c.n_fft / 2 + 1;
@@ -844,7 +912,7 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
 int finalize_freq(fcb_handle* h) {
     const fcb_config& c = h->cfg;
     const int nf = c.n_filters, D = c.dimension, nr = c.n_ratios;
-    FCB_TRY(pack_conv2d(h, "encoder.model.0", 3, nf, c.kernel_size, c.kernel_size, 1, 1, &h->f_enc_conv0));
+    FCB_TRY(pack_conv2d(h, "encoder.model.0", 3, nf, c.kernel_size, c.kernel_size, 1, 1, &h->f_enc_conv0, 4));
     int n = 1, mult = 1;
     for (int i = nr - 1; i >= 0; --i) {               // encoder applies the ratios reversed (seanet_encoder.py:288)
         const int fr = c.ratios_f[i], tr = c.ratios[i];
@@ -872,6 +940,7 @@ int finalize_freq(fcb_handle* h) {
         Conv2W up; ResBlock2W rb;
         FCB_TRY(pack_convtr2d(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, fr, tr, &up));
         FCB_TRY(pack_resblock2d(h, "decoder.model." + std::to_string(n + 2), mult * nf / 2, &rb));
+        if (i == nr - 1) up.out_pad[0][1] = 1;         // SEANetDecoder2d last_out_padding default [(0, 1), (0, 0)]
         h->f_dec_up.push_back(up); h->f_dec_rb.push_back(rb);
         mult /= 2; n += 3;
     }
@@ -954,6 +1023,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
+    { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
     cudaMemPool_t pool;
@@ -1073,6 +1143,27 @@ int fcb_finalize(fcb_handle* h) {
             h->by_name[pre + ".shortcut"] = &h->dec_rb[i].sc;
         }
         h->by_name["decoder.model." + std::to_string(nn + 1)] = &h->dec_final;
+    }
+    if (h->cfg.arch == 1) {   // name map for fcb_debug_conv2d
+        const fcb_config& cc = h->cfg;
+        h->by_name2["encoder.model.0"] = &h->f_enc_conv0;
+        int nn = 1;
+        for (size_t i = 0; i < h->f_enc_rb.size(); ++i, nn += 3) {
+            const std::string pre = "encoder.model." + std::to_string(nn);
+            h->by_name2[pre + ".block.1"] = &h->f_enc_rb[i].c1;
+            h->by_name2[pre + ".block.3"] = &h->f_enc_rb[i].c2;
+            h->by_name2[pre + ".shortcut"] = &h->f_enc_rb[i].sc;
+            h->by_name2["encoder.model." + std::to_string(nn + 2)] = &h->f_enc_down[i];
+        }
+        nn = (cc.lstm_layers > 0 ? 2 : 1) + 1;          // decoder: conv0, [lstm], ReshapeModule
+        for (size_t i = 0; i < h->f_dec_up.size(); ++i, nn += 3) {
+            h->by_name2["decoder.model." + std::to_string(nn + 1)] = &h->f_dec_up[i];
+            const std::string pre = "decoder.model." + std::to_string(nn + 2);
+            h->by_name2[pre + ".block.1"] = &h->f_dec_rb[i].c1;
+            h->by_name2[pre + ".block.3"] = &h->f_dec_rb[i].c2;
+            h->by_name2[pre + ".shortcut"] = &h->f_dec_rb[i].sc;
+        }
+        h->by_name2["decoder.model." + std::to_string(nn + 1)] = &h->f_dec_final;
     }
     h->finalized = true;
     return FCB_OK;
@@ -1196,7 +1287,35 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
         h->use_tc = value != 0;
         return FCB_OK;
     }
+    if (strcmp(key, "use_tc2d") == 0) {     // bit mask of 2-D layer classes on the tensor-core path (see Conv2W::tc_class)
+        if (value < 0 || value > 7) return fail(h, FCB_E_INVALID, "use_tc2d must be a bit mask in [0, 7]");
+        h->use_tc2d = value;
+        return FCB_OK;
+    }
     return fail(h, FCB_E_INVALID, std::string("unknown option: ") + key);
+}
+
+int fcb_debug_conv2d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t F, int32_t T, int32_t elu,
+                     float* y, int64_t y_capacity, float* stats, int32_t* dims, void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!layer || !x || !y || !dims || B <= 0 || F <= 0 || T <= 0) return fail(h, FCB_E_INVALID, "fcb_debug_conv2d: bad arguments");
+    std::string n(layer);
+    auto it = h->by_name2.find(n);
+    if (it == h->by_name2.end()) return fail(h, FCB_E_INVALID, "fcb_debug_conv2d: unknown layer " + n);
+    const Conv2W* L = it->second;
+    Run r{h, B, (cudaStream_t)stream};
+    Act2 in;
+    in.p = const_cast<float*>(x); in.F_raw = in.F = F; in.T_raw = in.T = T; in.C = L->cin;
+    Act2 o;
+    FCB_TRY(run_conv2d(r, in, nullptr, elu != 0, *L, &o));
+    const long long total = (long long)B * o.F_raw * o.T_raw * o.C;
+    if (total > y_capacity) { release2(r, o); return fail(h, FCB_E_INVALID, "fcb_debug_conv2d: y too small"); }
+    FCB_CK(cudaMemcpyAsync(y, o.p, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+    if (stats) FCB_CK(cudaMemcpyAsync(stats, o.stats, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToDevice, r.st));
+    dims[0] = o.F_raw; dims[1] = o.T_raw; dims[2] = o.C; dims[3] = o.f_off; dims[4] = o.t_off; dims[5] = o.F; dims[6] = o.T;
+    dims[7] = L->cin;
+    FCB_TRY(release2(r, o));
+    return FCB_OK;
 }
 
 int fcb_debug_conv1d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t T, int32_t elu,

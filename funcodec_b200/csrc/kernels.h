@@ -24,6 +24,7 @@ cudaError_t launch_sumsq_partials(const float* x, int B, int L, double* partials
 
 // conv_tc.cu
 bool conv_tc_supported(int C_in, int C_out_eff, int K, int S, int D);
+bool conv_tc_supported_2d(int cin, int C_out_eff, int KT, int ST);
 int conv_tc_n_tile(int C_out_eff);
 int conv_tc_num_parts(int T_out, int C_out_eff);
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts);
@@ -32,7 +33,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
 int conv2d_num_parts(const Conv2dParams& p);
 cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st);
 cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, int L, int n_fft, int hop, int n_frames,
-                                 float* feats, cudaStream_t st);
+                                 int cpad, float* feats, cudaStream_t st);
 cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,
                          const float* scale, float* frames, float* out, int out_len, cudaStream_t st);
 

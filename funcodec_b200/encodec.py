@@ -125,6 +125,32 @@ class B200Encodec:
         n = B * t_out.value * c_out.value
         return y[:n].view(B, t_out.value, c_out.value), stats, row_off.value
 
+    def set_option(self, key: str, value: int) -> None:
+        """fcb_set_option ("use_tc" may only be cleared after construction; "use_tc2d" may change at any time)."""
+        self._ck(self._lib.fcb_set_option(self._h, key.encode(), int(value)), f"fcb_set_option({key})")
+
+    def debug_conv2d(self, layer: str, x_bftc: torch.Tensor, elu: bool = False):
+        """fcb_debug_conv2d test hook (FreqCodec): one packed 2-D layer on a plain channels-last input [B,F,T,C] ->
+        (raw y [B,F_raw,T_raw,C_out], stats [B,2], (f_off, t_off, F, T) logical window).  Inputs with fewer channels than
+        the layer stores (the 3 mag_phase features of encoder.model.0, stored as 4) are zero-padded."""
+        x = x_bftc.to(self.device, torch.float32)
+        B, F, T, C = x.shape
+        dims = (ctypes.c_int32 * 8)()
+        c_store = 4 if (layer == "encoder.model.0" and C == 3) else C
+        if c_store != C:
+            x = torch.cat([x, torch.zeros(B, F, T, c_store - C, device=self.device)], dim=-1)
+        x = x.contiguous()
+        cap = min(B * (F + 1) * (T + 1) * 4096, 1 << 28)      # >= B * F_raw * T_raw * C_out for every supported layer
+        y = torch.empty(cap, dtype=torch.float32, device=self.device)
+        stats = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self._lib.fcb_debug_conv2d(self._h, layer.encode(), _ptr(x), B, F, T, int(elu), _ptr(y), cap, _ptr(stats),
+                                                dims, self._stream()), f"fcb_debug_conv2d({layer})")
+        F_raw, T_raw, Co, f_off, t_off, Fl, Tl, cs = [int(v) for v in dims]
+        if cs != c_store:
+            raise ValueError(f"{layer} stores {cs} input channels, got {c_store}")
+        return y[:B * F_raw * T_raw * Co].view(B, F_raw, T_raw, Co), stats, (f_off, t_off, Fl, Tl)
+
     def _prep_speech(self, speech: torch.Tensor) -> torch.Tensor:
         if speech.dim() == 3:
             if speech.shape[1] != 1:

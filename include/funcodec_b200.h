@@ -147,6 +147,9 @@ FCB_API int fcb_get_phase_ms(fcb_handle* h, float* ms_out /* [FCB_NUM_PHASES] */
 
 /* Options (integer valued): "use_tc" 1/0 -- tensor-core (tcgen05) conv path vs fp32 SIMT path; must be set
  * before fcb_finalize to enable, may be cleared at any time.  Env FCB_DISABLE_TC=1 sets the default to 0. */
+/* "use_tc2d" (FreqCodec, arch 1): bit mask of the 2-D layer classes that run on the tensor-core path -- 1: C_in % 32 == 0,
+ * 2: C_in < 32 (several frequency taps per 32-channel chunk), 4: C_out padded to 16 (the 32 -> 3 output conv); default 7,
+ * 0 = every 2-D conv on the fp32 SIMT kernel.  May be changed at any time; env FCB_USE_TC2D=<mask> sets the default. */
 FCB_API int fcb_set_option(fcb_handle* h, const char* key, int32_t value);
 
 /* TEST HOOK (tests/test_gpu_layers.py): run ONE packed conv layer, addressed by its reference module prefix
@@ -157,6 +160,14 @@ FCB_API int fcb_set_option(fcb_handle* h, const char* key, int32_t value);
 FCB_API int fcb_debug_conv1d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t T, int32_t elu,
                              float* y, int64_t y_capacity, float* stats, int32_t* t_out, int32_t* c_out,
                              int32_t* row_off, void* stream);
+
+/* TEST HOOK (tests/test_gpu_freq.py), FreqCodec 2-D layers: x dev [B][F][T][C_store] plain channels-last input where
+ * C_store is the layer's stored input channel count (returned in dims[7]; 4 for "encoder.model.0": 3 features + one zero
+ * channel).  y dev receives the RAW output [B][F_raw][T_raw][C]; dims[8] = {F_raw, T_raw, C, f_off, t_off, F, T, C_store}:
+ * the logical window of a transposed conv is rows f_off..f_off+F-1, columns t_off..t_off+T-1 (unpad2d, conv.py:430-445);
+ * GroupNorm statistics cover the whole raw tensor. */
+FCB_API int fcb_debug_conv2d(fcb_handle* h, const char* layer, const float* x, int32_t B, int32_t F, int32_t T, int32_t elu,
+                             float* y, int64_t y_capacity, float* stats, int32_t* dims /* [8] */, void* stream);
 
 FCB_API const char* fcb_last_error(const fcb_handle* h);
 FCB_API void fcb_destroy(fcb_handle* h);

@@ -230,14 +230,44 @@ def rvq_decode(codes_qbt, embed):
 
 
 # --------------------------------------------------------------------------- L3 model (Encodec)
+def linear_overlap_add(frames, stride: int):
+    """_linear_overlap_add (codec_basic.py:77-116): triangular weights taken from the FIRST frame's length (a shorter
+    later frame uses the leading part of the same triangle), weighted sum / sum of weights."""
+    total_size = stride * (len(frames) - 1) + frames[-1].shape[-1]
+    frame_length = frames[0].shape[-1]
+    t = torch.linspace(0, 1, frame_length + 2, dtype=frames[0].dtype)[1:-1]
+    weight = 0.5 - (t - 0.5).abs()
+    sum_weight = torch.zeros(total_size, dtype=frames[0].dtype)
+    out = torch.zeros(*frames[0].shape[:-1], total_size, dtype=frames[0].dtype)
+    offset = 0
+    for frame in frames:
+        n = frame.shape[-1]
+        out[..., offset:offset + n] += weight[:n] * frame
+        sum_weight[offset:offset + n] += weight[:n]
+        offset += stride
+    return out / sum_weight
+
+
+def segment_plan(length: int, sample_rate: int, segment_dur, overlap_ratio: float):
+    """(segment_length, stride, offsets) of Encodec._encode (codec_basic.py:287-298,346-358)."""
+    if segment_dur is None:
+        return length, length, [0]
+    seg = int(segment_dur * sample_rate)
+    stride = max(1, int((1 - overlap_ratio) * seg))
+    return seg, stride, list(range(0, length, stride))
+
+
 class OracleEncodec:
     """Restatement of Encodec's inference methods (funcodec/models/codec_basic.py:670-836) for the
-    named configs: time_group_norm, non-causal, audio_normalize, segment_dur=None, use_ddp RVQ
-    without projections (CostumeQuantizer, costume_quantizer.py:77-119)."""
+    named configs: time_group_norm, non-causal, audio_normalize, use_ddp RVQ without projections
+    (CostumeQuantizer, costume_quantizer.py:77-119); segment_dur=None (one frame) or a segment length in seconds
+    (per-segment normalisation / encode / decode + linear overlap-add, codec_basic.py:334-359,382-396)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], ratios: Sequence[int], sample_rate: int = 16000,
                  lstm_layers: int = 2, audio_normalize: bool = True, dtype=torch.float32,
-                 manual_lstm: bool = False):
+                 manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01):
+        self.segment_dur = segment_dur
+        self.overlap_ratio = overlap_ratio
         sd = {k: v.detach().to("cpu", dtype) if v.is_floating_point() else v.detach().cpu()
               for k, v in state_dict.items()}
         self.enc = sub_dict(sd, "encoder.")
@@ -276,10 +306,12 @@ class OracleEncodec:
 
     @torch.no_grad()
     def inference(self, speech, need_recon=True, bit_width=None, use_scale=True, want_margin=False):
-        """Encodec.inference / inference_encoding (codec_basic.py:670-764), single segment."""
+        """Encodec.inference / inference_encoding (codec_basic.py:670-764)."""
         speech = speech.to(self.dtype)
         if speech.dim() == 2:
             speech = speech.unsqueeze(1)
+        if self.segment_dur is not None:
+            return self._inference_segmented(speech, need_recon, bit_width, use_scale, want_margin)
         emb, scale = self.encode_frame(speech)
         n_q = self.n_q_for(bit_width)
         quant, codes, sub, margins = rvq_forward(emb.permute(0, 2, 1), self.embed, n_q, want_margin)
@@ -290,6 +322,22 @@ class OracleEncodec:
         return dict(recon_speech=recon, code_indices=[codes],
                     code_embeddings=[(quant_btd, scale if use_scale else None)],
                     sub_quants=[sub], encoder_out=emb, margins=margins)
+
+    def _inference_segmented(self, speech, need_recon, bit_width, use_scale, want_margin):
+        seg, stride, offsets = segment_plan(speech.shape[-1], self.sample_rate, self.segment_dur, self.overlap_ratio)
+        n_q = self.n_q_for(bit_width)
+        idx, embs, subs, encs, margins, frames = [], [], [], [], [], []
+        for off in offsets:
+            emb, scale = self.encode_frame(speech[:, :, off:off + seg])
+            quant, codes, sub, mg = rvq_forward(emb.permute(0, 2, 1), self.embed, n_q, want_margin)
+            quant_btd = quant.permute(0, 2, 1)
+            idx.append(codes); subs.append(sub); encs.append(emb); margins.append(mg)
+            embs.append((quant_btd, scale if use_scale else None))
+            if need_recon:
+                frames.append(self.decode_frame(quant_btd, scale if use_scale else None))
+        recon = linear_overlap_add(frames, stride)[:, :, :speech.shape[-1]] if need_recon else None
+        return dict(recon_speech=recon, code_indices=idx, code_embeddings=embs, sub_quants=subs, encoder_out=encs,
+                    margins=margins)
 
     @torch.no_grad()
     def inference_decoding(self, token_idx_btq):

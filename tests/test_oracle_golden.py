@@ -152,3 +152,32 @@ def test_numpy_cross_check_conv_groupnorm():
          "m.conv.norm.weight": torch.from_numpy(gw), "m.conv.norm.bias": torch.from_numpy(gb)}
     got = O.sconv1d(torch.from_numpy(x), p, "m", stride=s).numpy()[0]
     assert np.abs(got - yn).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_model_inference_segmented(golden_dir, tag):
+    """segment_dur != None (codec_basic.py:287-298,334-359,382-396): per-segment scale / codes / embeddings and the
+    linear overlap-add, against the unmodified reference (tools/gen_golden_seg.py)."""
+    z = np.load(os.path.join(golden_dir, "model_small_ds320_segmented.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    sd = init_state_dict(cfg, int(z["seed"]))
+    dur, ov, B, L, _, seg, stride, n_seg = z[f"{tag}.meta"]
+    ora = O.OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers, segment_dur=float(dur), overlap_ratio=float(ov))
+    assert O.segment_plan(int(L), cfg.sample_rate, float(dur), float(ov))[:2] == (int(seg), int(stride))
+    r = ora.inference(torch.from_numpy(z[f"{tag}.wav"]))
+    assert len(r["code_indices"]) == int(n_seg)
+    for i in range(int(n_seg)):
+        assert np.array_equal(r["code_indices"][i].numpy(), z[f"{tag}.codes{i}"].astype(np.int64))
+        assert np.abs(r["code_embeddings"][i][0].numpy() - z[f"{tag}.quant{i}"]).max() <= 1e-6
+        assert np.array_equal(r["code_embeddings"][i][1].numpy(), z[f"{tag}.scale{i}"])
+        assert np.abs(r["encoder_out"][i].numpy() - z[f"{tag}.encoder_out{i}"]).max() <= 1e-6
+    assert r["recon_speech"].shape == z[f"{tag}.recon"].shape
+    assert np.abs(r["recon_speech"].numpy() - z[f"{tag}.recon"]).max() <= 1e-6
+
+
+def test_overlap_add_overrun_is_an_error():
+    """The reference cannot overlap-add a non-final frame that ends after the final one (codec_basic.py:112 raises);
+    the oracle keeps that behaviour."""
+    frames = [torch.ones(1, 1, 1920), torch.ones(1, 1, 1920), torch.ones(1, 1, 1600), torch.ones(1, 1, 640)]
+    with pytest.raises(RuntimeError):
+        O.linear_overlap_add(frames, 880)
