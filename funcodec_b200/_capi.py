@@ -24,6 +24,15 @@ class FcbConfig(Structure):
                 ("stft_hop", c_int32)]
 
 
+FCB_MAX_TAIL_SEGMENTS = 16
+
+
+class FcbSegmentPlan(Structure):
+    _fields_ = [("n_seg", c_int32), ("n_full", c_int32), ("n_tail", c_int32), ("frames_full", c_int32),
+                ("decoded_full", c_int32), ("tail_len", c_int32 * FCB_MAX_TAIL_SEGMENTS),
+                ("tail_frames", c_int32 * FCB_MAX_TAIL_SEGMENTS), ("total_frames", c_int64)]
+
+
 class FcbError(RuntimeError):
     pass
 
@@ -50,6 +59,9 @@ SYMBOLS = {
     "fcb_set_option": (c_int32, [c_void_p, c_char_p, c_int32]),
     "fcb_debug_conv1d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,
                                    POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "fcb_plan_segments": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "fcb_roundtrip_segmented": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "fcb_debug_conv2d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,
                                    POINTER(c_int32), c_void_p]),
     "fcb_last_error": (c_char_p, [c_void_p]),

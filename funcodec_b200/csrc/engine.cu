@@ -1252,6 +1252,116 @@ int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t
     return rc;
 }
 
+int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan) {
+    if (!h || !plan) return FCB_E_INVALID;
+    if (h->cfg.arch != 0) return fail(h, FCB_E_INVALID, "segmented processing supports the time-domain Encodec only");
+    if (L <= 0 || seg_len <= 0 || stride <= 0 || stride > seg_len)
+        return fail(h, FCB_E_INVALID, "fcb_plan_segments: need L > 0 and 0 < stride <= seg_len");
+    const int hop = h->hop();
+    fcb_segment_plan p{};
+    p.n_seg = (L + stride - 1) / stride;                                    // len(range(0, L, stride))
+    p.n_full = L >= seg_len ? (L - seg_len) / stride + 1 : 0;              // offsets with a whole segment left
+    if (p.n_full > p.n_seg) p.n_full = p.n_seg;
+    p.n_tail = p.n_seg - p.n_full;
+    if (p.n_tail > FCB_MAX_TAIL_SEGMENTS) return fail(h, FCB_E_INVALID, "fcb_plan_segments: too many short trailing segments (overlap too high)");
+    p.frames_full = (seg_len + hop - 1) / hop;
+    p.decoded_full = p.frames_full * hop;
+    p.total_frames = (int64_t)p.n_full * p.frames_full;
+    for (int i = 0; i < p.n_tail; ++i) {
+        p.tail_len[i] = L - (p.n_full + i) * stride;
+        p.tail_frames[i] = (p.tail_len[i] + hop - 1) / hop;
+        p.total_frames += p.tail_frames[i];
+    }
+    // _linear_overlap_add sizes its output from the LAST frame (codec_basic.py:101); an earlier frame that ends later raises
+    const int dl_last = p.n_tail ? p.tail_frames[p.n_tail - 1] * hop : p.decoded_full;
+    const long long total = (long long)stride * (p.n_seg - 1) + dl_last;
+    for (int i = 0; i < p.n_seg; ++i) {
+        const int dl = i < p.n_full ? p.decoded_full : p.tail_frames[i - p.n_full] * hop;
+        if ((long long)i * stride + dl > total)
+            return fail(h, FCB_E_INVALID, "segment plan not representable: a decoded segment ends after the final one "
+                                          "(the reference's _linear_overlap_add raises here)");
+    }
+    *plan = p;
+    return FCB_OK;
+}
+
+int fcb_roundtrip_segmented(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t seg_len, int32_t stride,
+                            int32_t n_q, int32_t use_scale, int64_t* codes, float* quant, float* scale, float* recon,
+                            void* stream) {
+    FCB_TRY(check_ready(h));
+    if (!wav || !codes || B <= 0) return fail(h, FCB_E_INVALID, "fcb_roundtrip_segmented: bad arguments");
+    if (B > 512) return fail(h, FCB_E_INVALID, "fcb_roundtrip_segmented: at most 512 clips per call (split the batch)");
+    fcb_segment_plan pl;
+    FCB_TRY(fcb_plan_segments(h, L, seg_len, stride, &pl));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = h->cfg.dimension, hop = h->hop();
+    const bool apply = use_scale && h->cfg.audio_normalize;
+    Run r{h, B, st};                       // owner of the temporaries that span the whole call
+    OlaParams ola{};
+    float* frames_full = nullptr;
+    if (recon && pl.n_full > 0) FCB_TRY(alloc_f(r, &frames_full, (size_t)pl.n_full * B * pl.decoded_full));
+    // ---- the full-length segments: one batch of n_full*B clips, in chunks of <= 512 clips
+    const int n_clips = pl.n_full * B, T0 = pl.frames_full;
+    for (int c0 = 0; c0 < n_clips; ) {
+        // whole segments per chunk when possible (gather writes segment-major blocks)
+        int segs = 512 / B;
+        if (segs < 1) segs = 1;
+        const int s0 = c0 / B;
+        if (segs > pl.n_full - s0) segs = pl.n_full - s0;
+        const int nc = segs * B;
+        Run rc{h, nc, st};
+        float* x = nullptr;
+        FCB_TRY(alloc_f(rc, &x, (size_t)nc * seg_len));
+        FCB_CK(launch_gather_segments(wav, B, L, seg_len, stride, s0, segs, x, st));
+        h->launches++;
+        float* q = quant ? quant + (size_t)c0 * T0 * D : nullptr;
+        float* sc = scale ? scale + c0 : nullptr;
+        if (!q) FCB_TRY(alloc_f(rc, &q, (size_t)nc * T0 * D));
+        if (!sc) FCB_TRY(alloc_f(rc, &sc, nc));
+        const bool whole = (nc == n_clips);
+        int64_t* cdst = codes + (size_t)c0 * T0;                         // [n_q][n_clips][T0], this chunk's clips
+        int64_t* ctmp = cdst;
+        if (!whole) FCB_TRY(pool_alloc(rc, (void**)&ctmp, (size_t)n_q * nc * T0 * sizeof(int64_t)));
+        FCB_TRY(do_encode(h, x, nc, seg_len, n_q, ctmp, q, sc, nullptr, nullptr, st));
+        if (!whole)
+            FCB_CK(cudaMemcpy2DAsync(cdst, (size_t)n_clips * T0 * sizeof(int64_t), ctmp, (size_t)nc * T0 * sizeof(int64_t),
+                                     (size_t)nc * T0 * sizeof(int64_t), n_q, cudaMemcpyDeviceToDevice, st));
+        if (recon) FCB_TRY(run_decoder(rc, q, T0, apply ? sc : nullptr, frames_full + (size_t)c0 * pl.decoded_full, pl.decoded_full));
+        c0 += nc;
+    }
+    // ---- the shorter trailing segments, one by one
+    size_t code_off = (size_t)n_q * n_clips * T0, quant_off = (size_t)n_clips * T0 * D;
+    for (int i = 0; i < pl.n_tail; ++i) {
+        const int len = pl.tail_len[i], Ti = pl.tail_frames[i], dl = Ti * hop;
+        Run rc{h, B, st};
+        float* x = nullptr;
+        FCB_TRY(alloc_f(rc, &x, (size_t)B * len));
+        FCB_CK(launch_gather_segments(wav, B, L, len, stride, pl.n_full + i, 1, x, st));
+        h->launches++;
+        float* q = quant ? quant + quant_off : nullptr;
+        float* sc = scale ? scale + (size_t)(pl.n_full + i) * B : nullptr;
+        if (!q) FCB_TRY(alloc_f(rc, &q, (size_t)B * Ti * D));
+        if (!sc) FCB_TRY(alloc_f(rc, &sc, B));
+        FCB_TRY(do_encode(h, x, B, len, n_q, codes + code_off, q, sc, nullptr, nullptr, st));
+        if (recon) {
+            float* fr = nullptr;
+            FCB_TRY(alloc_f(r, &fr, (size_t)B * dl));
+            FCB_TRY(run_decoder(rc, q, Ti, apply ? sc : nullptr, fr, dl));
+            ola.tail[i] = fr; ola.tail_dl[i] = dl;
+        }
+        code_off += (size_t)n_q * B * Ti;
+        quant_off += (size_t)B * Ti * D;
+    }
+    if (recon) {
+        ola.full = frames_full; ola.n_seg = pl.n_seg; ola.n_full = pl.n_full;
+        ola.dl0 = pl.n_full > 0 ? pl.decoded_full : ola.tail_dl[0];       // weights come from the FIRST frame's length
+        ola.stride = stride; ola.B = B; ola.out_len = L; ola.out = recon;
+        FCB_CK(launch_overlap_add(ola, st));
+        h->launches++;
+    }
+    return FCB_OK;
+}
+
 int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t L, int32_t n_q, int32_t use_scale,
                        int64_t* codes_host, float* recon_host, void* stream) {
     FCB_TRY(check_ready(h));

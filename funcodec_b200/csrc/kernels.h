@@ -74,5 +74,16 @@ cudaError_t launch_embed_sum(const long long* codes, int q_major, const float* e
 cudaError_t launch_final_output(const float* raw, const float* stats, const float* gamma, const float* beta,
                                 const float* scale, int B, int T_raw, int out_len, float* out, cudaStream_t st);
 cudaError_t launch_fill(float* p, float v, long long n, cudaStream_t st);
+cudaError_t launch_gather_segments(const float* wav, int B, int L, int seg_len, int stride, int s0, int n_seg, float* out,
+                                   cudaStream_t st);
+constexpr int OLA_MAX_TAILS = 16;
+struct OlaParams {
+    const float* full;                 // decoded full-length segments [(s*B + b)][dl0]
+    const float* tail[OLA_MAX_TAILS];  // decoded shorter trailing segments [B][tail_dl[i]]
+    int tail_dl[OLA_MAX_TAILS];
+    int n_seg, n_full, dl0, stride, B, out_len;
+    float* out;                        // [B][out_len]
+};
+cudaError_t launch_overlap_add(const OlaParams& p, cudaStream_t st);
 
 }  // namespace fcb

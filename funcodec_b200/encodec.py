@@ -38,8 +38,12 @@ class B200Encodec:
     """Inference-only stand-in for funcodec.models.codec_basic.Encodec backed by the CUDA library."""
 
     def __init__(self, cfg: CodecConfig, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
-                 options: Optional[Dict[str, int]] = None):
+                 options: Optional[Dict[str, int]] = None, segment_dur: Optional[float] = None,
+                 overlap_ratio: Optional[float] = None):
         self.cfg = cfg
+        # Encodec(segment_dur=, overlap_ratio=) (codec_basic.py:143-144,218-219); the shipped YAMLs set both to null
+        self.segment_dur = segment_dur
+        self.overlap_ratio = overlap_ratio
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _capi.FcbError("B200Encodec needs a CUDA device; there is no CPU path")
@@ -125,6 +129,52 @@ class B200Encodec:
         n = B * t_out.value * c_out.value
         return y[:n].view(B, t_out.value, c_out.value), stats, row_off.value
 
+    @property
+    def segment_length(self) -> Optional[int]:        # codec_basic.py:287-291
+        return None if self.segment_dur is None else int(self.segment_dur * self.sample_rate)
+
+    @property
+    def segment_stride(self) -> Optional[int]:        # codec_basic.py:293-298
+        seg = self.segment_length
+        return None if seg is None else max(1, int((1 - self.overlap_ratio) * seg))
+
+    def plan_segments(self, L: int) -> "_capi.FcbSegmentPlan":
+        plan = _capi.FcbSegmentPlan()
+        self._ck(self._lib.fcb_plan_segments(self._h, L, self.segment_length, self.segment_stride, ctypes.byref(plan)),
+                 "fcb_plan_segments")
+        return plan
+
+    def _inference_segmented(self, x: torch.Tensor, need_recon: bool, n_q: int, use_scale: bool):
+        """Encodec.inference with segment_dur != None (codec_basic.py:334-359,382-396,695-718): one list entry per segment,
+        recon_speech = linear overlap-add of the decoded segments trimmed to L.  sub_quants are not produced here."""
+        B, L = x.shape
+        plan = self.plan_segments(L)
+        D, dev = self.cfg.dimension, self.device
+        nf, T0 = plan.n_full, plan.frames_full
+        codes = torch.empty(n_q * B * plan.total_frames, dtype=torch.int64, device=dev)
+        quant = torch.empty(B * plan.total_frames * D, dtype=torch.float32, device=dev)
+        scale = torch.empty((plan.n_seg, B, 1), dtype=torch.float32, device=dev)
+        recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev) if need_recon else None
+        with torch.cuda.device(dev):
+            self._ck(self._lib.fcb_roundtrip_segmented(self._h, _ptr(x), B, L, self.segment_length, self.segment_stride, n_q,
+                                                       int(use_scale), _ptr(codes), _ptr(quant), _ptr(scale), _ptr(recon),
+                                                       self._stream()), "fcb_roundtrip_segmented")
+        idx, embs = [], []
+        with_scale = use_scale and self.audio_normalize
+        cfull = codes[:n_q * nf * B * T0].view(n_q, nf, B, T0)
+        qfull = quant[:nf * B * T0 * D].view(nf, B, T0, D)
+        for s in range(nf):
+            idx.append(cfull[:, s])
+            embs.append((qfull[s], scale[s] if with_scale else None))
+        co, qo = n_q * nf * B * T0, nf * B * T0 * D
+        for i in range(plan.n_tail):
+            Ti = plan.tail_frames[i]
+            idx.append(codes[co:co + n_q * B * Ti].view(n_q, B, Ti))
+            embs.append((quant[qo:qo + B * Ti * D].view(B, Ti, D), scale[nf + i] if with_scale else None))
+            co += n_q * B * Ti
+            qo += B * Ti * D
+        return dict(recon_speech=recon, code_indices=idx, code_embeddings=embs, sub_quants=[None] * plan.n_seg)
+
     def set_option(self, key: str, value: int) -> None:
         """fcb_set_option ("use_tc" may only be cleared after construction; "use_tc2d" may change at any time)."""
         self._ck(self._lib.fcb_set_option(self._h, key.encode(), int(value)), f"fcb_set_option({key})")
@@ -171,6 +221,8 @@ class B200Encodec:
         Tf = self.num_frames(L)
         # the reference slices self.layers[:n_q] (ddp_core_vq.py:386): a bandwidth above the maximum uses every stage
         n_q = min(self.cfg.num_quantizers_for_bandwidth(bit_width), self.cfg.num_quantizers)
+        if self.segment_dur is not None:
+            return self._inference_segmented(x, need_recon, n_q, use_scale)
         D = self.cfg.dimension
         dev = self.device
         codes = torch.empty((n_q, B, Tf), dtype=torch.int64, device=dev)

@@ -38,8 +38,8 @@ def config_from_reference_model(model) -> CodecConfig:
         raise UnsupportedReferenceModel("weight_norm parametrisation is not supported (norm must be time_group_norm)")
     if "encoder.model.0.conv.norm.weight" not in sd:
         raise UnsupportedReferenceModel("norm must be time_group_norm")
-    if getattr(model, "segment_dur", None) is not None:
-        raise UnsupportedReferenceModel("segment_dur must be null (whole-utterance processing)")
+    if getattr(model, "segment_dur", None) is not None and freq:
+        raise UnsupportedReferenceModel("segment_dur must be null for FreqCodec (whole-utterance processing)")
     if getattr(q, "input_proj", None) is not None or getattr(q, "input_act", None) is not None:
         raise UnsupportedReferenceModel("quantizer projections / codec_range are not supported")
     if "quantizer.rq.model.embed" not in sd:
@@ -68,4 +68,5 @@ def config_from_reference_model(model) -> CodecConfig:
 def wrap_reference_encodec(model, device: str = "cuda:0"):
     from .encodec import B200Encodec
     cfg = config_from_reference_model(model)
-    return B200Encodec(cfg, model.state_dict(), device)
+    return B200Encodec(cfg, model.state_dict(), device, segment_dur=getattr(model, "segment_dur", None),
+                       overlap_ratio=getattr(model, "overlap_ratio", None))

@@ -132,6 +132,32 @@ FCB_API int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L,
 FCB_API int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t L, int32_t n_q,
                        int32_t use_scale, int64_t* codes_host, float* recon_host, void* stream);
 
+/* ---- segment_dur != None (Encodec.segment_length / segment_stride / _encode / _decode, codec_basic.py:287-298,334-359,
+ * 382-396; _linear_overlap_add :77-116).  The clip is cut at offsets 0, stride, 2*stride, ... < L into segments of
+ * seg_len samples (the last ones shorter); every segment is normalised, encoded, quantized and decoded on its own and
+ * the decoded segments are cross-faded.  seg_len = int(segment_dur * sample_rate),
+ * stride = max(1, int((1 - overlap_ratio) * seg_len)) are computed by the caller exactly like the reference properties.
+ * The n_full full-length segments run as ONE batch of n_full*B clips (clip index s*B + b); the n_tail shorter trailing
+ * segments run one by one.  Time-domain Encodec (arch 0) only. */
+#define FCB_MAX_TAIL_SEGMENTS 16
+typedef struct fcb_segment_plan {
+    int32_t n_seg, n_full, n_tail;       /* n_seg = n_full + n_tail = len(range(0, L, stride)) */
+    int32_t frames_full, decoded_full;   /* T' and T'*hop of a full segment */
+    int32_t tail_len[FCB_MAX_TAIL_SEGMENTS], tail_frames[FCB_MAX_TAIL_SEGMENTS];
+    int64_t total_frames;                /* n_full*frames_full + sum(tail_frames): frames per clip over all segments */
+} fcb_segment_plan;
+/* Fails (FCB_E_INVALID) when the reference would: more than FCB_MAX_TAIL_SEGMENTS short segments, or a non-final decoded
+ * segment ending after the final one (the reference's overlap-add raises a size mismatch there, codec_basic.py:112). */
+FCB_API int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan);
+/* Encodec.inference with segments.  Outputs (dev), full segments first then the tails in order:
+ *   codes  int64: [n_q][n_full*B][frames_full] followed, per tail i, by [n_q][B][tail_frames[i]]
+ *   quant  fp32 or NULL: [n_full*B][frames_full][D] followed by [B][tail_frames[i]][D] per tail
+ *   scale  fp32 or NULL: [n_seg][B]
+ *   recon  fp32 or NULL: [B][L] (NULL = encode only, Encodec.inference_encoding) */
+FCB_API int fcb_roundtrip_segmented(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t seg_len, int32_t stride,
+                                    int32_t n_q, int32_t use_scale, int64_t* codes, float* quant, float* scale,
+                                    float* recon, void* stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 FCB_API int64_t fcb_launch_count(const fcb_handle* h);
 /* Enable/disable per-phase device timing (CUDA events on `stream`); phase ids FCB_PHASE_*. */

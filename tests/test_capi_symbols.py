@@ -60,7 +60,9 @@ def test_config_from_reference_like_model():
     for f in ("ratios", "n_filters", "dimension", "kernel_size", "last_kernel_size", "residual_kernel_size", "lstm_layers",
               "codebook_size", "num_quantizers", "sample_rate", "audio_normalize"):
         assert getattr(got, f) == getattr(cfg, f), f
-    m.segment_dur = 1.0
+    m.segment_dur = 1.0                     # segmenting is handled by the wrapper (fcb_roundtrip_segmented), not the config
+    assert config_from_reference_model(m).ratios == cfg.ratios
+    m.quantizer.input_proj = object()
     with pytest.raises(UnsupportedReferenceModel):
         config_from_reference_model(m)
 
@@ -83,6 +85,10 @@ def test_config_from_reference_like_freqcodec():
     for f in ("arch", "ratios", "ratios_f", "n_fft", "stft_hop", "n_filters", "dimension", "kernel_size", "last_kernel_size",
               "residual_kernel_size", "lstm_layers", "codebook_size", "num_quantizers"):
         assert getattr(got, f) == getattr(cfg, f), f
+    m.segment_dur = 1.0
+    with pytest.raises(UnsupportedReferenceModel):
+        config_from_reference_model(m)
+    m.segment_dur = None
     m.codec_domain = ["stft", "stft"]
     with pytest.raises(UnsupportedReferenceModel):
         config_from_reference_model(m)

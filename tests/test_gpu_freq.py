@@ -1,6 +1,7 @@
 """GPU parity for the FreqCodec mag_phase variant (BASELINE config 4) through the C ABI:
 golden vectors from the unmodified reference + the CPU oracle (oracle/freqcodec_oracle.py) on seeded inputs."""
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -172,7 +173,7 @@ CASES2_SMALL = [
 def _check_conv2d_layer(model, sd, layer, cin, F, T, elu, tc2d):
     model.set_option("use_tc2d", tc2d)
     try:
-        g = torch.Generator().manual_seed(abs(hash((layer, F, T))) % (2 ** 31))
+        g = torch.Generator().manual_seed(zlib.crc32(f"{layer}/{cin}/{F}/{T}".encode()))     # reproducible across runs
         B = 2
         x = torch.randn(B, F, T, cin, generator=g)
         y, stats, win = model.debug_conv2d(layer, x, elu=elu)

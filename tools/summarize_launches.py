@@ -31,5 +31,5 @@ for k, (c, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"  {us / 1e3:9.3f} ms  {100 * us / all_us:5.1f}%  x{c:5d}  {k}")
 print("conv launches of the step (in order):")
 for i, name, g, b, us in step:
-    if "conv1d" in name or "rvq" in name or "igemm" in name:
+    if "conv1d" in name or "conv2d" in name or "rvq" in name or "igemm" in name:
         print(f"  id {i:6d} {us:10.1f} us grid {g:>18s} {name.split('(')[0][-60:]}")
