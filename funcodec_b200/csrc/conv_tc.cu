@@ -441,7 +441,7 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0;
+static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1;
 
 template <int N_TILE, bool FREQ>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
@@ -466,6 +466,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (const char* v = getenv("FCB_TC_GROUP_MMAS")) g_group_mmas = atoi(v) > 0 ? atoi(v) : TC_GROUP_MMAS;
         if (const char* v = getenv("FCB_TC_NA")) g_force_na = atoi(v);
         if (const char* v = getenv("FCB_TC_NB")) g_force_nb = atoi(v);
+        if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
     }
     // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
@@ -480,6 +481,12 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
         if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
         if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
+        // small n-tiles: a weight slab is only n_tile*256 bytes, so the ring is deepened until shared memory is full --
+        // every (chunk, tap) slab is a separate bulk copy whose ~1-2 us latency must be covered by the copies in flight
+        // (measured: the 32 -> 3 output conv of config 4, 49 slabs of 4 KB per tile, was bound by a 4-deep ring)
+        if (g_deep_ring)
+            while (nb < 24 && nb < n_slabs && tc_layout(p.K, p.S, p.n_tile, na, nb + 1).total <= 225 * 1024)
+                L = tc_layout(p.K, p.S, p.n_tile, na, ++nb);
         if (g_force_na > 0 && g_force_nb > 0) {
             const TcSmemLayout L2 = tc_layout(p.K, p.S, p.n_tile, g_force_na, g_force_nb);
             if (L2.total <= 225 * 1024 && g_force_na % 2 == 0) { na = g_force_na; nb = g_force_nb; L = L2; }
