@@ -55,10 +55,11 @@ struct TcSmemLayout {
     int a_stage;       // bytes per A stage (hi + lo)
     int b_stage;       // bytes per B stage (hi + lo)
     int na, nb;        // ring depths
-    int off_b, off_bar, total;
+    int off_b, off_stg, off_bar, total;
+    int stg_group;     // STAGE mode: bytes of raw-input staging per producer group (2 stages x n_in x a_rows x 128)
 };
 
-__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb) {
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb, int stg_inputs = 0) {
     TcSmemLayout L;
     const int qmax = (K - 1) / S;
     L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
@@ -66,7 +67,9 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     L.b_stage = 2 * n_tile * 128;
     L.na = na; L.nb = nb;
     L.off_b = na * L.a_stage;
-    L.off_bar = L.off_b + nb * L.b_stage;
+    L.off_stg = L.off_b + nb * L.b_stage;
+    L.stg_group = 2 * stg_inputs * L.a_rows * 128;
+    L.off_bar = L.off_stg + 2 * L.stg_group;
     L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
     return L;
 }
@@ -89,7 +92,7 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
     return t;
 }
 
-template <int N_TILE, bool FREQ>
+template <int N_TILE, bool FREQ, bool STAGE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
                                                                  const int n_tiles, const int w_resident, const int group_mmas) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
+    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, STAGE ? (has1 ? 2 : 1) : 0);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_units = n_chunks * S;
     const int upg = tc_units_per_group(K, S, group_mmas);
@@ -130,7 +133,130 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 16) {
+    if (STAGE && warp < 16) {
+        // =========================================================== producers, STAGE mode (experimental, off by default)
+        // The raw rows of a unit are fetched with per-thread cp.async (16 B each, zero-filled when out of range) into a
+        // staging area of the group one unit AHEAD of the unit being transformed, so the global-load latency of unit n+1
+        // overlaps the transform of unit n (the plain mode holds the rows in registers and serialises the two).  Every
+        // thread reads back only its own copies (cp.async.wait_group), so no extra barrier is involved.
+        const int grp = warp >> 3;
+        const int ptid = tid & (TC_PROD - 1);
+        const int jchunk = ptid & 7, rsub = ptid >> 3;
+        const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
+        const int pitch = FREQ ? p.fq.cin : C_in;
+        const uint32_t stg_in = (uint32_t)L.a_rows * 128u;                       // bytes per (stage, input)
+        const uint32_t stg_stage = (has1 ? 2u : 1u) * stg_in;
+        uint8_t* stg = smem_raw + L.off_stg + (uint32_t)grp * (uint32_t)L.stg_group + (uint32_t)jchunk * 16u;
+        constexpr int NR = 5;
+        // (tile, unit) -> this thread's source rows; returns the in-range mask of its NR rows
+        auto issue = [&](int tile, int unit, int st) -> uint32_t {
+            const TcTile tl = tc_tile(tile, n_nt, n_tt);
+            const int t0 = tl.tt * TC_M;
+            int b = tl.b, f_out = 0;
+            if (FREQ) { b = tl.b / p.fq.F_out; f_out = tl.b - b * p.fq.F_out; }
+            const int chunk = unit / S, ph = unit - chunk * S;
+            int c = chunk * TC_KC + jchunk * 4;
+            bool c_ok = c < C_in;
+            const float* xu0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * pitch;
+            const float* xu1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * pitch : nullptr;
+            if (FREQ) {
+                const int kf = c / pitch;
+                c -= kf * pitch;
+                int f_src = f_out * p.fq.SF + kf - p.fq.pad_f;
+                if (p.pad_zero) c_ok = c_ok && f_src >= 0 && f_src < p.fq.F_in;
+                else f_src = reflect_index(f_src, p.fq.F_in);
+                if (!c_ok) f_src = 0;
+                xu0 += (long long)(p.fq.f_off0 + f_src) * p.fq.T_raw0 * pitch;
+                if (has1) xu1 += (long long)(p.fq.f_off1 + f_src) * p.fq.T_raw1 * pitch;
+            }
+            uint8_t* dst = stg + (uint32_t)st * stg_stage;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int u = rsub + 32 * i;
+                if (u < L.a_rows) {
+                    const int gt = (t0 + u) * S + ph - p.pad_l;
+                    bool ok = c_ok && gt <= gt_max;
+                    int src = gt;
+                    if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
+                    else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
+                    const long long off = ok ? (long long)src * pitch + c : 0;      // !ok: any valid address, 0 bytes read
+                    cp_async16_zfill(dst + (uint32_t)u * 128u, (ok ? xu0 : p.in0.x) + off, ok ? 16u : 0u);
+                    if (has1) cp_async16_zfill(dst + stg_in + (uint32_t)u * 128u, (ok ? xu1 : p.in1.x) + off, ok ? 16u : 0u);
+                    mask |= (ok ? 1u : 0u) << i;
+                }
+            }
+            cp_async_commit();
+            return mask;
+        };
+        auto advance = [&](int& tile, int& unit) {
+            unit += 2;
+            while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+        };
+        int tile = blockIdx.x, unit = grp;
+        while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+        int as = grp % na_stages;
+        uint32_t aphase = 0;
+        int st = 0;
+        uint32_t m_cur = 0;
+        if (tile < n_tiles) m_cur = issue(tile, unit, 0);
+        while (tile < n_tiles) {
+            int ntile = tile, nunit = unit;
+            advance(ntile, nunit);
+            uint32_t m_nxt = 0;
+            if (ntile < n_tiles) m_nxt = issue(ntile, nunit, st ^ 1);
+            else cp_async_commit();                               // empty group: keeps the wait_group count uniform
+            cp_async_wait_group<1>();                              // this thread's copies of the CURRENT unit have landed
+            {
+                const TcTile tl = tc_tile(tile, n_nt, n_tt);
+                int b = tl.b;
+                if (FREQ) b = tl.b / p.fq.F_out;
+                const int chunk = unit / S;
+                int c = chunk * TC_KC + jchunk * 4;
+                const bool c_in = c < C_in;
+                if (FREQ) c -= (c / pitch) * pitch;
+                const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
+                const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
+                float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+                if (c_in && cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
+                if (c_in && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
+                uint8_t* hi = smA + as * L.a_stage;
+                uint8_t* lo = hi + L.a_rows * 128;
+                const uint8_t* srcb = stg + (uint32_t)st * stg_stage;
+                mbar_wait_backoff(a_empty + as, aphase ^ 1, 64);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int u = rsub + 32 * i;
+                    if (u < L.a_rows) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((m_cur >> i) & 1u) {
+                            const float4 xv = *reinterpret_cast<const float4*>(srcb + (uint32_t)u * 128u);
+                            v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
+                            v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
+                            if (has1) {
+                                const float4 yv = *reinterpret_cast<const float4*>(srcb + stg_in + (uint32_t)u * 128u);
+                                v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
+                                v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
+                            }
+                            if (p.elu) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
+                        }
+                        float4 h, l;
+                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                        const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
+                        *reinterpret_cast<float4*>(hi + o) = h;
+                        *reinterpret_cast<float4*>(lo + o) = l;
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(a_full + as);
+                as += 2;
+                if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
+            }
+            tile = ntile; unit = nunit; m_cur = m_nxt; st ^= 1;
+        }
+        cp_async_wait_group<0>();
+    } else if (warp < 16) {
         // =========================================================== producers: transformed A slabs
         const int grp = warp >> 3;                  // this group takes the units with (global unit index) % 2 == grp
         const int ptid = tid & (TC_PROD - 1);
@@ -443,9 +569,9 @@ static int g_num_sms = 0;
 
 static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1;
 
-template <int N_TILE, bool FREQ>
+template <int N_TILE, bool FREQ, bool STAGE>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
-    auto kern = conv1d_tc_kernel<N_TILE, FREQ>;
+    auto kern = conv1d_tc_kernel<N_TILE, FREQ, STAGE>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
@@ -453,6 +579,15 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
     kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);
     return cudaGetLastError();
+}
+
+template <int N_TILE>
+static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident,
+                                   bool freq, bool stage) {
+    if (freq) return stage ? launch_tc_n<N_TILE, true, true>(p, st, na, nb, smem, n_tiles, resident)
+                           : launch_tc_n<N_TILE, true, false>(p, st, na, nb, smem, n_tiles, resident);
+    return stage ? launch_tc_n<N_TILE, false, true>(p, st, na, nb, smem, n_tiles, resident)
+                 : launch_tc_n<N_TILE, false, false>(p, st, na, nb, smem, n_tiles, resident);
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
@@ -472,24 +607,41 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
     // (A even: the two producer groups alternate slots).
     const int n_slabs = ((p.C_in + TC_KC - 1) / TC_KC) * p.K;
+    const int limit = 225 * 1024;
     int resident = 0, na = 4, nb = 4;
+    bool stage = false;
     TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
-    if (n_slabs <= 64 && p.C_out == p.n_tile && L.total <= 225 * 1024) { resident = 1; nb = n_slabs; }   // one n-tile only
-    else {
-        L = tc_layout(p.K, p.S, p.n_tile, na, nb);
-        if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-        if (L.total > 225 * 1024) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-        if (L.total > 225 * 1024) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-        if (L.total > 225 * 1024) return cudaErrorInvalidConfiguration;
-        // small n-tiles: a weight slab is only n_tile*256 bytes, so the ring is deepened until shared memory is full --
-        // every (chunk, tap) slab is a separate bulk copy whose ~1-2 us latency must be covered by the copies in flight
-        // (measured: the 32 -> 3 output conv of config 4, 49 slabs of 4 KB per tile, was bound by a 4-deep ring)
-        if (g_deep_ring)
-            while (nb < 24 && nb < n_slabs && tc_layout(p.K, p.S, p.n_tile, na, nb + 1).total <= 225 * 1024)
-                L = tc_layout(p.K, p.S, p.n_tile, na, ++nb);
-        if (g_force_na > 0 && g_force_nb > 0) {
-            const TcSmemLayout L2 = tc_layout(p.K, p.S, p.n_tile, g_force_na, g_force_nb);
-            if (L2.total <= 225 * 1024 && g_force_na % 2 == 0) { na = g_force_na; nb = g_force_nb; L = L2; }
+    if (p.stage_in) {
+        // EXPERIMENTAL cp.async staging of the raw input (see the STAGE producer branch): needs room for two raw stages
+        // per producer group next to the A ring; tried with na = 4 then 2, weights resident if they fit, else a ring of >= 3
+        const int n_in = p.in1.x ? 2 : 1;
+        for (int try_na = 4; try_na >= 2 && !stage; try_na -= 2) {
+            TcSmemLayout Ls = tc_layout(p.K, p.S, p.n_tile, try_na, n_slabs, n_in);
+            if (n_slabs <= 64 && p.C_out == p.n_tile && Ls.total <= limit) { stage = true; resident = 1; na = try_na; nb = n_slabs; L = Ls; break; }
+            for (int try_nb = 6; try_nb >= 3; --try_nb) {
+                Ls = tc_layout(p.K, p.S, p.n_tile, try_na, try_nb, n_in);
+                if (Ls.total <= limit) { stage = true; na = try_na; nb = try_nb; L = Ls; break; }
+            }
+        }
+    }
+    if (!stage) {
+        if (n_slabs <= 64 && p.C_out == p.n_tile && L.total <= limit) { resident = 1; nb = n_slabs; }   // one n-tile only
+        else {
+            L = tc_layout(p.K, p.S, p.n_tile, na, nb);
+            if (L.total > limit) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+            if (L.total > limit) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+            if (L.total > limit) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+            if (L.total > limit) return cudaErrorInvalidConfiguration;
+            // small n-tiles: a weight slab is only n_tile*256 bytes, so the ring is deepened until shared memory is full
+            // (measured neutral on the config-4 output conv, whose limit turned out to be the producers; kept because a
+            // deeper ring can only hide more bulk-copy latency)
+            if (g_deep_ring)
+                while (nb < 24 && nb < n_slabs && tc_layout(p.K, p.S, p.n_tile, na, nb + 1).total <= limit)
+                    L = tc_layout(p.K, p.S, p.n_tile, na, ++nb);
+            if (g_force_na > 0 && g_force_nb > 0) {
+                const TcSmemLayout L2 = tc_layout(p.K, p.S, p.n_tile, g_force_na, g_force_nb);
+                if (L2.total <= limit && g_force_na % 2 == 0) { na = g_force_na; nb = g_force_nb; L = L2; }
+            }
         }
     }
     const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
@@ -497,10 +649,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     const int n_tiles = n_tt * n_nt * B;
     const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
     switch (p.n_tile) {
-        case 16: return freq ? launch_tc_n<16, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<16, false>(p, st, na, nb, L.total, n_tiles, resident);
-        case 32: return freq ? launch_tc_n<32, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<32, false>(p, st, na, nb, L.total, n_tiles, resident);
-        case 64: return freq ? launch_tc_n<64, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<64, false>(p, st, na, nb, L.total, n_tiles, resident);
-        case 128: return freq ? launch_tc_n<128, true>(p, st, na, nb, L.total, n_tiles, resident) : launch_tc_n<128, false>(p, st, na, nb, L.total, n_tiles, resident);
+        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
+        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
+        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
+        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
         default: return cudaErrorInvalidConfiguration;
     }
 }

@@ -82,6 +82,7 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
+    int tc_stage = 0;        // EXPERIMENTAL: cp.async-staged producer loads in conv_tc.cu ("tc_stage" option, FCB_TC_STAGE=1)
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
 
@@ -398,6 +399,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
     p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile;
+    p.stage_in = h->tc_stage;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
@@ -765,6 +767,7 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
         q.out = o.p; q.T_out = p.T_out; q.C_out = L.cout_tc;
         q.out_clip_stride = (long long)p.T_out * L.cout_tc;
         q.partials = partials;
+        q.stage_in = h->tc_stage;
         q.fq.KF = p.KF; q.fq.SF = p.SF; q.fq.pad_f = p.pad_f; q.fq.F_in = in0.F; q.fq.F_out = p.F_out; q.fq.cin = in0.C;
         q.fq.T_raw0 = in0.T_raw; q.fq.f_off0 = in0.f_off;
         q.fq.T_raw1 = in1 ? in1->T_raw : 0; q.fq.f_off1 = in1 ? in1->f_off : 0;
@@ -1023,6 +1026,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
+    { const char* e = getenv("FCB_TC_STAGE"); if (e && e[0] == '1') h->tc_stage = 1; }
     { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
@@ -1395,6 +1399,10 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     if (strcmp(key, "use_tc") == 0) {
         if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
         h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "tc_stage") == 0) {     // EXPERIMENTAL, not validated on hardware yet: cp.async-staged conv producers
+        h->tc_stage = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "use_tc2d") == 0) {     // bit mask of 2-D layer classes on the tensor-core path (see Conv2W::tc_class)
