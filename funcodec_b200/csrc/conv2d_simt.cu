@@ -190,6 +190,168 @@ cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st) {
     return cudaErrorInvalidConfiguration;
 }
 
+// =============================================================================================== small-C_out 2-D conv
+// EXPERIMENTAL (option "conv2d_small_cout", off by default, not yet run on hardware): the 32 -> 3 (7 x 7) output conv of
+// the FreqCodec decoder.  On the tensor-core path it wastes a 16-column n-tile on 3 outputs and re-transforms its input
+// once per frequency tap (13.6 ms at config 4); here one CTA stages the normalised + ELU'd input ONCE as a
+// (FT + K_F - 1) x (TT + K_T - 1) halo tile (8 channels at a time) and every thread keeps P = 5 adjacent time columns x
+// C_out <= 4 outputs in registers, sliding along the K_T taps (10.8 FMA per shared-memory load: FMA-bound).
+// Stride 1, reflect padding, no phase scatter.  Bound: fp32 FMA (38.8 GFMA per step at config 4).
+constexpr int SC_FT = 8, SC_P = 5, SC_TT = 32 * SC_P, SC_CIC = 8, SC_CO = 4, SC_KMAX = 7;
+
+__global__ void __launch_bounds__(256, 2) conv2d_small_cout_kernel(const Conv2dParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int tg = tid & 31, fr = tid >> 5;                   // time group (P columns), frequency row of this thread
+    const int b = blockIdx.z, f0 = blockIdx.y * SC_FT, t0 = blockIdx.x * SC_TT;
+    const int KF = p.KF, KT = p.KT, C_in = p.C_in;
+    const int HR = SC_FT + KF - 1, HC = SC_TT + KT - 1;       // halo rows / columns
+    // Xs[c4 (2)][HR][HC] float4: a lane's window starts at column tg*P, so the lane-to-lane stride is P = 5 float4 (odd)
+    // -> the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups: conflict-free 128-bit reads without padding
+    const int HCP = HC;
+    float4* Xs = reinterpret_cast<float4*>(smem);
+    float4* Ws = Xs + 2 * HR * HCP;                            // [KF][KT][c4 (2)][co (SC_CO)] float4 over the 4 channels of c4
+    const bool has1 = p.in1.x != nullptr;
+    const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
+    const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
+    const int CK = KF * C_in;
+
+    float acc[SC_P][SC_CO];
+#pragma unroll
+    for (int i = 0; i < SC_P; ++i)
+#pragma unroll
+        for (int j = 0; j < SC_CO; ++j) acc[i][j] = 0.f;
+
+    for (int ci0 = 0; ci0 < C_in; ci0 += SC_CIC) {
+        __syncthreads();
+        // ---- stage the halo tile of this channel chunk: deferred GroupNorm + resblock add + ELU applied once per element
+        for (int e = tid; e < 2 * HR * HC; e += 256) {
+            const int c4 = e & 1;
+            const int rc = e >> 1;
+            const int row = rc / HC, col = rc - row * HC;
+            const int c = ci0 + c4 * 4;
+            const int fs = reflect_index(f0 - p.pad_f + row, p.F_in);
+            const int ts = reflect_index(t0 - p.pad_t + col, p.T_in);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fs >= 0 && fs < p.F_in && ts >= 0 && ts < p.T_in) {
+                float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
+                const float4 x = __ldg(reinterpret_cast<const float4*>(
+                    p.in0.x + (((long long)b * p.in0.F_raw + p.in0.f_off + fs) * p.in0.T_raw + p.in0.t_off + ts) * C_in + c));
+                v.x = fmaf(x.x, a0.x, b0.x); v.y = fmaf(x.y, a0.y, b0.y); v.z = fmaf(x.z, a0.z, b0.z); v.w = fmaf(x.w, a0.w, b0.w);
+                if (has1) {
+                    float4 a1 = make_float4(1.f, 1.f, 1.f, 1.f), b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(
+                        p.in1.x + (((long long)b * p.in1.F_raw + p.in1.f_off + fs) * p.in1.T_raw + p.in1.t_off + ts) * C_in + c));
+                    v.x = v.x + fmaf(y.x, a1.x, b1.x); v.y = v.y + fmaf(y.y, a1.y, b1.y);
+                    v.z = v.z + fmaf(y.z, a1.z, b1.z); v.w = v.w + fmaf(y.w, a1.w, b1.w);
+                }
+                if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+            }
+            Xs[(c4 * HR + row) * HCP + col] = v;
+        }
+        // ---- weights of this chunk: Ws[((kf*KT + kt)*2 + c4)*SC_CO + co] = W[kt][kf*C_in + ci0 + c4*4 .. +3][co]
+        for (int e = tid; e < KF * KT * 2 * SC_CO; e += 256) {
+            const int co = e % SC_CO;
+            int r = e / SC_CO;
+            const int c4 = r & 1; r >>= 1;
+            const int kt = r % KT, kf = r / KT;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (co < p.C_out_eff) {
+                const float* wp = p.w + ((long long)kt * CK + kf * C_in + ci0 + c4 * 4) * p.C_out_eff + co;
+                w.x = __ldg(wp); w.y = __ldg(wp + p.C_out_eff); w.z = __ldg(wp + 2 * p.C_out_eff); w.w = __ldg(wp + 3 * p.C_out_eff);
+            }
+            Ws[e] = w;
+        }
+        __syncthreads();
+        // ---- compute: P sliding outputs x SC_CO channels per thread
+        for (int kf = 0; kf < KF; ++kf) {
+#pragma unroll
+            for (int c4 = 0; c4 < 2; ++c4) {
+                const float4* xr = Xs + (c4 * HR + fr + kf) * HCP;
+                float4 x[SC_P + SC_KMAX - 1];
+#pragma unroll
+                for (int j = 0; j < SC_P + SC_KMAX - 1; ++j) {
+                    x[j] = (j < SC_P + KT - 1) ? xr[tg * SC_P + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const float4* wr = Ws + ((kf * KT) * 2 + c4) * SC_CO;
+#pragma unroll
+                for (int kt = 0; kt < SC_KMAX; ++kt) {
+                    if (kt < KT) {
+                        const float4 w0 = wr[kt * 2 * SC_CO + 0], w1 = wr[kt * 2 * SC_CO + 1], w2 = wr[kt * 2 * SC_CO + 2],
+                                     w3 = wr[kt * 2 * SC_CO + 3];
+#pragma unroll
+                        for (int i = 0; i < SC_P; ++i) {
+                            const float4 xv = x[i + kt];
+                            acc[i][0] = fmaf(xv.x, w0.x, acc[i][0]); acc[i][0] = fmaf(xv.y, w0.y, acc[i][0]);
+                            acc[i][0] = fmaf(xv.z, w0.z, acc[i][0]); acc[i][0] = fmaf(xv.w, w0.w, acc[i][0]);
+                            acc[i][1] = fmaf(xv.x, w1.x, acc[i][1]); acc[i][1] = fmaf(xv.y, w1.y, acc[i][1]);
+                            acc[i][1] = fmaf(xv.z, w1.z, acc[i][1]); acc[i][1] = fmaf(xv.w, w1.w, acc[i][1]);
+                            acc[i][2] = fmaf(xv.x, w2.x, acc[i][2]); acc[i][2] = fmaf(xv.y, w2.y, acc[i][2]);
+                            acc[i][2] = fmaf(xv.z, w2.z, acc[i][2]); acc[i][2] = fmaf(xv.w, w2.w, acc[i][2]);
+                            acc[i][3] = fmaf(xv.x, w3.x, acc[i][3]); acc[i][3] = fmaf(xv.y, w3.y, acc[i][3]);
+                            acc[i][3] = fmaf(xv.z, w3.z, acc[i][3]); acc[i][3] = fmaf(xv.w, w3.w, acc[i][3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias, raw store of the real channels, GroupNorm partial statistics
+    float s = 0.f, ss = 0.f;
+    const int f = f0 + fr;
+    if (f < p.F_out) {
+#pragma unroll
+        for (int i = 0; i < SC_P; ++i) {
+            const int t = t0 + tg * SC_P + i;
+            if (t >= p.T_out) continue;
+            float* dst = p.out + (((long long)b * p.F_out + f) * p.T_out + t) * p.C_out_eff;
+#pragma unroll
+            for (int co = 0; co < SC_CO; ++co) {
+                if (co < p.C_out_eff) {
+                    const float o = acc[i][co] + __ldg(p.bias + co);
+                    dst[co] = o;
+                    s += o; ss = fmaf(o, o, ss);
+                }
+            }
+        }
+    }
+    if (p.partials) {
+        __shared__ double red[64];
+        double ds = (double)s, dss = (double)ss;
+        block_reduce_2d(ds, dss, red);
+        if (tid == 0) {
+            const int nparts = gridDim.x * gridDim.y;
+            double* dst = p.partials + ((long long)b * nparts + blockIdx.y * gridDim.x + blockIdx.x) * 2;
+            dst[0] = ds; dst[1] = dss;
+        }
+    }
+}
+
+bool conv2d_small_cout_supported(const Conv2dParams& p) {
+    return p.SF == 1 && p.ST == 1 && p.FR == 1 && p.TR == 1 && !p.pad_zero && p.C_out_eff <= SC_CO && p.C_in % SC_CIC == 0 &&
+           p.KF <= SC_KMAX && p.KT <= SC_KMAX && p.F_out == p.F_in && p.T_out == p.T_in;
+}
+
+// partial statistics per clip (the caller passes B * this many (sum, sum^2) pairs)
+int conv2d_small_cout_num_parts(const Conv2dParams& p) {
+    return ((p.T_out + SC_TT - 1) / SC_TT) * ((p.F_out + SC_FT - 1) / SC_FT);
+}
+
+cudaError_t launch_conv2d_small_cout(const Conv2dParams& p, cudaStream_t st) {
+    if (!conv2d_small_cout_supported(p)) return cudaErrorInvalidValue;
+    const int HR = SC_FT + p.KF - 1, HC = SC_TT + p.KT - 1, HCP = HC;
+    const size_t smem = ((size_t)2 * HR * HCP + (size_t)p.KF * p.KT * 2 * SC_CO) * sizeof(float4);
+    cudaError_t e = ensure_dynamic_smem((const void*)conv2d_small_cout_kernel, 110 * 1024);
+    if (e != cudaSuccess) return e;
+    if (smem > 110 * 1024) return cudaErrorInvalidConfiguration;
+    dim3 grid((p.T_out + SC_TT - 1) / SC_TT, (p.F_out + SC_FT - 1) / SC_FT, p.B);
+    conv2d_small_cout_kernel<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 // =============================================================================================== STFT front end
 // One CTA = 8 frames of one clip.  X[k] = sum_n (x[n]/scale) w[n] e^{-2 pi i k n / N}, then the mag_phase features
 // (codec_freq.py:365-373) written channels-last as [B][N/2+1][T_s][cpad] = (log max(|X|,1e-6), Re X/max(|X|,1e-6), Im ...)

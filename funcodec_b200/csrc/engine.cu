@@ -82,6 +82,7 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
+    int conv2d_small_cout = 0;   // EXPERIMENTAL: halo-tile SIMT kernel for the C_out <= 4 2-D conv ("conv2d_small_cout" option)
     int tc_stage = 0;        // EXPERIMENTAL: cp.async-staged producer loads in conv_tc.cu ("tc_stage" option, FCB_TC_STAGE=1)
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
@@ -744,10 +745,14 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
     o.owned = true;
     p.out = o.p;
     // tensor-core path (conv_tc.cu, 2-D mode) when the layer has a slab image and its class is enabled
-    const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && (h->use_tc2d & L.tc_class) != 0;
-    const int nparts = tc ? conv_tc_num_parts(p.T_out, L.cout_tc) : conv2d_num_parts(p);
+    // EXPERIMENTAL halo-tile kernel for C_out <= 4 (the 32 -> 3 output conv), "conv2d_small_cout" option
+    const bool small = h->conv2d_small_cout && !L.transposed && conv2d_small_cout_supported(p);
+    const bool tc = !small && h->use_tc && L.n_tile > 0 && L.w_tc && (h->use_tc2d & L.tc_class) != 0;
+    // statistics partials per clip: the pseudo-clip kernels emit n per output frequency row
+    const int nparts = small ? conv2d_small_cout_num_parts(p)
+                             : p.F_out * (tc ? conv_tc_num_parts(p.T_out, L.cout_tc) : conv2d_num_parts(p));
     double* partials = nullptr;
-    FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * p.F_out * nparts * 2 * sizeof(double)));
+    FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double)));
     FCB_TRY(alloc_f(r, &o.stats, (size_t)r.B * 2));
     FCB_TRY(alloc_f(r, &o.coef, (size_t)r.B * 2 * o.C));
     o.gamma = L.gamma; o.beta = L.beta;
@@ -776,11 +781,13 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
         q.fq.c_store = p.Cc;
         int np2 = 0;
         FCB_CK(launch_conv_tc(q, r.B * p.F_out, r.st, &np2));
-        if (np2 != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch (2-D)");
+        if (np2 * p.F_out != nparts) return fail(h, FCB_E_INVALID, "internal: partial count mismatch (2-D)");
+    } else if (small) {
+        FCB_CK(launch_conv2d_small_cout(p, r.st));
     } else {
         FCB_CK(launch_conv2d(p, r.st));
     }
-    FCB_CK(launch_stats_finalize(partials, p.F_out * nparts, (double)per_clip, h->cfg.gn_eps, 0, o.stats, r.B, r.st, L.gamma,
+    FCB_CK(launch_stats_finalize(partials, nparts, (double)per_clip, h->cfg.gn_eps, 0, o.stats, r.B, r.st, L.gamma,
                                  L.beta, o.C, o.coef));
     h->launches += 2;
     FCB_TRY(pool_free(r, partials));
@@ -1399,6 +1406,10 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     if (strcmp(key, "use_tc") == 0) {
         if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
         h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "conv2d_small_cout") == 0) {   // EXPERIMENTAL, not validated on hardware yet
+        h->conv2d_small_cout = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "tc_stage") == 0) {     // EXPERIMENTAL, not validated on hardware yet: cp.async-staged conv producers

@@ -32,6 +32,9 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
 // conv2d_simt.cu (FreqCodec 2-D path)
 int conv2d_num_parts(const Conv2dParams& p);
 cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st);
+bool conv2d_small_cout_supported(const Conv2dParams& p);          // EXPERIMENTAL: C_out <= 4 stride-1 conv (halo tile, FMA-bound)
+int conv2d_small_cout_num_parts(const Conv2dParams& p);
+cudaError_t launch_conv2d_small_cout(const Conv2dParams& p, cudaStream_t st);
 cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, int L, int n_fft, int hop, int n_frames,
                                  int cpad, float* feats, cudaStream_t st);
 cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,

@@ -63,3 +63,30 @@ def test_stage_mode_model_matches_default():
     same = (ra["code_indices"][0] == rb["code_indices"][0]).all(dim=0).float().mean().item()
     assert same >= 0.999, same
     assert (ra["recon_speech"] - rb["recon_speech"]).abs().max().item() <= 1e-5 or same < 1.0
+
+
+def test_small_cout_conv2d(golden_dir):
+    """`conv2d_small_cout`: the halo-tile SIMT kernel for the 32 -> 3 (and the small model's 4 -> 3) output conv against the
+    float64 truth, plus the config-4 architecture end to end with it."""
+    import test_gpu_freq as TF
+    cfg, sd, model, oracle = TF._full()
+    zs, cfgs, sds, models, _ = TF._small(golden_dir)
+    for m, s_, cases in ((model, sd, [("decoder.model.16", 32, 40, 150, True), ("decoder.model.16", 32, 257, 11, True),
+                                      ("decoder.model.16", 32, 9, 333, False)]),):
+        m.set_option("conv2d_small_cout", 1)
+        try:
+            for layer, cin, F, T, elu in cases:
+                TF._check_conv2d_layer(m, s_, layer, cin, F, T, elu, 7)
+        finally:
+            m.set_option("conv2d_small_cout", 0)
+    model.set_option("conv2d_small_cout", 1)
+    try:
+        g = torch.Generator().manual_seed(4)
+        wav = 0.1 * torch.randn(2, 8000, generator=g)
+        ora = oracle.inference(wav, want_margin=True)
+        quant = ora["code_embeddings"][0][0]
+        d = model.inference_decoding_emb(quant)
+        dref = oracle.decode_frame(quant, None)
+        assert (d["recon_speech"].cpu() - dref).abs().max().item() <= 1e-3
+    finally:
+        model.set_option("conv2d_small_cout", 0)
