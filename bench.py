@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): skip the host-buffer leg")
+    ap.add_argument("--e2e-mode", choices=["sharded-host", "scatter"], default="sharded-host",
+                    help="N > 1 end-to-end leg: every rank round-trips its own pinned host shard (default; the reference's "
+                         "multi-process inference), or rank 0 holds the whole batch and scatters / gathers it over NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -307,13 +310,17 @@ def main():
     e2e_ms, h2d, d2h = float("nan"), 0, 0
     if args.skip_e2e:
         pass
-    elif world == 1:
+    elif world == 1 or args.e2e_mode == "sharded-host":
+        # every rank owns its shard of the clips in ITS OWN pinned host memory and calls fcb_roundtrip_host on it: this is
+        # the reference's multi-GPU inference (N processes over a split wav.scp, encoding_decoding.sh:69-100) -- the path
+        # shards with no data-path collective
         hw = (0.1 * torch.randn(B, L, generator=g)).pin_memory()
         hc = torch.empty((n_q, B, Tf), dtype=torch.int64).pin_memory()
         hr = torch.empty((B, 1, L), dtype=torch.float32).pin_memory()
         for _ in range(2):
             model.roundtrip_host(hw, hc, hr)
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         e0.record()
         for _ in range(e2e_steps):
@@ -321,9 +328,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-        h2d = B * L * 4
-        d2h = hc.numel() * 8 + hr.numel() * 4
+        barrier()
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        h2d = world * B * L * 4
+        d2h = world * (hc.numel() * 8 + hr.numel() * 4)
     else:
+        # --e2e-mode scatter: ONE in-memory batch held by rank 0 spread over the GPUs of the box (NCCL scatter / gather)
         from funcodec_b200.parallel import ShardedCodec
         GB = world * B
 
@@ -397,7 +410,8 @@ def main():
                     clocks=clocks, gpu_launches=int(launches),
                     e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps,
-                             path="fcb_roundtrip_host (pinned host buffers)" if world == 1 else
+                             path="fcb_roundtrip_host (pinned host buffers, one shard per rank)"
+                                  if (world == 1 or args.e2e_mode == "sharded-host") else
                                   "rank0 pinned host -> H2D -> NCCL scatter -> fcb_roundtrip -> NCCL gather -> D2H"),
                     roofline=roofline, cpu_baseline=cpu, phase_ms_last_step=phases)
         print(json.dumps(line))
