@@ -181,3 +181,19 @@ def test_overlap_add_overrun_is_an_error():
     frames = [torch.ones(1, 1, 1920), torch.ones(1, 1, 1920), torch.ones(1, 1, 1600), torch.ones(1, 1, 640)]
     with pytest.raises(RuntimeError):
         O.linear_overlap_add(frames, 880)
+
+
+def test_laura_call_patterns_on_the_oracle():
+    """the LauraTTS call patterns (tests/laura_calls.py) run against the oracle stand-in; the GPU suite
+    replays the same calls through funcodec_b200.Speech2Token and compares."""
+    from laura_calls import OracleSpeech2Token, laura_codec_calls
+    cfg = get_config("small_ds320")
+    sd = init_state_dict(cfg, 3)
+    ora = O.OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    g = torch.Generator().manual_seed(5)
+    prompt = 0.1 * torch.randn(1, 320 * 12 + 100, generator=g)
+    r = laura_codec_calls(OracleSpeech2Token(ora), prompt, sd["quantizer.rq.model.embed"])
+    assert tuple(r["codec"].shape) == (13, cfg.num_quantizers) and len(r["continual"]) == 13 and len(r["continual"][0]) == 2
+    assert tuple(r["gen_only_lm"].shape) == (1, 1, 13 * 320) == tuple(r["gen"].shape)
+    # with exactly the predicted groups, decoding the codes and decoding their summed codewords are the same computation
+    assert (r["gen_only_lm"] - r["gen"]).abs().max().item() <= 1e-5
