@@ -418,6 +418,105 @@ cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, in
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------- STFT as a GEMM
+// EXPERIMENTAL (option "stft_tc", off by default, not yet run on hardware): X = frames x DFT basis on the tensor-core conv
+// kernel.  With hop and n_fft multiples of 32 the padded waveform viewed as rows of 32 samples [Lp/32][32] is a
+// channels-last tensor, and frame m = rows 5m .. 5m+15 (hop 160, n_fft 512): a k = n_fft/32, s = hop/32 conv with
+// C_out = 2*(n_fft/2+1) basis columns (window folded in).  The kernels below are the glue: padded/scaled rows in,
+// (re, im) columns -> mag_phase features out.
+__global__ void wave_rows_kernel(const float* __restrict__ wav, const float* __restrict__ scale, int L, int n_fft, long long n_out,
+                                 float* __restrict__ rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;          // sample of the padded signal
+    const int b = blockIdx.y;
+    if (i >= n_out) return;
+    const int src = reflect_index((int)i - n_fft / 2, L);                            // center=True, pad_mode="reflect"
+    float v = 0.f;
+    if (src >= 0 && src < L && i < (long long)L + n_fft) v = wav[(long long)b * L + src] / (scale ? scale[b] : 1.0f);
+    rows[(long long)b * n_out + i] = v;
+}
+
+cudaError_t launch_wave_rows(const float* wav, const float* scale, int B, int L, int n_fft, int n_rows, float* rows, cudaStream_t st) {
+    const long long n_out = (long long)n_rows * 32;
+    wave_rows_kernel<<<dim3((unsigned)((n_out + 255) / 256), B), 256, 0, st>>>(wav, scale, L, n_fft, n_out, rows);
+    return cudaGetLastError();
+}
+
+// spec [B][T_s][ld] with Re X[k] in column k and Im X[k] in column n_bins + k  ->  feats [B][n_bins][T_s][cpad]
+// (32 x 32 shared-memory transpose: coalesced on both sides)
+__global__ void magphase_from_spec_kernel(const float* __restrict__ spec, int ld, int n_bins, int n_frames, int cpad,
+                                          float* __restrict__ feats) {
+    __shared__ float re[32][33], im[32][33];
+    const int b = blockIdx.z, k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                          // 256 threads: 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int m = m0 + r, k = k0 + tx;
+        float a = 0.f, c = 0.f;
+        if (m < n_frames && k < n_bins) {
+            const float* sp = spec + ((long long)b * n_frames + m) * ld;
+            a = sp[k]; c = sp[n_bins + k];
+        }
+        re[r][tx] = a; im[r][tx] = c;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, m = m0 + tx;
+        if (k < n_bins && m < n_frames) {
+            const float xr = re[tx][r], xi = im[tx][r];
+            const float mag = hypotf(xr, xi);
+            const float cl = fmaxf(mag, 1e-6f);
+            float* dst = feats + (((long long)b * n_bins + k) * n_frames + m) * cpad;
+            dst[0] = logf(cl); dst[1] = xr / cl; dst[2] = xi / cl;
+            for (int c = 3; c < cpad; ++c) dst[c] = 0.f;
+        }
+    }
+}
+
+cudaError_t launch_magphase_from_spec(const float* spec, int ld, int B, int n_bins, int n_frames, int cpad, float* feats,
+                                      cudaStream_t st) {
+    magphase_from_spec_kernel<<<dim3((n_bins + 31) / 32, (n_frames + 31) / 32, B), 256, 0, st>>>(spec, ld, n_bins, n_frames, cpad, feats);
+    return cudaGetLastError();
+}
+
+// decoder output raw [B][F_raw][T_raw][3] (+ deferred GroupNorm coef) -> Y [B][n_frames][ld]: column k = softplus(mag) * re,
+// column n_bins + k = softplus(mag) * im (codec_freq.py:417-425), zero beyond 2*n_bins: the A operand of the iSTFT GEMM
+__global__ void spec_rows_kernel(const float* __restrict__ raw, const float* __restrict__ coef, int F_raw, int T_raw, int n_bins,
+                                 int n_frames, int ld, float* __restrict__ Y) {
+    __shared__ float yr[32][33], yi[32][33];
+    const int b = blockIdx.z, k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* cf = coef + (long long)b * 6;
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, m = m0 + tx;
+        float a = 0.f, c = 0.f;
+        if (k < n_bins && m < n_frames) {
+            const float* src = raw + (((long long)b * F_raw + k) * T_raw + m) * 3;
+            const float y0 = fmaf(src[0], cf[0], cf[3]);
+            const float y1 = fmaf(src[1], cf[1], cf[4]);
+            const float y2 = fmaf(src[2], cf[2], cf[5]);
+            const float mag = y0 > 20.f ? y0 : log1pf(expf(y0));
+            a = mag * y1; c = mag * y2;
+        }
+        yr[r][tx] = a; yi[r][tx] = c;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int m = m0 + r, k = k0 + tx;
+        if (m < n_frames && k < n_bins) {
+            float* dst = Y + ((long long)b * n_frames + m) * ld;
+            dst[k] = yr[tx][r];
+            dst[n_bins + k] = yi[tx][r];
+        }
+    }
+}
+
+cudaError_t launch_spec_rows(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_bins, int n_frames, int ld,
+                             float* Y, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(Y, 0, (size_t)B * n_frames * ld * sizeof(float), st);     // the padding columns
+    if (e != cudaSuccess) return e;
+    spec_rows_kernel<<<dim3((n_bins + 31) / 32, (n_frames + 31) / 32, B), 256, 0, st>>>(raw, coef, F_raw, T_raw, n_bins, n_frames, ld, Y);
+    return cudaGetLastError();
+}
+
 // =============================================================================================== iSTFT back end
 // Frame synthesis: (deferred GroupNorm of the decoder's last conv) -> softplus(mag) * (re + i im) (codec_freq.py:417-425)
 // -> irfft (DC / Nyquist imaginary parts ignored) -> x hann window, one CTA per (frame, clip) -> frames [B][T_s][N].
@@ -486,6 +585,12 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* 
     float v = acc / env;
     if (scale) v *= scale[b];
     out[(long long)b * out_len + n] = v;
+}
+
+cudaError_t launch_istft_ola(const float* frames, const float* scale, int B, int n_fft, int hop, int n_frames, int out_len,
+                             float* out, cudaStream_t st) {
+    istft_ola_kernel<<<dim3((out_len + 255) / 256, B), 256, 0, st>>>(frames, scale, n_fft, hop, n_frames, out_len, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,

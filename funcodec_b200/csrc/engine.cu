@@ -82,6 +82,9 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
+    int stft_tc = 0;             // EXPERIMENTAL: STFT / iSTFT as tensor-core GEMMs ("stft_tc" option)
+    ConvW stft_w, istft_w;       // their basis matrices as conv_tc weight images (finalize_freq)
+    int stft_ld = 0, istft_ld = 0;   // padded column counts: STFT output (2*n_bins -> x128), iSTFT input (2*n_bins -> x32)
     int conv2d_small_cout = 0;   // EXPERIMENTAL: halo-tile SIMT kernel for the C_out <= 4 2-D conv ("conv2d_small_cout" option)
     int tc_stage = 0;        // EXPERIMENTAL: cp.async-staged producer loads in conv_tc.cu ("tc_stage" option, FCB_TC_STAGE=1)
     std::vector<void*> dev_allocs;
@@ -534,6 +537,7 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
 
 // SEANetDecoder.forward + Encodec._decode_frame (codec_basic.py:398-408) + trim (:711).
 int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len);
+int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, float* out);
 
 int run_decoder_time(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
     fcb_handle* h = r.h;
@@ -834,8 +838,21 @@ int run_encoder_freq(Run& r, const float* wav, int L, float* scale_out, Act* out
     const int cfe = h->f_enc_conv0.cin;                 // 3 mag_phase features stored as 4 channels (pack_conv2d)
     FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * cfe));
     a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = cfe;
-    FCB_CK(launch_stft_magphase(wav, scale, B, L, c.n_fft, c.stft_hop, Ts, cfe, a.p, r.st));
-    h->launches++;
+    if (h->stft_tc && h->stft_w.n_tile > 0) {       // EXPERIMENTAL: rows of 32 samples -> DFT-basis GEMM -> mag_phase features
+        const int n_rows = (L + c.n_fft + 31) / 32;
+        float *rows = nullptr, *spec = nullptr;
+        FCB_TRY(alloc_f(r, &rows, (size_t)B * n_rows * 32));
+        FCB_TRY(alloc_f(r, &spec, (size_t)B * Ts * h->stft_ld));
+        FCB_CK(launch_wave_rows(wav, scale, B, L, c.n_fft, n_rows, rows, r.st));
+        FCB_TRY(run_plain_tc(r, rows, n_rows, h->stft_w, Ts, spec));
+        FCB_CK(launch_magphase_from_spec(spec, h->stft_ld, B, n_bins, Ts, cfe, a.p, r.st));
+        h->launches += 2;
+        FCB_TRY(pool_free(r, rows));
+        FCB_TRY(pool_free(r, spec));
+    } else {
+        FCB_CK(launch_stft_magphase(wav, scale, B, L, c.n_fft, c.stft_hop, Ts, cfe, a.p, r.st));
+        h->launches++;
+    }
     if (scale_owned) FCB_TRY(pool_free(r, scale));
     Act2 x;
     FCB_TRY(run_conv2d(r, a, nullptr, false, h->f_enc_conv0, &x));
@@ -911,17 +928,101 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
     if (f.F != n_bins || f.C != 3) return fail(h, FCB_E_INVALID, "FreqCodec decoder: output is not [n_fft/2+1 bins x 3 channels]");
     float* frames = nullptr;
     FCB_TRY(alloc_f(r, &frames, (size_t)r.B * f.T * c.n_fft));
-    FCB_CK(launch_istft(f.p, f.coef, r.B, f.F_raw, f.T_raw, c.n_fft, c.stft_hop, f.T, scale, frames, wav_out, out_len, r.st));
-    h->launches += 2;
+    if (h->stft_tc && h->istft_w.n_tile > 0) {      // EXPERIMENTAL: softplus(mag)*(re, im) rows -> inverse-DFT GEMM -> overlap-add
+        float* Y = nullptr;
+        FCB_TRY(alloc_f(r, &Y, (size_t)r.B * f.T * h->istft_ld));
+        FCB_CK(launch_spec_rows(f.p, f.coef, r.B, f.F_raw, f.T_raw, n_bins, f.T, h->istft_ld, Y, r.st));
+        FCB_TRY(run_plain_tc(r, Y, f.T, h->istft_w, f.T, frames));
+        FCB_CK(launch_istft_ola(frames, scale, r.B, c.n_fft, c.stft_hop, f.T, out_len, wav_out, r.st));
+        h->launches += 3;
+        FCB_TRY(pool_free(r, Y));
+    } else {
+        FCB_CK(launch_istft(f.p, f.coef, r.B, f.F_raw, f.T_raw, c.n_fft, c.stft_hop, f.T, scale, frames, wav_out, out_len, r.st));
+        h->launches += 2;
+    }
     FCB_TRY(pool_free(r, frames));
     FCB_TRY(release2(r, f));
     FCB_TRY(phase_end(r));
     return FCB_OK;
 }
 
+// EXPERIMENTAL ("stft_tc"): the windowed DFT / inverse-DFT bases as tensor-core conv weight images.
+//  STFT : rows of 32 samples are the channels-last input, X[m][co] = sum_{k, ci} x[(m*s + k)*32 + ci] * Wf[k][ci][co] with
+//         Wf = hann[n] cos(2 pi co n / N) for co < n_bins, -hann[n] sin(2 pi (co - n_bins) n / N) for the next n_bins columns;
+//  iSTFT: frames[m][j] = sum_ci Y[m][ci] * Wi[ci][j], Wi = c_k cos(2 pi k j / N) hann[j] / N (ci = k), -c_k sin(.) hann[j] / N
+//         (ci = n_bins + k), c_0 = c_{N/2} = 1 (their imaginary parts are ignored, as irfft does), c_k = 2 otherwise.
+int pack_stft_bases(fcb_handle* h) {
+    const fcb_config& c = h->cfg;
+    const int N = c.n_fft, hop = c.stft_hop, n_bins = N / 2 + 1;
+    h->stft_w.n_tile = 0; h->istft_w.n_tile = 0;
+    if (!h->use_tc || N % 32 != 0 || hop % 32 != 0 || N < hop) return FCB_OK;
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> hann(N);
+    for (int n = 0; n < N; ++n) hann[n] = 0.5 - 0.5 * cos(two_pi * n / N);
+    {   // forward
+        const int K = N / 32, cout = (2 * n_bins + 127) / 128 * 128;
+        if (!conv_tc_supported(32, cout, K, hop / 32, 1)) return FCB_OK;
+        std::vector<float> wp((size_t)K * 32 * cout, 0.f), bias(cout, 0.f);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < n_bins; ++k) {
+                const double ang = two_pi * (double)(((long long)k * n) % N) / N;
+                wp[(size_t)n * cout + k] = (float)(hann[n] * cos(ang));
+                wp[(size_t)n * cout + n_bins + k] = (float)(-hann[n] * sin(ang));
+            }
+        ConvW& o = h->stft_w;
+        o.cin = 32; o.cout = cout; o.k = K; o.s = hop / 32;
+        std::vector<float> img;
+        const int n_tile = conv_tc_n_tile(cout);
+        build_tc_image(wp, K, 32, cout, n_tile, &img);
+        FCB_TRY(upload(h, img, &o.w_tc));
+        FCB_TRY(upload(h, bias, &o.bias));
+        o.n_tile = n_tile;
+        h->stft_ld = cout;
+    }
+    {   // inverse
+        const int cin = (2 * n_bins + 31) / 32 * 32, cout = N;
+        if (!conv_tc_supported(cin, cout, 1, 1, 1)) return FCB_OK;
+        std::vector<float> wp((size_t)cin * cout, 0.f), bias(cout, 0.f);
+        for (int k = 0; k < n_bins; ++k) {
+            const bool edge = (k == 0 || k == N / 2);
+            for (int j = 0; j < N; ++j) {
+                const double ang = two_pi * (double)(((long long)k * j) % N) / N;
+                wp[(size_t)k * cout + j] = (float)((edge ? 1.0 : 2.0) * cos(ang) * hann[j] / N);
+                wp[(size_t)(n_bins + k) * cout + j] = edge ? 0.f : (float)(-2.0 * sin(ang) * hann[j] / N);
+            }
+        }
+        ConvW& o = h->istft_w;
+        o.cin = cin; o.cout = cout; o.k = 1; o.s = 1;
+        std::vector<float> img;
+        const int n_tile = conv_tc_n_tile(cout);
+        build_tc_image(wp, 1, cin, cout, n_tile, &img);
+        FCB_TRY(upload(h, img, &o.w_tc));
+        FCB_TRY(upload(h, bias, &o.bias));
+        o.n_tile = n_tile;
+        h->istft_ld = cin;
+    }
+    return FCB_OK;
+}
+
+// one plain tensor-core conv without padding, normalisation or statistics: out[B][T_out][cout] (used by the GEMM STFT / iSTFT)
+int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, float* out) {
+    fcb_handle* h = r.h;
+    ConvParams p{};
+    p.in0.x = x; p.in0.clip_stride = (long long)T_in * L.cin;
+    p.T_in = T_in; p.C_in = L.cin; p.K = L.k; p.S = L.s; p.D = 1; p.pad_l = 0; p.T_ext = T_in; p.pad_zero = 1;
+    p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.bias = L.bias;
+    p.out = out; p.T_out = T_out; p.C_out = L.cout; p.out_clip_stride = (long long)T_out * L.cout;
+    p.stage_in = h->tc_stage;
+    int np = 0;
+    FCB_CK(launch_conv_tc(p, r.B, r.st, &np));
+    h->launches++;
+    return FCB_OK;
+}
+
 int finalize_freq(fcb_handle* h) {
     const fcb_config& c = h->cfg;
     const int nf = c.n_filters, D = c.dimension, nr = c.n_ratios;
+    FCB_TRY(pack_stft_bases(h));
     FCB_TRY(pack_conv2d(h, "encoder.model.0", 3, nf, c.kernel_size, c.kernel_size, 1, 1, &h->f_enc_conv0, 4));
     int n = 1, mult = 1;
     for (int i = nr - 1; i >= 0; --i) {               // encoder applies the ratios reversed (seanet_encoder.py:288)
@@ -1406,6 +1507,10 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     if (strcmp(key, "use_tc") == 0) {
         if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
         h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "stft_tc") == 0) {             // EXPERIMENTAL, not validated on hardware yet
+        h->stft_tc = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "conv2d_small_cout") == 0) {   // EXPERIMENTAL, not validated on hardware yet

@@ -40,6 +40,15 @@ cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, in
 cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,
                          const float* scale, float* frames, float* out, int out_len, cudaStream_t st);
 
+// EXPERIMENTAL STFT / iSTFT as tensor-core GEMMs ("stft_tc" option): the glue kernels around two conv_tc launches
+cudaError_t launch_wave_rows(const float* wav, const float* scale, int B, int L, int n_fft, int n_rows, float* rows, cudaStream_t st);
+cudaError_t launch_magphase_from_spec(const float* spec, int ld, int B, int n_bins, int n_frames, int cpad, float* feats,
+                                      cudaStream_t st);
+cudaError_t launch_spec_rows(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_bins, int n_frames, int ld,
+                             float* Y, cudaStream_t st);
+cudaError_t launch_istft_ola(const float* frames, const float* scale, int B, int n_fft, int hop, int n_frames, int out_len,
+                             float* out, cudaStream_t st);
+
 // lstm.cu
 struct LstmSeqParams {
     const float* gx;      // [B][T][4H] input projection incl. both biases, columns packed unit-major (n' = 4*j + gate)

@@ -90,3 +90,28 @@ def test_small_cout_conv2d(golden_dir):
         assert (d["recon_speech"].cpu() - dref).abs().max().item() <= 1e-3
     finally:
         model.set_option("conv2d_small_cout", 0)
+
+
+def test_stft_as_gemm(golden_dir):
+    """`stft_tc`: STFT / iSTFT as tensor-core GEMMs against the oracle (torch.stft / istft), config-4 architecture and the
+    small golden model, encoder output and decode-only waveform."""
+    import test_gpu_freq as TF
+    for getter in (TF._full, lambda: TF._small(golden_dir)[1:]):
+        cfg, sd, model, oracle = getter()
+        model.set_option("stft_tc", 1)
+        try:
+            g = torch.Generator().manual_seed(9)
+            wav = 0.1 * torch.randn(2, 160 * 33 + 17, generator=g)
+            ora = oracle.inference(wav, want_margin=True)
+            r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
+            err = (r["encoder_out"].cpu() - ora["encoder_out"]).abs().max().item()
+            print(f"stft_tc {cfg.name}: encoder_out max-abs err {err:.3e}")
+            assert err <= 5e-5
+            quant = ora["code_embeddings"][0][0]
+            d = model.inference_decoding_emb(quant)
+            dref = oracle.decode_frame(quant, None)
+            derr = (d["recon_speech"].cpu() - dref).abs().max().item()
+            print(f"stft_tc {cfg.name}: decode-only max-abs err {derr:.3e}")
+            assert derr <= 1e-3
+        finally:
+            model.set_option("stft_tc", 0)
