@@ -84,6 +84,7 @@ struct fcb_handle {
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
     int stft_tc = 0;             // EXPERIMENTAL: STFT / iSTFT as tensor-core GEMMs ("stft_tc" option)
     ConvW stft_w, istft_w;       // their basis matrices as conv_tc weight images (finalize_freq)
+    bool stft_packed = false;
     int stft_ld = 0, istft_ld = 0;   // padded column counts: STFT output (2*n_bins -> x128), iSTFT input (2*n_bins -> x32)
     int conv2d_small_cout = 0;   // EXPERIMENTAL: halo-tile SIMT kernel for the C_out <= 4 2-D conv ("conv2d_small_cout" option)
     int tc_stage = 0;        // EXPERIMENTAL: cp.async-staged producer loads in conv_tc.cu ("tc_stage" option, FCB_TC_STAGE=1)
@@ -538,6 +539,7 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
 // SEANetDecoder.forward + Encodec._decode_frame (codec_basic.py:398-408) + trim (:711).
 int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len);
 int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, float* out);
+int pack_stft_bases(fcb_handle* h);
 
 int run_decoder_time(Run& r, const float* emb, int n_frames, const float* scale, float* wav_out, int out_len) {
     fcb_handle* h = r.h;
@@ -838,6 +840,7 @@ int run_encoder_freq(Run& r, const float* wav, int L, float* scale_out, Act* out
     const int cfe = h->f_enc_conv0.cin;                 // 3 mag_phase features stored as 4 channels (pack_conv2d)
     FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * cfe));
     a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = cfe;
+    if (h->stft_tc && !h->stft_packed) { h->stft_packed = true; FCB_TRY(pack_stft_bases(h)); }   // lazily: the default path never builds them
     if (h->stft_tc && h->stft_w.n_tile > 0) {       // EXPERIMENTAL: rows of 32 samples -> DFT-basis GEMM -> mag_phase features
         const int n_rows = (L + c.n_fft + 31) / 32;
         float *rows = nullptr, *spec = nullptr;
@@ -928,6 +931,7 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
     if (f.F != n_bins || f.C != 3) return fail(h, FCB_E_INVALID, "FreqCodec decoder: output is not [n_fft/2+1 bins x 3 channels]");
     float* frames = nullptr;
     FCB_TRY(alloc_f(r, &frames, (size_t)r.B * f.T * c.n_fft));
+    if (h->stft_tc && !h->stft_packed) { h->stft_packed = true; FCB_TRY(pack_stft_bases(h)); }
     if (h->stft_tc && h->istft_w.n_tile > 0) {      // EXPERIMENTAL: softplus(mag)*(re, im) rows -> inverse-DFT GEMM -> overlap-add
         float* Y = nullptr;
         FCB_TRY(alloc_f(r, &Y, (size_t)r.B * f.T * h->istft_ld));
@@ -1022,7 +1026,6 @@ int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, fl
 int finalize_freq(fcb_handle* h) {
     const fcb_config& c = h->cfg;
     const int nf = c.n_filters, D = c.dimension, nr = c.n_ratios;
-    FCB_TRY(pack_stft_bases(h));
     FCB_TRY(pack_conv2d(h, "encoder.model.0", 3, nf, c.kernel_size, c.kernel_size, 1, 1, &h->f_enc_conv0, 4));
     int n = 1, mult = 1;
     for (int i = nr - 1; i >= 0; --i) {               // encoder applies the ratios reversed (seanet_encoder.py:288)
