@@ -1138,6 +1138,8 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
     { const char* e = getenv("FCB_TC_STAGE"); if (e && e[0] == '1') h->tc_stage = 1; }
+    { const char* e = getenv("FCB_CONV2D_SMALL_COUT"); if (e && e[0] == '1') h->conv2d_small_cout = 1; }
+    { const char* e = getenv("FCB_STFT_TC"); if (e && e[0] == '1') h->stft_tc = 1; }
     { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
