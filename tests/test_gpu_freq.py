@@ -110,6 +110,24 @@ def test_freq_full_config_shapes_and_oracle_spot_check(tc2d):
         model.set_option("use_tc2d", 7)
 
 
+def test_freq_config4_arch_golden(golden_dir):
+    """The config-4 architecture against vectors of the UNMODIFIED reference FreqCodec (tools/gen_golden_freq.py,
+    weights = init_state_dict(cfg, 0) loaded into the reference module)."""
+    cfg, sd, model, oracle = _full()
+    z = np.load(os.path.join(golden_dir, "freq_magphase_config4_arch.npz"))
+    wav = torch.from_numpy(z["wav"])
+    ora = oracle.inference(wav, want_margin=True)
+    r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
+    assert np.abs(r["encoder_out"].cpu().numpy() - z["encoder_out"]).max() <= EMB_TOL
+    res = assert_codes_parity(r["code_indices"][0].cpu().numpy(), z["codes"], ora["margins"].numpy(), MARGIN, min_exact_rate=0.9,
+                              what="config-4 golden")
+    if not (res["first_stage"] >= 0).any():
+        assert np.abs(r["recon_speech"].cpu().numpy() - z["recon"]).max() <= WAV_TOL
+    d = model.inference_decoding_emb(torch.from_numpy(z["quant"]))
+    dref = oracle.decode_frame(torch.from_numpy(z["quant"]), None)
+    assert (d["recon_speech"].cpu() - dref).abs().max().item() <= WAV_TOL * 10      # un-scaled output (~10x amplitude)
+
+
 # ---------------------------------------------------------------------------------------------- layer level (2-D)
 _STRIDES2 = {"encoder.model.3": (4, 1), "encoder.model.6": (4, 2), "encoder.model.9": (4, 1), "encoder.model.12": (4, 1),
              "decoder.model.4": (4, 1), "decoder.model.7": (4, 1), "decoder.model.10": (4, 2), "decoder.model.13": (4, 1)}

@@ -21,3 +21,20 @@ def test_freqcodec_magphase_oracle_vs_reference(golden_dir):
     assert np.abs(r["code_embeddings"][0][1].numpy() - z["scale"]).max() <= 1e-7
     assert r["recon_speech"].shape == z["recon"].shape
     assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 5e-6
+
+
+def test_freqcodec_config4_architecture_oracle_vs_reference(golden_dir):
+    """BASELINE config 4's architecture (n_filters 32, D 128, K 1024, n_q 32, conv groups = 1) on a 0.5 s clip: the oracle
+    against the unmodified reference FreqCodec (tools/gen_golden_freq.py); weights = init_state_dict(cfg, 0)."""
+    from funcodec_b200 import get_config, init_state_dict
+    z = np.load(os.path.join(golden_dir, "freq_magphase_config4_arch.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    sd = init_state_dict(cfg, int(z["seed"]))
+    assert abs(float(sum(v.double().abs().sum().item() for v in sd.values())) - float(z["sd_checksum"])) <= 1e-6 * float(z["sd_checksum"])
+    o = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)))
+    r = o.inference(torch.from_numpy(z["wav"]), want_margin=True)
+    assert np.abs(r["encoder_out"].numpy() - z["encoder_out"]).max() <= 1e-5
+    assert np.array_equal(r["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert np.abs(r["code_embeddings"][0][0].numpy() - z["quant"]).max() <= 1e-5
+    assert r["recon_speech"].shape == z["recon"].shape
+    assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 1e-5

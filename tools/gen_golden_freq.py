@@ -62,3 +62,24 @@ if __name__ == "__main__":
     path = os.path.join(OUT, "freq_magphase_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", "codes", out["codes"].shape, "recon", out["recon"].shape)
+
+    # BASELINE config 4 architecture (repo YAML: n_filters 32, D 128, K 1024, n_q 32, groups = 1) on a short clip; weights
+    # are funcodec_b200.weights.init_state_dict(cfg, 0) loaded into the reference module (not stored in the fixture)
+    from funcodec_b200 import get_config, init_state_dict
+    cfg = get_config("freqcodec_magphase_16k_n32_ds320")
+    sd = init_state_dict(cfg, 0)
+    m = build(cfg.n_filters, cfg.dimension, cfg.codebook_size, cfg.num_quantizers, ratios)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.split(".")[-1] in ("cluster_size", "embed_avg", "inited", "window") or "discriminator" in k for k in missing), (missing, unexpected)
+    m.quantizer.rq.model.inited.fill_(1)
+    g = torch.Generator().manual_seed(4)
+    wav = 0.1 * torch.randn(1, 8000, generator=g)
+    with torch.no_grad():
+        r = m.inference(wav, need_recon=True, bit_width=None, use_scale=True)
+        emb, scale = m._encode(wav.unsqueeze(1))[0]
+    out = dict(cfg_name=cfg.name, seed=0, wav=wav.numpy(), codes=r["code_indices"][0].numpy().astype(np.int16),
+               quant=r["code_embeddings"][0][0].numpy(), scale=r["code_embeddings"][0][1].numpy(), recon=r["recon_speech"].numpy(),
+               encoder_out=emb.numpy(), sd_checksum=float(sum(v.double().abs().sum().item() for v in sd.values())))
+    path = os.path.join(OUT, "freq_magphase_config4_arch.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", "codes", out["codes"].shape, "recon", out["recon"].shape)
