@@ -82,6 +82,7 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
+    int lstm_prefetch_poll = 0;  // EXPERIMENTAL: see LstmSeqParams::prefetch_poll
     int stft_tc = 0;             // EXPERIMENTAL: STFT / iSTFT as tensor-core GEMMs ("stft_tc" option)
     ConvW stft_w, istft_w;       // their basis matrices as conv_tc weight images (finalize_freq)
     bool stft_packed = false;
@@ -463,6 +464,7 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
         sp.skip = view_of(x);
         sp.barrier = h->lstm_barrier;
         sp.B = B; sp.T = T; sp.H = H;
+        sp.prefetch_poll = h->lstm_prefetch_poll;
         FCB_CK(launch_lstm_seq(sp, r.st));
         h->launches += 1;
         FCB_TRY(release(r, gx));
@@ -1140,6 +1142,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     { const char* e = getenv("FCB_TC_STAGE"); if (e && e[0] == '1') h->tc_stage = 1; }
     { const char* e = getenv("FCB_CONV2D_SMALL_COUT"); if (e && e[0] == '1') h->conv2d_small_cout = 1; }
     { const char* e = getenv("FCB_STFT_TC"); if (e && e[0] == '1') h->stft_tc = 1; }
+    { const char* e = getenv("FCB_LSTM_PREFETCH_POLL"); if (e && e[0] == '1') h->lstm_prefetch_poll = 1; }
     { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
@@ -1512,6 +1515,10 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     if (strcmp(key, "use_tc") == 0) {
         if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
         h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "lstm_prefetch_poll") == 0) {  // EXPERIMENTAL, not validated on hardware yet
+        h->lstm_prefetch_poll = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "stft_tc") == 0) {             // EXPERIMENTAL, not validated on hardware yet

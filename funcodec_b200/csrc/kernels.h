@@ -58,6 +58,7 @@ struct LstmSeqParams {
     InView skip;          // the SLSTM input (normalised on load) when y_out != nullptr
     unsigned* barrier;    // device counter for the per-step grid barrier (zeroed by the launcher)
     int B, T, H;
+    int prefetch_poll;    // EXPERIMENTAL ("lstm_prefetch_poll" option): software-pipelined barrier polling in the loader warp
 };
 cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st);
 int lstm_pick_units(int H);

@@ -115,3 +115,17 @@ def test_stft_as_gemm(golden_dir):
             assert derr <= 1e-3
         finally:
             model.set_option("stft_tc", 0)
+
+
+def test_lstm_prefetch_poll_is_bit_identical():
+    """`lstm_prefetch_poll` only changes WHEN the loader warp reads a group's counter: outputs must be bit-identical."""
+    from funcodec_b200.encodec import B200Encodec
+    cfg = get_config("encodec_16k_n32_ds640")
+    sd = init_state_dict(cfg, 0)
+    a = B200Encodec(cfg, sd, "cuda:0")
+    b = B200Encodec(cfg, sd, "cuda:0", options={"lstm_prefetch_poll": 1})
+    g = torch.Generator().manual_seed(13)
+    wav = 0.1 * torch.randn(19, 16000 + 321, generator=g)          # 3 clip groups, the last one partial
+    ra, rb = a.inference(wav), b.inference(wav)
+    assert torch.equal(ra["code_indices"][0], rb["code_indices"][0])
+    assert torch.equal(ra["recon_speech"], rb["recon_speech"])
