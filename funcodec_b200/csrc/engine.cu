@@ -38,6 +38,7 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl
     float* beta = nullptr;   // [cout]
     float* w_tc = nullptr;   // tensor-core image: [n_tile idx][chunk][tap][hi|lo][n_tile rows x 128 B swizzled]
     int n_tile = 0;          // 0: no tensor-core image (layer runs on the SIMT kernel)
+    float* w_tc64 = nullptr; // EXPERIMENTAL ("tc_m256"): the same image with n_tile = 64 for conv_tc_m256.cu (deep layers)
 };
 
 struct LstmW {
@@ -82,6 +83,7 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
+    int tc_m256 = 0;             // EXPERIMENTAL: deep conv layers on conv_tc_m256.cu ("tc_m256" option, before fcb_finalize)
     int lstm_prefetch_poll = 0;  // EXPERIMENTAL: see LstmSeqParams::prefetch_poll
     int stft_tc = 0;             // EXPERIMENTAL: STFT / iSTFT as tensor-core GEMMs ("stft_tc" option)
     ConvW stft_w, istft_w;       // their basis matrices as conv_tc weight images (finalize_freq)
@@ -202,6 +204,10 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
     build_tc_image(wp, K, cin, cout_eff, n_tile, &img);
     FCB_TRY(upload(h, img, &o->w_tc));
     o->n_tile = n_tile;
+    if (h->tc_m256 && n_tile == 128 && conv_tc_m256_supported(cin, cout_eff, K, 1, 1)) {
+        build_tc_image(wp, K, cin, cout_eff, 64, &img);
+        FCB_TRY(upload(h, img, &o->w_tc64));
+    }
     return FCB_OK;
 }
 
@@ -408,12 +414,14 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     p.stage_in = h->tc_stage;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
+    const bool m2 = tc && h->tc_m256 && L.w_tc64 && conv_tc_m256_supported(p.C_in, p.C_out, p.K, p.S, 1);   // EXPERIMENTAL
+    if (m2) { p.w_tc = L.w_tc64; p.n_tile = 64; }
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
     o.owned = true;
     p.out = o.p;
     double* partials = nullptr;
     const bool c1 = !tc && conv_cout1_supported(p);
-    const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out)
+    const int nparts = m2 ? conv_tc_m256_num_parts(p.T_out, p.C_out) : tc ? conv_tc_num_parts(p.T_out, p.C_out)
                           : (c1 ? conv_cout1_num_parts(p.T_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B));
     if (want_norm) {
         FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double)));
@@ -423,7 +431,8 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     }
     p.partials = partials;
     int np2 = 0;
-    if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
+    if (m2) FCB_CK(launch_conv_tc_m256(p, r.B, r.st, &np2));
+    else if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
     else if (c1) FCB_CK(launch_conv_cout1(p, r.B, r.st, &np2));
     else FCB_CK(launch_conv(p, r.B, r.st, &np2));
     h->launches++;
@@ -1142,6 +1151,7 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     { const char* e = getenv("FCB_TC_STAGE"); if (e && e[0] == '1') h->tc_stage = 1; }
     { const char* e = getenv("FCB_CONV2D_SMALL_COUT"); if (e && e[0] == '1') h->conv2d_small_cout = 1; }
     { const char* e = getenv("FCB_STFT_TC"); if (e && e[0] == '1') h->stft_tc = 1; }
+    { const char* e = getenv("FCB_TC_M256"); if (e && e[0] == '1') h->tc_m256 = 1; }
     { const char* e = getenv("FCB_LSTM_PREFETCH_POLL"); if (e && e[0] == '1') h->lstm_prefetch_poll = 1; }
     { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
@@ -1515,6 +1525,11 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     if (strcmp(key, "use_tc") == 0) {
         if (h->finalized && value && !h->use_tc) return fail(h, FCB_E_STATE, "use_tc can only be enabled before fcb_finalize");
         h->use_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "tc_m256") == 0) {             // EXPERIMENTAL, not validated on hardware yet
+        if (h->finalized && value && !h->tc_m256) return fail(h, FCB_E_STATE, "tc_m256 can only be enabled before fcb_finalize");
+        h->tc_m256 = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "lstm_prefetch_poll") == 0) {  // EXPERIMENTAL, not validated on hardware yet

@@ -29,6 +29,11 @@ int conv_tc_n_tile(int C_out_eff);
 int conv_tc_num_parts(int T_out, int C_out_eff);
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts);
 
+// conv_tc_m256.cu: EXPERIMENTAL deep-layer variant (M = 256 rows per CTA, N = 64; every weight slab feeds both halves)
+bool conv_tc_m256_supported(int C_in, int C_out_eff, int K, int S, int D);
+int conv_tc_m256_num_parts(int T_out, int C_out_eff);
+cudaError_t launch_conv_tc_m256(const ConvParams& p, int B, cudaStream_t st, int* nparts);
+
 // conv2d_simt.cu (FreqCodec 2-D path)
 int conv2d_num_parts(const Conv2dParams& p);
 cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st);

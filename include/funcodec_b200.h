@@ -176,7 +176,9 @@ FCB_API int fcb_get_phase_ms(fcb_handle* h, float* ms_out /* [FCB_NUM_PHASES] */
 /* "use_tc2d" (FreqCodec, arch 1): bit mask of the 2-D layer classes that run on the tensor-core path -- 1: C_in % 32 == 0,
  * 2: C_in < 32 (several frequency taps per 32-channel chunk), 4: C_out padded to 16 (the 32 -> 3 output conv); default 7,
  * 0 = every 2-D conv on the fp32 SIMT kernel.  May be changed at any time; env FCB_USE_TC2D=<mask> sets the default. */
-/* "lstm_prefetch_poll" 1/0 (default 0): EXPERIMENTAL software-pipelined barrier polling in the LSTM kernel's loader warp.
+/* "tc_m256" 1/0 (default 0; before fcb_finalize; env FCB_TC_M256=1): EXPERIMENTAL deep-layer conv kernel (C_in >= 256): 256 time rows
+ * per CTA share every weight slab (conv_tc_m256.cu).
+ * "lstm_prefetch_poll" 1/0 (default 0): EXPERIMENTAL software-pipelined barrier polling in the LSTM kernel's loader warp.
  * "stft_tc" 1/0 (default 0): EXPERIMENTAL STFT / iSTFT of the FreqCodec front / back end as two tensor-core GEMMs (windowed DFT
  * bases as conv weight images) instead of the direct-DFT kernels; needs n_fft and hop to be multiples of 32.
  * "conv2d_small_cout" 1/0 (default 0): EXPERIMENTAL halo-tile SIMT kernel for 2-D convs with C_out <= 4 (FreqCodec's 32 -> 3

@@ -129,3 +129,33 @@ def test_lstm_prefetch_poll_is_bit_identical():
     ra, rb = a.inference(wav), b.inference(wav)
     assert torch.equal(ra["code_indices"][0], rb["code_indices"][0])
     assert torch.equal(ra["recon_speech"], rb["recon_speech"])
+
+
+def test_m256_deep_layers():
+    """`tc_m256`: the deep layers (C_in >= 256) on conv_tc_m256.cu (M = 256 rows per CTA, N = 64) against float64, and the
+    model against the default kernels."""
+    import test_gpu_layers as TL
+    from funcodec_b200.encodec import B200Encodec
+    m = TL._models()
+    sd, cfg = m["sd"], m["cfg"]
+    model = B200Encodec(cfg, sd, "cuda:0", options={"tc_m256": 1})
+    for layer, cin, T, elu in TL.CASES + [("encoder.model.12", 256, 5 * 300 + 1, True), ("decoder.model.6", 512, 700, True)]:
+        if cin < 256:
+            continue
+        g = torch.Generator().manual_seed(2000 + T)
+        x_btc = torch.randn(2, T, cin, generator=g)
+        y, stats, row_off = model.debug_conv(layer, x_btc, elu=elu, want_stats=".lstm." not in layer)
+        ref, ref_off, kept = TL._truth(sd, layer, x_btc.permute(0, 2, 1), elu)
+        ref_btc = ref.permute(0, 2, 1)
+        rms = ref_btc.pow(2).mean().sqrt().item()
+        err = (y.cpu().double() - ref_btc).abs().max().item()
+        print(f"m256 {layer:28s} T={T:5d} rel err {err / rms:.3e}")
+        assert err <= 2e-5 * rms, (layer, err, rms)
+        if stats is not None:
+            mean = ref.mean(dim=(1, 2))
+            assert (stats.cpu().double()[:, 0] - mean).abs().max().item() <= 1e-5 * rms
+    g = torch.Generator().manual_seed(3)
+    wav = 0.1 * torch.randn(3, 16000 * 2 + 77, generator=g)
+    ra, rb = m["tc"].inference(wav), model.inference(wav)
+    same = (ra["code_indices"][0] == rb["code_indices"][0]).all(dim=0).float().mean().item()
+    assert same >= 0.99, same

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: validate and time the code paths written ahead of hardware access (all OFF by default):
 #   tc_stage (cp.async-staged conv producers), conv2d_small_cout (halo-tile 32->3 conv), stft_tc (STFT / iSTFT as GEMMs),
-#   lstm_prefetch_poll (software-pipelined barrier polling in the LSTM loader warp).
+#   lstm_prefetch_poll (software-pipelined barrier polling in the LSTM loader warp), tc_m256 (deep conv layers, M = 256).
 # tools/gpu_round2_bringup.sh <tag>      (~2-3 min of box time)
 TAG=${1:-r2a}
 mkdir -p gpurun_out
@@ -21,7 +21,9 @@ PY
 }
 BENCH_ARGS="" run cfg2_default FCB_TC_STAGE=0
 BENCH_ARGS="" run cfg2_stage FCB_TC_STAGE=1
+BENCH_ARGS="" run cfg2_m256 FCB_TC_M256=1
 BENCH_ARGS="" run cfg2_lstm_prefetch FCB_LSTM_PREFETCH_POLL=1
+BENCH_ARGS="" run cfg2_all FCB_TC_STAGE=1 FCB_TC_M256=1 FCB_LSTM_PREFETCH_POLL=1
 BENCH_ARGS="--workload config4" run cfg4_default FCB_TC_STAGE=0
 BENCH_ARGS="--workload config4" run cfg4_lstm_prefetch FCB_LSTM_PREFETCH_POLL=1
 BENCH_ARGS="--workload config4" run cfg4_stage FCB_TC_STAGE=1
