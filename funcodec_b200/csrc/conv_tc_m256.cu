@@ -4,7 +4,10 @@
 // feeds only 12 MMAs = 768 tensor cycles, 42 B/clk per SM, more than L2 can deliver to 148 SMs (tensor pipe 44 %,
 // profiles/conv_ncu_r1n.txt).  Here a CTA owns M = 256 time rows as two 128-row halves, one per producer group, and every
 // weight slab (N = 64: 16 KB) is used for both halves: 24 MMAs (768 tensor cycles) per 16 KB = 21 B/clk per SM.
-// TMEM: per half two ping-pong accumulators + running totals, 6 x 64 = 384 columns.
+// TMEM: per half two ping-pong accumulators + running totals, 6 x 64 = 384 columns (N = 128 would need 768).
+// Known cap: an M128 N64 K8 tf32 MMA reads 4 KB of A + 2 KB of B from shared memory for 32.8 tensor cycles; at 128 B/clk
+// of operand bandwidth that is ~48 cycles, so this variant tops out near 68 % of the tensor pipe (vs the 44 % measured
+// with the weight stream as the limit); the real fix for 100 % is cta_group::2, where the CTA pair shares the operands.
 //
 // Same contract as conv1d_tc_kernel (1-D layers only, no FREQ / STAGE modes, weights always streamed through the ring):
 // fused [GroupNorm apply + resblock add + ELU + reflect pad] on the input, bias + raw store + GroupNorm partials on the
