@@ -124,11 +124,19 @@ def pick_cpu_threads(run_once):
     return best
 
 
+def make_oracle(cfg, sd):
+    """The CPU port of the reference model for this config (time-domain Encodec or mag_phase FreqCodec)."""
+    if cfg.arch == 1:
+        from oracle.freqcodec_oracle import OracleFreqCodec
+        return OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)), cfg.sample_rate, cfg.lstm_layers, cfg.n_fft, cfg.stft_hop)
+    from oracle.encodec_oracle import OracleEncodec
+    return OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+
+
 def cpu_oracle_time(cfg, sd, B, L, bit_width, reps, warm):
     """Times the oracle (CPU port of the reference's PyTorch path) on a bounded sample; returns (frames/s, s/pass, threads)."""
     import torch
-    from oracle.encodec_oracle import OracleEncodec
-    o = OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    o = make_oracle(cfg, sd)
     g = torch.Generator().manual_seed(1235)
     wav = 0.1 * torch.randn(B, L, generator=g)
     threads = pick_cpu_threads(lambda: o.inference(wav, need_recon=True, bit_width=bit_width, use_scale=True))
@@ -154,8 +162,7 @@ def run_reference(args):
     cfg = get_config(cfg_name)
     sd = init_state_dict(cfg, 0)
     sample_B = min(B, 2)            # bounded sample: 2 clips of the workload's length per step
-    from oracle.encodec_oracle import OracleEncodec
-    o = OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    o = make_oracle(cfg, sd)
     g = torch.Generator().manual_seed(1235)
     wav = 0.1 * torch.randn(sample_B, L, generator=g)
 

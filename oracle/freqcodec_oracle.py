@@ -118,6 +118,7 @@ class OracleFreqCodec:
         self.embed = sd["quantizer.rq.model.embed"]
         self.ratios = [tuple(r) for r in ratios]
         self.lstm_layers = lstm_layers
+        self.sample_rate = sample_rate
         self.n_fft, self.hop = n_fft, hop
         self.audio_normalize = audio_normalize
         self.dtype = dtype
@@ -157,12 +158,15 @@ class OracleFreqCodec:
         return wav
 
     @torch.no_grad()
-    def inference(self, speech, need_recon=True, use_scale=True, want_margin=False):
+    def inference(self, speech, need_recon=True, bit_width=None, use_scale=True, want_margin=False):
         speech = speech.to(self.dtype)
         if speech.dim() == 2:
             speech = speech.unsqueeze(1)
         emb, scale, feats = self.encode_frame(speech)
-        quant, codes, sub, margins = O.rvq_forward(emb.permute(0, 2, 1), self.embed, self.embed.shape[0], want_margin)
+        n_q_max, bins, _ = self.embed.shape
+        hop = self.hop * int(torch.tensor([r[1] for r in self.ratios]).prod())          # samples per codec frame
+        n_q = O.num_quantizers_for_bandwidth(n_q_max, bins, self.sample_rate, hop, bit_width)
+        quant, codes, sub, margins = O.rvq_forward(emb.permute(0, 2, 1), self.embed, min(n_q, n_q_max), want_margin)
         quant_btd = quant.permute(0, 2, 1)
         recon = None
         if need_recon:
