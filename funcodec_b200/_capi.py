@@ -60,6 +60,7 @@ SYMBOLS = {
     "fcb_debug_conv1d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,
                                    POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "fcb_plan_segments": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "fcb_plan_segments_for_hop": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "fcb_roundtrip_segmented": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "fcb_debug_conv2d": (c_int32, [c_void_p, c_char_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p,

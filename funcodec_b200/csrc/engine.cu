@@ -1382,18 +1382,21 @@ int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t
     return rc;
 }
 
-int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan) {
-    if (!h || !plan) return FCB_E_INVALID;
-    if (h->cfg.arch != 0) return fail(h, FCB_E_INVALID, "segmented processing supports the time-domain Encodec only");
-    if (L <= 0 || seg_len <= 0 || stride <= 0 || stride > seg_len)
-        return fail(h, FCB_E_INVALID, "fcb_plan_segments: need L > 0 and 0 < stride <= seg_len");
-    const int hop = h->hop();
+// Pure arithmetic (no device, no handle): error text through *why when not representable.
+static int plan_segments_hop(int hop, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan, const char** why) {
+    if (hop <= 0 || L <= 0 || seg_len <= 0 || stride <= 0 || stride > seg_len) {
+        *why = "fcb_plan_segments: need hop > 0, L > 0 and 0 < stride <= seg_len";
+        return FCB_E_INVALID;
+    }
     fcb_segment_plan p{};
     p.n_seg = (L + stride - 1) / stride;                                    // len(range(0, L, stride))
     p.n_full = L >= seg_len ? (L - seg_len) / stride + 1 : 0;              // offsets with a whole segment left
     if (p.n_full > p.n_seg) p.n_full = p.n_seg;
     p.n_tail = p.n_seg - p.n_full;
-    if (p.n_tail > FCB_MAX_TAIL_SEGMENTS) return fail(h, FCB_E_INVALID, "fcb_plan_segments: too many short trailing segments (overlap too high)");
+    if (p.n_tail > FCB_MAX_TAIL_SEGMENTS) {
+        *why = "fcb_plan_segments: too many short trailing segments (overlap too high)";
+        return FCB_E_INVALID;
+    }
     p.frames_full = (seg_len + hop - 1) / hop;
     p.decoded_full = p.frames_full * hop;
     p.total_frames = (int64_t)p.n_full * p.frames_full;
@@ -1407,11 +1410,28 @@ int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride,
     const long long total = (long long)stride * (p.n_seg - 1) + dl_last;
     for (int i = 0; i < p.n_seg; ++i) {
         const int dl = i < p.n_full ? p.decoded_full : p.tail_frames[i - p.n_full] * hop;
-        if ((long long)i * stride + dl > total)
-            return fail(h, FCB_E_INVALID, "segment plan not representable: a decoded segment ends after the final one "
-                                          "(the reference's _linear_overlap_add raises here)");
+        if ((long long)i * stride + dl > total) {
+            *why = "segment plan not representable: a decoded segment ends after the final one "
+                   "(the reference's _linear_overlap_add raises here)";
+            return FCB_E_INVALID;
+        }
     }
     *plan = p;
+    return FCB_OK;
+}
+
+int fcb_plan_segments_for_hop(int32_t hop, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan) {
+    if (!plan) return FCB_E_INVALID;
+    const char* why = "";
+    return plan_segments_hop(hop, L, seg_len, stride, plan, &why);
+}
+
+int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan) {
+    if (!h || !plan) return FCB_E_INVALID;
+    if (h->cfg.arch != 0) return fail(h, FCB_E_INVALID, "segmented processing supports the time-domain Encodec only");
+    const char* why = "";
+    const int rc = plan_segments_hop(h->hop(), L, seg_len, stride, plan, &why);
+    if (rc != FCB_OK) return fail(h, rc, why);
     return FCB_OK;
 }
 

@@ -149,6 +149,8 @@ typedef struct fcb_segment_plan {
 /* Fails (FCB_E_INVALID) when the reference would: more than FCB_MAX_TAIL_SEGMENTS short segments, or a non-final decoded
  * segment ending after the final one (the reference's overlap-add raises a size mismatch there, codec_basic.py:112). */
 FCB_API int fcb_plan_segments(fcb_handle* h, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan);
+/* The same arithmetic without a handle or a device (hop = samples per codec frame): host-side planning and the CPU tests. */
+FCB_API int fcb_plan_segments_for_hop(int32_t hop, int32_t L, int32_t seg_len, int32_t stride, fcb_segment_plan* plan);
 /* Encodec.inference with segments.  Outputs (dev), full segments first then the tails in order:
  *   codes  int64: [n_q][n_full*B][frames_full] followed, per tail i, by [n_q][B][tail_frames[i]]
  *   quant  fp32 or NULL: [n_full*B][frames_full][D] followed by [B][tail_frames[i]][D] per tail

@@ -35,3 +35,46 @@ def test_peak_limit_and_wav_io(tmp_path):
     P.save_wav_pcm16(path, x.view(1, -1), 16000, rescale=True)
     y, sr = P.load_wav(path)
     assert sr == 16000 and np.abs(y - x.numpy()).max() <= 1.0 / 32768 + 1e-6
+
+
+def test_segment_plan_matches_the_reference_arithmetic():
+    """fcb_plan_segments_for_hop (pure host arithmetic of the C ABI) against Encodec._encode's offsets / lengths
+    (codec_basic.py:346-358) and the condition under which the reference's _linear_overlap_add raises (:101-112)."""
+    import ctypes
+    import random
+    import torch
+    from funcodec_b200 import _capi
+    from oracle import encodec_oracle as O
+    lib = _capi.load_library()
+    rnd = random.Random(7)
+    seen_ok = seen_bad = 0
+    for _ in range(400):
+        hop = rnd.choice([40, 320, 640])
+        seg = rnd.randint(hop // 2, 12 * hop)
+        stride = max(1, int((1 - rnd.choice([0.0, 0.01, 0.1, 0.25, 0.5, 0.75])) * seg))
+        L = rnd.randint(1, 40 * hop)
+        offsets = list(range(0, L, stride))
+        lens = [min(seg, L - o) for o in offsets]
+        dec = [-(-n // hop) * hop for n in lens]
+        n_tail = sum(1 for n in lens if n < seg)
+        try:
+            O.linear_overlap_add([torch.zeros(1, 1, d) + 1 for d in dec], stride)
+            ref_ok = True
+        except RuntimeError:
+            ref_ok = False
+        plan = _capi.FcbSegmentPlan()
+        rc = lib.fcb_plan_segments_for_hop(hop, L, seg, stride, ctypes.byref(plan))
+        if n_tail > _capi.FCB_MAX_TAIL_SEGMENTS:
+            assert rc != 0
+            continue
+        assert (rc == 0) == ref_ok, (hop, seg, stride, L, rc, ref_ok)
+        if rc != 0:
+            seen_bad += 1
+            continue
+        seen_ok += 1
+        assert plan.n_seg == len(offsets) and plan.n_full == len(offsets) - n_tail and plan.n_tail == n_tail
+        assert plan.frames_full * hop == -(-seg // hop) * hop == plan.decoded_full
+        assert [plan.tail_len[i] for i in range(n_tail)] == lens[plan.n_full:]
+        assert [plan.tail_frames[i] * hop for i in range(n_tail)] == dec[plan.n_full:]
+        assert plan.total_frames == sum(d // hop for d in dec)
+    assert seen_ok > 50 and seen_bad > 10, (seen_ok, seen_bad)
