@@ -38,3 +38,32 @@ def test_freqcodec_config4_architecture_oracle_vs_reference(golden_dir):
     assert np.abs(r["code_embeddings"][0][0].numpy() - z["quant"]).max() <= 1e-5
     assert r["recon_speech"].shape == z["recon"].shape
     assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 1e-5
+
+
+def test_freq_layers_oracle_vs_reference_modules(golden_dir):
+    """sconv2d / sconvtr2d / resblock2d against the reference MODULES SConv2d / SConvTranspose2d / SEANetResnetBlock2d
+    (tools/gen_golden_freq_layers.py): every kernel / stride family, odd lengths, out_padding."""
+    from oracle import freqcodec_oracle as FO
+    z = np.load(os.path.join(golden_dir, "freq_layers.npz"))
+
+    def sd_of(prefix):
+        return {"L." + k[len(prefix) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix + ".sd.")}
+
+    n = 0
+    while f"conv{n}.x" in z.files:
+        cin, cout, kf, kt, sf, st = [int(v) for v in z[f"conv{n}.meta"]]
+        y = FO.sconv2d(torch.from_numpy(z[f"conv{n}.x"]), sd_of(f"conv{n}"), "L", stride=(sf, st))
+        assert y.shape == z[f"conv{n}.y"].shape, (n, y.shape)
+        assert np.abs(y.numpy() - z[f"conv{n}.y"]).max() <= 2e-6, n
+        n += 1
+    assert n == 6
+    n = 0
+    while f"convtr{n}.x" in z.files:
+        cin, cout, sf, st, fl, fr, tl, tr = [int(v) for v in z[f"convtr{n}.meta"]]
+        y = FO.sconvtr2d(torch.from_numpy(z[f"convtr{n}.x"]), sd_of(f"convtr{n}"), "L", (sf, st), ((fl, fr), (tl, tr)))
+        assert y.shape == z[f"convtr{n}.y"].shape, (n, y.shape, z[f"convtr{n}.y"].shape)
+        assert np.abs(y.numpy() - z[f"convtr{n}.y"]).max() <= 2e-6, n
+        n += 1
+    assert n == 3
+    y = FO.resblock2d(torch.from_numpy(z["rb.x"]), sd_of("rb"), "L")
+    assert np.abs(y.numpy() - z["rb.y"]).max() <= 2e-6
