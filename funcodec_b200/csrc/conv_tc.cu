@@ -56,10 +56,10 @@ struct TcSmemLayout {
     int b_stage;       // bytes per B stage (hi + lo)
     int na, nb;        // ring depths
     int off_b, off_stg, off_bar, total;
-    int stg_group;     // STAGE mode: bytes of raw-input staging per producer group (2 stages x n_in x a_rows x 128)
+    int stg_group;     // STAGE mode: bytes of raw-input staging per producer group (depth x n_in x a_rows x 128)
 };
 
-__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb, int stg_inputs = 0) {
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb, int stg_inputs = 0, int stg_depth = 2) {
     TcSmemLayout L;
     const int qmax = (K - 1) / S;
     L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
@@ -68,7 +68,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     L.na = na; L.nb = nb;
     L.off_b = na * L.a_stage;
     L.off_stg = L.off_b + nb * L.b_stage;
-    L.stg_group = 2 * stg_inputs * L.a_rows * 128;
+    L.stg_group = stg_depth * stg_inputs * L.a_rows * 128;
     L.off_bar = L.off_stg + 2 * L.stg_group;
     L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
     return L;
@@ -94,14 +94,15 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 
 template <int N_TILE, bool FREQ, bool STAGE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles, const int w_resident, const int group_mmas) {
+                                                                 const int n_tiles, const int w_resident, const int group_mmas,
+                                                                 const int stg_depth) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, STAGE ? (has1 ? 2 : 1) : 0);
+    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, STAGE ? (has1 ? 2 : 1) : 0, stg_depth);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_units = n_chunks * S;
     const int upg = tc_units_per_group(K, S, group_mmas);
@@ -136,16 +137,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     if (STAGE && warp < 16) {
         // =========================================================== producers, STAGE mode (experimental, off by default)
         // The raw rows of a unit are fetched with per-thread cp.async (16 B each, zero-filled when out of range) into a
-        // staging area of the group one unit AHEAD of the unit being transformed, so the global-load latency of unit n+1
-        // overlaps the transform of unit n (the plain mode holds the rows in registers and serialises the two).  Every
-        // thread reads back only its own copies (cp.async.wait_group), so no extra barrier is involved.
+        // staging ring of the group, stg_depth - 1 units AHEAD of the unit being transformed, so the global-load latency
+        // of the next units overlaps the transform of this one (the plain mode holds the rows in registers and serialises
+        // the two; per SM that caps the bytes in flight at ~34 KB, i.e. ~2.4 TB/s at ~2 us of loaded latency -- what the
+        // wide layers measure).  Every thread reads back only its own copies (cp.async.wait_group): no extra barrier.
         const int grp = warp >> 3;
         const int ptid = tid & (TC_PROD - 1);
         const int jchunk = ptid & 7, rsub = ptid >> 3;
         const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
         const int pitch = FREQ ? p.fq.cin : C_in;
         const uint32_t stg_in = (uint32_t)L.a_rows * 128u;                       // bytes per (stage, input)
-        const uint32_t stg_stage = (has1 ? 2u : 1u) * stg_in;
+        const uint32_t stg_stage = (has1 ? 2u : 1u) * stg_in;         // bytes per staging slot
         uint8_t* stg = smem_raw + L.off_stg + (uint32_t)grp * (uint32_t)L.stg_group + (uint32_t)jchunk * 16u;
         constexpr int NR = 5;
         // (tile, unit) -> this thread's source rows; returns the in-range mask of its NR rows
@@ -193,20 +195,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             unit += 2;
             while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
         };
+        // transform cursor (tile, unit) and issue cursor (itile, iunit), the latter stg_depth - 1 units ahead; the in-range
+        // masks of the units in flight are packed 5 bits per staging slot
         int tile = blockIdx.x, unit = grp;
         while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+        int itile = tile, iunit = unit;
         int as = grp % na_stages;
         uint32_t aphase = 0;
-        int st = 0;
-        uint32_t m_cur = 0;
-        if (tile < n_tiles) m_cur = issue(tile, unit, 0);
+        int st = 0, ist = 0;
+        uint32_t masks = 0;
+        for (int d = 0; d < stg_depth - 1; ++d) {                     // prologue: fill the pipeline
+            if (itile < n_tiles) {
+                masks = (masks & ~(31u << (5 * ist))) | (issue(itile, iunit, ist) << (5 * ist));
+                advance(itile, iunit);
+            } else {
+                cp_async_commit();
+            }
+            if (++ist == stg_depth) ist = 0;
+        }
         while (tile < n_tiles) {
-            int ntile = tile, nunit = unit;
-            advance(ntile, nunit);
-            uint32_t m_nxt = 0;
-            if (ntile < n_tiles) m_nxt = issue(ntile, nunit, st ^ 1);
-            else cp_async_commit();                               // empty group: keeps the wait_group count uniform
-            cp_async_wait_group<1>();                              // this thread's copies of the CURRENT unit have landed
+            if (itile < n_tiles) {
+                masks = (masks & ~(31u << (5 * ist))) | (issue(itile, iunit, ist) << (5 * ist));
+                advance(itile, iunit);
+            } else {
+                cp_async_commit();                                // empty group: keeps the wait_group count uniform
+            }
+            if (++ist == stg_depth) ist = 0;
+            // all but the stg_depth - 1 most recent groups are complete: this thread's copies of the CURRENT unit have landed
+            if (stg_depth == 2) cp_async_wait_group<1>();
+            else if (stg_depth == 3) cp_async_wait_group<2>();
+            else cp_async_wait_group<3>();
+            const uint32_t m_cur = (masks >> (5 * st)) & 31u;
             {
                 const TcTile tl = tc_tile(tile, n_nt, n_tt);
                 int b = tl.b;
@@ -253,7 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 as += 2;
                 if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
             }
-            tile = ntile; unit = nunit; m_cur = m_nxt; st ^= 1;
+            advance(tile, unit);
+            if (++st == stg_depth) st = 0;
         }
         cp_async_wait_group<0>();
     } else if (warp < 16) {
@@ -567,27 +587,27 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1;
+static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1, g_stage_depth = 0, g_stage_na = 0;
 
 template <int N_TILE, bool FREQ, bool STAGE>
-static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
+static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident, int depth) {
     auto kern = conv1d_tc_kernel<N_TILE, FREQ, STAGE>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);
+    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas, depth);
     return cudaGetLastError();
 }
 
 template <int N_TILE>
 static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident,
-                                   bool freq, bool stage) {
-    if (freq) return stage ? launch_tc_n<N_TILE, true, true>(p, st, na, nb, smem, n_tiles, resident)
-                           : launch_tc_n<N_TILE, true, false>(p, st, na, nb, smem, n_tiles, resident);
-    return stage ? launch_tc_n<N_TILE, false, true>(p, st, na, nb, smem, n_tiles, resident)
-                 : launch_tc_n<N_TILE, false, false>(p, st, na, nb, smem, n_tiles, resident);
+                                   bool freq, bool stage, int depth) {
+    if (freq) return stage ? launch_tc_n<N_TILE, true, true>(p, st, na, nb, smem, n_tiles, resident, depth)
+                           : launch_tc_n<N_TILE, true, false>(p, st, na, nb, smem, n_tiles, resident, depth);
+    return stage ? launch_tc_n<N_TILE, false, true>(p, st, na, nb, smem, n_tiles, resident, depth)
+                 : launch_tc_n<N_TILE, false, false>(p, st, na, nb, smem, n_tiles, resident, depth);
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
@@ -602,6 +622,8 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (const char* v = getenv("FCB_TC_NA")) g_force_na = atoi(v);
         if (const char* v = getenv("FCB_TC_NB")) g_force_nb = atoi(v);
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
+        if (const char* v = getenv("FCB_TC_STAGE_DEPTH")) g_stage_depth = atoi(v);
+        if (const char* v = getenv("FCB_TC_STAGE_NA")) g_stage_na = atoi(v);
     }
     // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
@@ -611,16 +633,26 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     int resident = 0, na = 4, nb = 4;
     bool stage = false;
     TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
+    int depth = 2;
     if (p.stage_in) {
-        // EXPERIMENTAL cp.async staging of the raw input (see the STAGE producer branch): needs room for two raw stages
-        // per producer group next to the A ring; tried with na = 4 then 2, weights resident if they fit, else a ring of >= 3
+        // EXPERIMENTAL cp.async staging of the raw input (see the STAGE producer branch): needs room for `depth` raw slots
+        // per producer group next to the A ring.  Preference: more bytes in flight first (deeper staging with a 2-stage A
+        // ring), FCB_TC_STAGE_DEPTH / FCB_TC_STAGE_NA pin a configuration for sweeps; weights resident if they fit, else a
+        // ring of >= 3 slabs.
         const int n_in = p.in1.x ? 2 : 1;
-        for (int try_na = 4; try_na >= 2 && !stage; try_na -= 2) {
-            TcSmemLayout Ls = tc_layout(p.K, p.S, p.n_tile, try_na, n_slabs, n_in);
-            if (n_slabs <= 64 && p.C_out == p.n_tile && Ls.total <= limit) { stage = true; resident = 1; na = try_na; nb = n_slabs; L = Ls; break; }
+        static const int pref[][2] = {{2, 4}, {2, 3}, {4, 2}, {2, 2}};        // (na, depth)
+        for (int c = 0; c < 4 && !stage; ++c) {
+            const int try_na = pref[c][0], try_d = pref[c][1];
+            if (g_stage_depth > 0 && try_d != g_stage_depth) continue;
+            if (g_stage_na > 0 && try_na != g_stage_na) continue;
+            TcSmemLayout Ls = tc_layout(p.K, p.S, p.n_tile, try_na, n_slabs, n_in, try_d);
+            if (n_slabs <= 64 && p.C_out == p.n_tile && Ls.total <= limit) {
+                stage = true; resident = 1; na = try_na; nb = n_slabs; depth = try_d; L = Ls;
+                break;
+            }
             for (int try_nb = 6; try_nb >= 3; --try_nb) {
-                Ls = tc_layout(p.K, p.S, p.n_tile, try_na, try_nb, n_in);
-                if (Ls.total <= limit) { stage = true; na = try_na; nb = try_nb; L = Ls; break; }
+                Ls = tc_layout(p.K, p.S, p.n_tile, try_na, try_nb, n_in, try_d);
+                if (Ls.total <= limit) { stage = true; na = try_na; nb = try_nb; depth = try_d; L = Ls; break; }
             }
         }
     }
@@ -649,10 +681,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     const int n_tiles = n_tt * n_nt * B;
     const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
     switch (p.n_tile) {
-        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
-        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
-        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
-        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq, stage);
+        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
+        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
+        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
+        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
         default: return cudaErrorInvalidConfiguration;
     }
 }

@@ -21,6 +21,9 @@ PY
 }
 BENCH_ARGS="" run cfg2_default FCB_TC_STAGE=0
 BENCH_ARGS="" run cfg2_stage FCB_TC_STAGE=1
+BENCH_ARGS="" run cfg2_stage_d2na4 FCB_TC_STAGE=1 FCB_TC_STAGE_DEPTH=2 FCB_TC_STAGE_NA=4
+BENCH_ARGS="" run cfg2_stage_d3na2 FCB_TC_STAGE=1 FCB_TC_STAGE_DEPTH=3 FCB_TC_STAGE_NA=2
+BENCH_ARGS="" run cfg2_stage_d4na2 FCB_TC_STAGE=1 FCB_TC_STAGE_DEPTH=4 FCB_TC_STAGE_NA=2
 BENCH_ARGS="" run cfg2_m256 FCB_TC_M256=1
 BENCH_ARGS="" run cfg2_lstm_prefetch FCB_LSTM_PREFETCH_POLL=1
 BENCH_ARGS="" run cfg2_all FCB_TC_STAGE=1 FCB_TC_M256=1 FCB_LSTM_PREFETCH_POLL=1
