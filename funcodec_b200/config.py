@@ -32,6 +32,17 @@ class CodecConfig:
     ratios_f: Tuple[int, ...] = ()
     n_fft: int = 512
     stft_hop: int = 160
+    # grouped 2-D convs (encoder_conf / decoder_conf `conv_group_ratio`, decoder_conf `tr_conv_group_ratio`;
+    # seanet_encoder.py:224,234,321, seanet_decoder.py:219,229,324): groups = channels // 2 // ratio, -1 = dense
+    conv_group_ratio: int = -1
+    tr_conv_group_ratio: int = -1
+
+    def conv_groups(self, channels: int) -> int:
+        """groups of a 2-D conv whose reference expression is `channels // 2 // conv_group_ratio`."""
+        return channels // 2 // self.conv_group_ratio if self.conv_group_ratio > 0 else 1
+
+    def tr_conv_groups(self, channels: int) -> int:
+        return channels // 2 // self.tr_conv_group_ratio if self.tr_conv_group_ratio > 0 else 1
 
     @property
     def hop_length(self) -> int:
@@ -80,6 +91,12 @@ PRESETS: Dict[str, CodecConfig] = {
     # conv groups = 1 -- the hub model's gr8 grouping is not in the repository)
     "freqcodec_magphase_16k_n32_ds320": CodecConfig(name="freqcodec_magphase_16k_n32_ds320", arch=1, ratios=(1, 1, 2, 1),
                                                     ratios_f=(4, 4, 4, 4)),
+    # the hub checkpoint BASELINE config 4 names ("...gr8nq32ds320"): conv_group_ratio 8 in the resblocks / downsampling convs;
+    # its YAML is not in the repository, so the transposed convs are assumed grouped alike
+    "freqcodec_magphase_16k_n32_ds320_gr8": CodecConfig(name="freqcodec_magphase_16k_n32_ds320_gr8", arch=1, ratios=(1, 1, 2, 1),
+                                                        ratios_f=(4, 4, 4, 4), conv_group_ratio=8, tr_conv_group_ratio=8),
+    "freq_small_grouped": CodecConfig(name="freq_small_grouped", arch=1, ratios=(1, 1, 2, 1), ratios_f=(4, 4, 4, 4), n_filters=8,
+                                      dimension=32, codebook_size=64, num_quantizers=6, conv_group_ratio=1, tr_conv_group_ratio=2),
     "freq_small": CodecConfig(name="freq_small", arch=1, ratios=(1, 1, 2, 1), ratios_f=(4, 4, 4, 4), n_filters=4,
                               dimension=32, codebook_size=64, num_quantizers=6),
     "small_ds320": CodecConfig(name="small_ds320", ratios=(8, 5, 4, 2), n_filters=8, dimension=64,

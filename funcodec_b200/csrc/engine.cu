@@ -625,20 +625,27 @@ int pack_tc2d(fcb_handle* h, const std::vector<float>& wp, const std::vector<flo
 
 // SConv2d weight [cout][cin][kf][kt] -> [kt][kf*cin_store + ci][cout]; cin_store >= cin pads the stored input channels
 // with zero weights (the 3-channel mag_phase features are kept as 4 channels so that a frequency tap is one 16-byte load).
+// groups > 1 (conv_group_ratio): the reference weight is [cout][cin / groups][kf][kt]; it is expanded into the dense
+// block-diagonal matrix (zeros outside the groups), so the same dense kernels run it -- identical results, dense MACs.
 int pack_conv2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int kf, int kt, int sf, int st, Conv2W* o,
-                int cin_store = 0) {
+                int cin_store = 0, int groups = 1) {
     if (cin_store < cin) cin_store = cin;
+    if (groups < 1 || cin % groups != 0 || cout % groups != 0)
+        return fail(h, FCB_E_INVALID, "conv groups do not divide the channels of " + prefix + " (check conv_group_ratio)");
+    const int cig = cin / groups, cog = cout / groups;
     const HostTensor *w, *b, *g, *be;
-    FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, kf, kt}, &w));
+    FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cig, kf, kt}, &w));
     FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
     FCB_TRY(need(h, prefix + ".conv.norm.weight", {cout}, &g));
     FCB_TRY(need(h, prefix + ".conv.norm.bias", {cout}, &be));
     std::vector<float> p((size_t)kt * kf * cin_store * cout, 0.f);
-    for (int co = 0; co < cout; ++co)
-        for (int ci = 0; ci < cin; ++ci)
+    for (int co = 0; co < cout; ++co) {
+        const int ci0 = (co / cog) * cig;                 // first input channel of this output channel's group
+        for (int cl = 0; cl < cig; ++cl)
             for (int a = 0; a < kf; ++a)
                 for (int c = 0; c < kt; ++c)
-                    p[(((size_t)c * kf + a) * cin_store + ci) * cout + co] = w->data[(((size_t)co * cin + ci) * kf + a) * kt + c];
+                    p[(((size_t)c * kf + a) * cin_store + ci0 + cl) * cout + co] = w->data[(((size_t)co * cig + cl) * kf + a) * kt + c];
+    }
     o->cin = cin_store; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = sf; o->st = st; o->transposed = false;
     o->kf_eff = kf; o->kt_eff = kt;
     FCB_TRY(upload(h, p, &o->w));
@@ -652,23 +659,28 @@ int pack_conv2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int
 // SConvTranspose2d (k = 2s per axis) weight [cin][cout][2fr][2tr] -> 2x2-tap conv, C_out' = fr*tr*cout:
 // packed[kti][kfi*cin + ci][(pf*tr + pt)*cout + co] = W[ci][co][pf + (1-kfi)*fr][pt + (1-kti)*tr]
 // (tap index 0 <-> the previous input row / column, as in pack_convtr).
-int pack_convtr2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int fr, int tr, Conv2W* o) {
+int pack_convtr2d(fcb_handle* h, const std::string& prefix, int cin, int cout, int fr, int tr, Conv2W* o, int groups = 1) {
     const int kf = 2 * fr, kt = 2 * tr;
+    if (groups < 1 || cin % groups != 0 || cout % groups != 0)
+        return fail(h, FCB_E_INVALID, "conv groups do not divide the channels of " + prefix + " (check tr_conv_group_ratio)");
+    const int cig = cin / groups, cog = cout / groups;     // nn.ConvTranspose2d weight: [cin][cout / groups][kf][kt]
     const HostTensor *w, *b, *g, *be;
-    FCB_TRY(need(h, prefix + ".convtr.convtr.weight", {cin, cout, kf, kt}, &w));
+    FCB_TRY(need(h, prefix + ".convtr.convtr.weight", {cin, cog, kf, kt}, &w));
     FCB_TRY(need(h, prefix + ".convtr.convtr.bias", {cout}, &b));
     FCB_TRY(need(h, prefix + ".convtr.norm.weight", {cout}, &g));
     FCB_TRY(need(h, prefix + ".convtr.norm.bias", {cout}, &be));
     const int ce = fr * tr * cout;
-    std::vector<float> p((size_t)2 * 2 * cin * ce), bias(ce);
+    std::vector<float> p((size_t)2 * 2 * cin * ce, 0.f), bias(ce);
     for (int kti = 0; kti < 2; ++kti)
         for (int kfi = 0; kfi < 2; ++kfi)
             for (int ci = 0; ci < cin; ++ci)
                 for (int pf = 0; pf < fr; ++pf)
                     for (int pt = 0; pt < tr; ++pt)
-                        for (int co = 0; co < cout; ++co)
+                        for (int cl = 0; cl < cog; ++cl) {
+                            const int co = (ci / cig) * cog + cl;      // output channels of input channel ci's group
                             p[(((size_t)kti * 2 + kfi) * cin + ci) * ce + (pf * tr + pt) * cout + co] =
-                                w->data[(((size_t)ci * cout + co) * kf + pf + (1 - kfi) * fr) * kt + pt + (1 - kti) * tr];
+                                w->data[(((size_t)ci * cog + cl) * kf + pf + (1 - kfi) * fr) * kt + pt + (1 - kti) * tr];
+                        }
     for (int ph = 0; ph < fr * tr; ++ph)
         for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
     o->cin = cin; o->cout = cout; o->kf = kf; o->kt = kt; o->sf = fr; o->st = tr; o->transposed = true;
@@ -681,11 +693,15 @@ int pack_convtr2d(fcb_handle* h, const std::string& prefix, int cin, int cout, i
     return FCB_OK;
 }
 
+// groups = channels // 2 // ratio (seanet_encoder.py:224,234,321; seanet_decoder.py:324), dense when ratio <= 0
+int conv_groups_of(int channels, int ratio) { return ratio > 0 ? channels / 2 / ratio : 1; }
+
 int pack_resblock2d(fcb_handle* h, const std::string& prefix, int dim, ResBlock2W* o) {
-    const int rk = h->cfg.residual_kernel_size;
-    FCB_TRY(pack_conv2d(h, prefix + ".block.1", dim, dim / 2, rk, rk, 1, 1, &o->c1));
-    FCB_TRY(pack_conv2d(h, prefix + ".block.3", dim / 2, dim, 1, 1, 1, 1, &o->c2));
-    FCB_TRY(pack_conv2d(h, prefix + ".shortcut", dim, dim, 1, 1, 1, 1, &o->sc));
+    const int rk = h->cfg.residual_kernel_size, gr = h->cfg.conv_group_ratio;
+    const int gb = conv_groups_of(dim / 2, gr);            // min(in, out) = dim / 2 for both block convs
+    FCB_TRY(pack_conv2d(h, prefix + ".block.1", dim, dim / 2, rk, rk, 1, 1, &o->c1, 0, gb));
+    FCB_TRY(pack_conv2d(h, prefix + ".block.3", dim / 2, dim, 1, 1, 1, 1, &o->c2, 0, gb));
+    FCB_TRY(pack_conv2d(h, prefix + ".shortcut", dim, dim, 1, 1, 1, 1, &o->sc, 0, conv_groups_of(dim, gr)));
     return FCB_OK;
 }
 
@@ -1043,7 +1059,8 @@ int finalize_freq(fcb_handle* h) {
         const int fr = c.ratios_f[i], tr = c.ratios[i];
         ResBlock2W rb; Conv2W down;
         FCB_TRY(pack_resblock2d(h, "encoder.model." + std::to_string(n), mult * nf, &rb));
-        FCB_TRY(pack_conv2d(h, "encoder.model." + std::to_string(n + 2), mult * nf, 2 * mult * nf, 2 * fr, 2 * tr, fr, tr, &down));
+        FCB_TRY(pack_conv2d(h, "encoder.model." + std::to_string(n + 2), mult * nf, 2 * mult * nf, 2 * fr, 2 * tr, fr, tr, &down, 0,
+                            conv_groups_of(mult * nf, c.conv_group_ratio)));
         h->f_enc_rb.push_back(rb); h->f_enc_down.push_back(down);
         mult *= 2; n += 3;
     }
@@ -1063,7 +1080,8 @@ int finalize_freq(fcb_handle* h) {
     for (int i = 0; i < nr; ++i) {
         const int fr = c.ratios_f[i], tr = c.ratios[i];
         Conv2W up; ResBlock2W rb;
-        FCB_TRY(pack_convtr2d(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, fr, tr, &up));
+        FCB_TRY(pack_convtr2d(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, fr, tr, &up,
+                              conv_groups_of(mult * nf, c.tr_conv_group_ratio)));
         FCB_TRY(pack_resblock2d(h, "decoder.model." + std::to_string(n + 2), mult * nf / 2, &rb));
         if (i == nr - 1) up.out_pad[0][1] = 1;         // SEANetDecoder2d last_out_padding default [(0, 1), (0, 0)]
         h->f_dec_up.push_back(up); h->f_dec_rb.push_back(rb);

@@ -60,6 +60,7 @@ class B200Encodec:
         c.lstm_layers, c.codebook_size, c.num_quantizers = cfg.lstm_layers, cfg.codebook_size, cfg.num_quantizers
         c.sample_rate, c.audio_normalize, c.gn_eps = cfg.sample_rate, int(cfg.audio_normalize), cfg.gn_eps
         c.arch, c.n_fft, c.stft_hop = cfg.arch, cfg.n_fft, cfg.stft_hop
+        c.conv_group_ratio, c.tr_conv_group_ratio = cfg.conv_group_ratio, cfg.tr_conv_group_ratio
         for i, r in enumerate(cfg.ratios_f):
             c.ratios_f[i] = r
         self._h = ctypes.c_void_p()

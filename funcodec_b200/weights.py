@@ -51,12 +51,12 @@ def conv_specs(cfg: CodecConfig) -> List[Dict]:
 
 def _freq_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
     """SEANetEncoder2d / SEANetDecoder2d parameter names and shapes (seanet_encoder.py:252-363, seanet_decoder.py:244-360),
-    conv groups = 1."""
+    grouped like the reference when cfg.conv_group_ratio / tr_conv_group_ratio > 0."""
     sh: Dict[str, Tuple[int, ...]] = {}
     nf, D, rk = cfg.n_filters, cfg.dimension, cfg.residual_kernel_size
 
-    def conv2(name, cin, cout, kf, kt):
-        sh[name + ".conv.conv.weight"] = (cout, cin, kf, kt); sh[name + ".conv.conv.bias"] = (cout,)
+    def conv2(name, cin, cout, kf, kt, groups=1):
+        sh[name + ".conv.conv.weight"] = (cout, cin // groups, kf, kt); sh[name + ".conv.conv.bias"] = (cout,)
         sh[name + ".conv.norm.weight"] = (cout,); sh[name + ".conv.norm.bias"] = (cout,)
 
     def conv1(name, cin, cout, k):
@@ -64,8 +64,9 @@ def _freq_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
         sh[name + ".conv.norm.weight"] = (cout,); sh[name + ".conv.norm.bias"] = (cout,)
 
     def rb(name, dim):
-        conv2(name + ".block.1", dim, dim // 2, rk, rk); conv2(name + ".block.3", dim // 2, dim, 1, 1)
-        conv2(name + ".shortcut", dim, dim, 1, 1)
+        g = cfg.conv_groups(dim // 2)                    # min(in, out) = dim // 2 for both block convs
+        conv2(name + ".block.1", dim, dim // 2, rk, rk, g); conv2(name + ".block.3", dim // 2, dim, 1, 1, g)
+        conv2(name + ".shortcut", dim, dim, 1, 1, cfg.conv_groups(dim))
 
     def lstm(name, H):
         for l in range(cfg.lstm_layers):
@@ -76,7 +77,7 @@ def _freq_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
     n, mult = 1, 1
     for fr, tr in reversed(list(zip(cfg.ratios_f, cfg.ratios))):
         rb(f"encoder.model.{n}", mult * nf)
-        conv2(f"encoder.model.{n + 2}", mult * nf, 2 * mult * nf, 2 * fr, 2 * tr)
+        conv2(f"encoder.model.{n + 2}", mult * nf, 2 * mult * nf, 2 * fr, 2 * tr, cfg.conv_groups(mult * nf))
         mult *= 2; n += 3
     n += 1
     if cfg.lstm_layers > 0:
@@ -89,7 +90,8 @@ def _freq_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
     n += 1
     for fr, tr in zip(cfg.ratios_f, cfg.ratios):
         name = f"decoder.model.{n + 1}"
-        sh[name + ".convtr.convtr.weight"] = (mult * nf, mult * nf // 2, 2 * fr, 2 * tr); sh[name + ".convtr.convtr.bias"] = (mult * nf // 2,)
+        sh[name + ".convtr.convtr.weight"] = (mult * nf, mult * nf // 2 // cfg.tr_conv_groups(mult * nf), 2 * fr, 2 * tr)
+        sh[name + ".convtr.convtr.bias"] = (mult * nf // 2,)
         sh[name + ".convtr.norm.weight"] = (mult * nf // 2,); sh[name + ".convtr.norm.bias"] = (mult * nf // 2,)
         rb(f"decoder.model.{n + 2}", mult * nf // 2)
         mult //= 2; n += 3

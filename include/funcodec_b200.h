@@ -66,6 +66,10 @@ typedef struct fcb_config {
     int32_t ratios_f[FCB_MAX_RATIOS];
     int32_t n_fft;                  /* 512 */
     int32_t stft_hop;               /* 160 */
+    /* grouped 2-D convs (arch 1): encoder_conf / decoder_conf conv_group_ratio and decoder_conf tr_conv_group_ratio
+     * (seanet_encoder.py:224,234,321; seanet_decoder.py:219,229,324): groups = channels / 2 / ratio; <= 0: dense */
+    int32_t conv_group_ratio;
+    int32_t tr_conv_group_ratio;
 } fcb_config;
 
 typedef struct fcb_handle fcb_handle;

@@ -30,10 +30,12 @@ def pad2d_reflect(x, pad_time: Tuple[int, int], pad_freq: Tuple[int, int]):
     return padded[..., : padded.shape[-2] - extra_f, : padded.shape[-1] - extra_t]
 
 
-def sconv2d(x, p: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), groups: int = 1):
+def sconv2d(x, p: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), groups: int = None):
     """SConv2d.forward, non-causal (conv.py:342-376) + NormConv2d (conv.py:180-184): frequency axis gets no extra padding."""
     w = p[prefix + ".conv.conv.weight"]
     b = p[prefix + ".conv.conv.bias"]
+    if groups is None:                            # nn.Conv2d weight is [C_out, C_in / groups, kf, kt] (conv_group_ratio > 0)
+        groups = x.shape[1] // w.shape[1]
     kf, kt = w.shape[-2:]
     sf, st = stride
     pt_f = (kf - 1) - (sf - 1)
@@ -48,10 +50,12 @@ def sconv2d(x, p: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), groups: i
     return F.group_norm(y, 1, p[prefix + ".conv.norm.weight"], p[prefix + ".conv.norm.bias"], EPS_GN)
 
 
-def sconvtr2d(x, p: Dict[str, torch.Tensor], prefix: str, stride, out_padding=((0, 0), (0, 0)), groups: int = 1):
+def sconvtr2d(x, p: Dict[str, torch.Tensor], prefix: str, stride, out_padding=((0, 0), (0, 0)), groups: int = None):
     """SConvTranspose2d.forward, non-causal (conv.py:407-447): convtr -> GroupNorm -> unpad2d with out_padding."""
     w = p[prefix + ".convtr.convtr.weight"]
     b = p[prefix + ".convtr.convtr.bias"]
+    if groups is None:                            # nn.ConvTranspose2d weight is [C_in, C_out / groups, kf, kt]
+        groups = b.shape[0] // w.shape[1]
     kf, kt = w.shape[-2:]
     sf, st = stride
     y = F.conv_transpose2d(x, w, b, stride=(sf, st), groups=groups)
@@ -66,7 +70,7 @@ def sconvtr2d(x, p: Dict[str, torch.Tensor], prefix: str, stride, out_padding=((
 
 
 def resblock2d(x, p, prefix: str):
-    """SEANetResnetBlock2d.forward (seanet_encoder.py:188-237), true_skip=False, groups=1."""
+    """SEANetResnetBlock2d.forward (seanet_encoder.py:188-237), true_skip=False; conv groups follow the weight shapes."""
     h = sconv2d(O.elu(x), p, prefix + ".block.1")
     h = sconv2d(O.elu(h), p, prefix + ".block.3")
     return sconv2d(x, p, prefix + ".shortcut") + h

@@ -159,3 +159,24 @@ def test_m256_deep_layers():
     ra, rb = m["tc"].inference(wav), model.inference(wav)
     same = (ra["code_indices"][0] == rb["code_indices"][0]).all(dim=0).float().mean().item()
     assert same >= 0.99, same
+
+
+def test_grouped_freq_model(golden_dir):
+    """conv_group_ratio / tr_conv_group_ratio > 0: the engine expands the grouped weights to dense block-diagonal matrices at
+    pack time (engine.cu pack_conv2d / pack_convtr2d); against the vectors of the unmodified grouped reference model.
+    (Opt-in until it has run on hardware; the expansion itself is checked on CPU in test_oracle_golden_freq.py.)"""
+    from funcodec_b200.encodec import B200Encodec
+    from oracle.freqcodec_oracle import OracleFreqCodec
+    from parity_utils import assert_codes_parity
+    z = np.load(os.path.join(golden_dir, "freq_magphase_small_grouped.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    sd = init_state_dict(cfg, int(z["seed"]))
+    model = B200Encodec(cfg, sd, "cuda:0")
+    wav = torch.from_numpy(z["wav"])
+    ora = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios))).inference(wav, want_margin=True)
+    r = model.inference(wav, need_recon=True, need_encoder_out=True)
+    assert np.abs(r["encoder_out"].cpu().numpy() - z["encoder_out"]).max() <= 5e-5
+    res = assert_codes_parity(r["code_indices"][0].cpu().numpy(), z["codes"], ora["margins"].numpy(), 2e-3, min_exact_rate=0.9,
+                              what="grouped")
+    if not (res["first_stage"] >= 0).any():
+        assert np.abs(r["recon_speech"].cpu().numpy() - z["recon"]).max() <= 1e-4

@@ -67,3 +67,59 @@ def test_freq_layers_oracle_vs_reference_modules(golden_dir):
     assert n == 3
     y = FO.resblock2d(torch.from_numpy(z["rb.x"]), sd_of("rb"), "L")
     assert np.abs(y.numpy() - z["rb.y"]).max() <= 2e-6
+
+
+def _dense_convtr_weights(sd):
+    """The engine's treatment of grouped transposed 2-D convs (engine.cu pack_convtr2d): block-diagonal dense weights
+    [C_in][C_out]; plain convs are expanded by _dense_conv_weight once the consumer's C_in is known."""
+    out = dict(sd)
+    for k, w in sd.items():
+        if w.dim() == 4 and k.endswith(".convtr.convtr.weight"):
+            cin, cog = w.shape[:2]
+            cout = sd[k.replace("weight", "bias")].shape[0]
+            cig = cin // (cout // cog)
+            dense = torch.zeros(cin, cout, *w.shape[2:])
+            for ci in range(cin):
+                dense[ci, (ci // cig) * cog:(ci // cig + 1) * cog] = w[ci]
+            out[k] = dense
+    return out
+
+
+def _dense_conv_weight(w, cin):
+    cout, cig = w.shape[:2]
+    g = cin // cig
+    cog = cout // g
+    dense = torch.zeros(cout, cin, *w.shape[2:])
+    for co in range(cout):
+        dense[co, (co // cog) * cig:(co // cog + 1) * cig] = w[co]
+    return dense
+
+
+def test_freqcodec_grouped_convs_oracle_vs_reference(golden_dir):
+    """conv_group_ratio / tr_conv_group_ratio > 0 (seanet_encoder.py:224,234,321; seanet_decoder.py:219,229,324): the oracle
+    against the unmodified reference, and the dense block-diagonal expansion the engine uses against both."""
+    from funcodec_b200 import get_config, init_state_dict
+    z = np.load(os.path.join(golden_dir, "freq_magphase_small_grouped.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    assert cfg.conv_group_ratio > 0 and cfg.tr_conv_group_ratio > 0
+    sd = init_state_dict(cfg, int(z["seed"]))
+    assert sd["encoder.model.1.shortcut.conv.conv.weight"].shape[1] == cfg.n_filters // cfg.conv_groups(cfg.n_filters)
+    ratios = list(zip(cfg.ratios_f, cfg.ratios))
+    wav = torch.from_numpy(z["wav"])
+    r = OracleFreqCodec(sd, ratios).inference(wav)
+    assert np.abs(r["encoder_out"].numpy() - z["encoder_out"]).max() <= 5e-6
+    assert np.array_equal(r["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 5e-6
+    # dense expansion: every grouped weight becomes block-diagonal; the (group-inferring) oracle then runs groups = 1
+    dense = _dense_convtr_weights(sd)
+    from funcodec_b200.weights import state_dict_shapes
+    dense_cfg = get_config("freq_small_grouped").__class__(**{**cfg.to_dict(), "conv_group_ratio": -1, "tr_conv_group_ratio": -1})
+    for k, shp in state_dict_shapes(dense_cfg).items():
+        if k.endswith(".conv.conv.weight") and len(shp) == 4:
+            dense[k] = _dense_conv_weight(sd[k], shp[1])
+            assert tuple(dense[k].shape) == tuple(shp)
+        elif k.endswith(".convtr.convtr.weight"):
+            assert tuple(dense[k].shape) == tuple(shp)
+    r2 = OracleFreqCodec(dense, ratios).inference(wav)
+    assert np.array_equal(r2["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert np.abs(r2["recon_speech"].numpy() - z["recon"]).max() <= 1e-5
