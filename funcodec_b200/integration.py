@@ -49,8 +49,6 @@ def config_from_reference_model(model) -> CodecConfig:
     n_lstm = len([k for k in sd if k.startswith("decoder.model.1.lstm.weight_ih_l")])
     last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.model."))
     rb_k = sd["encoder.model.1.block.1.conv.conv.weight"].shape[-1]
-    if freq and sd["encoder.model.1.block.1.conv.conv.weight"].shape[1] != sd["encoder.model.0.conv.conv.weight"].shape[0]:
-        raise UnsupportedReferenceModel("grouped 2-D convs (conv_group_ratio > 0) are not supported")
     dconf = getattr(model, "domain_conf", None) or {}
     cfg = CodecConfig(name="from_reference", ratios=ratios, arch=1 if freq else 0, ratios_f=ratios_f,
                       n_fft=int(dconf.get("n_fft", 512)), stft_hop=int(dconf.get("hop_length", 160)),
@@ -62,6 +60,20 @@ def config_from_reference_model(model) -> CodecConfig:
                       audio_normalize=bool(model.audio_normalize))
     if cfg.hop_length != int(q.encoder_hop_length):
         raise UnsupportedReferenceModel("quantizer.encoder_hop_length does not match prod(ratios)")
+    if freq:
+        # the modules do not keep conv_group_ratio / tr_conv_group_ratio: recover them from the weight shapes
+        from dataclasses import replace
+        from .weights import state_dict_shapes
+        for gr in (-1, 1, 2, 4, 8, 16, 32):
+            for tgr in (-1, 1, 2, 4, 8, 16, 32):
+                cand = replace(cfg, conv_group_ratio=gr, tr_conv_group_ratio=tgr)
+                try:
+                    shapes = state_dict_shapes(cand)
+                except ZeroDivisionError:
+                    continue
+                if all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items() if k in sd and k.endswith(".weight")):
+                    return cand
+        raise UnsupportedReferenceModel("2-D conv weight shapes match no conv_group_ratio / tr_conv_group_ratio")
     return cfg
 
 

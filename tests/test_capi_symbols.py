@@ -85,6 +85,14 @@ def test_config_from_reference_like_freqcodec():
     for f in ("arch", "ratios", "ratios_f", "n_fft", "stft_hop", "n_filters", "dimension", "kernel_size", "last_kernel_size",
               "residual_kernel_size", "lstm_layers", "codebook_size", "num_quantizers"):
         assert getattr(got, f) == getattr(cfg, f), f
+    assert (got.conv_group_ratio, got.tr_conv_group_ratio) == (-1, -1)
+    # grouped 2-D convs: the ratios are recovered from the weight shapes
+    gcfg = get_config("freq_small_grouped")
+    gsd = init_state_dict(gcfg, 0)
+    m.state_dict = lambda: gsd
+    got = config_from_reference_model(m)
+    assert (got.conv_group_ratio, got.tr_conv_group_ratio, got.n_filters) == (gcfg.conv_group_ratio, gcfg.tr_conv_group_ratio, gcfg.n_filters)
+    m.state_dict = lambda: sd
     m.segment_dur = 1.0
     with pytest.raises(UnsupportedReferenceModel):
         config_from_reference_model(m)
