@@ -31,6 +31,9 @@ WORKLOADS = {
     "config3": ("encodec_16k_n32_ds320", 64, 480000, None),
     "config5": ("encodec_16k_n32_ds640", 64, 160000, None),
     "config4": ("freqcodec_magphase_16k_n32_ds320", 32, 160000, None),
+    # the grouped ("gr8") hub variant BASELINE config 4 names; its YAML is not in the repository (conv_group_ratio = 8 assumed
+    # for the transposed convs too); the engine runs the grouped weights as dense block-diagonal matrices
+    "config4_gr8": ("freqcodec_magphase_16k_n32_ds320_gr8", 32, 160000, None),
 }
 # SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the 48 conv launches of ONE config-2 step, from the
@@ -41,6 +44,9 @@ ALGO = {
                                   rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
     "freqcodec_magphase_16k_n32_ds320": dict(conv_bytes_per_10s=803.2e6, conv_gmac_per_10s=24.95, lstm_gmac_per_10s=4.20,
                                              rvq_gflop_per_10s_nq32=2.10, weight_bytes=64.9e6),
+    # gr8: same activations; SURVEY §8(d): 10.42 GMAC per 10 s clip of grouped math (the engine executes the dense 24.95)
+    "freqcodec_magphase_16k_n32_ds320_gr8": dict(conv_bytes_per_10s=803.2e6, conv_gmac_per_10s=10.42, lstm_gmac_per_10s=4.20,
+                                                 rvq_gflop_per_10s_nq32=2.10, weight_bytes=64.9e6),
     "encodec_16k_n32_ds320": dict(conv_bytes_per_10s=780.1e6, conv_gmac_per_10s=15.67, lstm_gmac_per_10s=4.19,
                                   rvq_gflop_per_10s_nq32=4.19, weight_bytes=59.4e6),
 }
