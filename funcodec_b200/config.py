@@ -91,6 +91,11 @@ PRESETS: Dict[str, CodecConfig] = {
     # conv groups = 1 -- the hub model's gr8 grouping is not in the repository)
     "freqcodec_magphase_16k_n32_ds320": CodecConfig(name="freqcodec_magphase_16k_n32_ds320", arch=1, ratios=(1, 1, 2, 1),
                                                     ratios_f=(4, 4, 4, 4)),
+    # repo YAML conf/freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml (ratios [[4, 2], [4, 1], [4, 2], [4, 1]], hop 640)
+    "freqcodec_magphase_16k_n32_ds640": CodecConfig(name="freqcodec_magphase_16k_n32_ds640", arch=1, ratios=(2, 1, 2, 1),
+                                                    ratios_f=(4, 4, 4, 4)),
+    "freq_small_ds640": CodecConfig(name="freq_small_ds640", arch=1, ratios=(2, 1, 2, 1), ratios_f=(4, 4, 4, 4), n_filters=4,
+                                    dimension=32, codebook_size=64, num_quantizers=6),
     # the hub checkpoint BASELINE config 4 names ("...gr8nq32ds320"): conv_group_ratio 8 in the resblocks / downsampling convs;
     # its YAML is not in the repository, so the transposed convs are assumed grouped alike
     "freqcodec_magphase_16k_n32_ds320_gr8": CodecConfig(name="freqcodec_magphase_16k_n32_ds320_gr8", arch=1, ratios=(1, 1, 2, 1),

@@ -180,3 +180,24 @@ def test_grouped_freq_model(golden_dir):
                               what="grouped")
     if not (res["first_stage"] >= 0).any():
         assert np.abs(r["recon_speech"].cpu().numpy() - z["recon"]).max() <= 1e-4
+
+
+def test_freq_ds640_ratio_set(golden_dir):
+    """conf/freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml's ratio set (time strides 2, 1, 2, 1) against vectors of the
+    unmodified reference (opt-in until it has run on hardware; same kernels as the ds320 set, different strides)."""
+    from funcodec_b200.encodec import B200Encodec
+    from oracle.freqcodec_oracle import OracleFreqCodec
+    from parity_utils import assert_codes_parity
+    z = np.load(os.path.join(golden_dir, "freq_magphase_small_ds640.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    sd = init_state_dict(cfg, int(z["seed"]))
+    model = B200Encodec(cfg, sd, "cuda:0")
+    wav = torch.from_numpy(z["wav"])
+    ora = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios))).inference(wav, want_margin=True)
+    r = model.inference(wav, need_recon=True, need_encoder_out=True)
+    assert np.abs(r["encoder_out"].cpu().numpy() - z["encoder_out"]).max() <= 5e-5
+    res = assert_codes_parity(r["code_indices"][0].cpu().numpy(), z["codes"], ora["margins"].numpy(), 2e-3, min_exact_rate=0.9,
+                              what="ds640 ratios")
+    assert tuple(r["recon_speech"].shape) == tuple(z["recon"].shape)
+    if not (res["first_stage"] >= 0).any():
+        assert np.abs(r["recon_speech"].cpu().numpy() - z["recon"]).max() <= 1e-4

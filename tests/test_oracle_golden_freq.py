@@ -123,3 +123,21 @@ def test_freqcodec_grouped_convs_oracle_vs_reference(golden_dir):
     r2 = OracleFreqCodec(dense, ratios).inference(wav)
     assert np.array_equal(r2["code_indices"][0].numpy(), z["codes"].astype(np.int64))
     assert np.abs(r2["recon_speech"].numpy() - z["recon"]).max() <= 1e-5
+
+
+def test_freqcodec_ds640_ratios_oracle_vs_reference(golden_dir):
+    """The ratio set of conf/freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml ([[4, 2], [4, 1], [4, 2], [4, 1]]: a time stride
+    in the first decoder stage / last encoder stage) against the unmodified reference; also the host-side frame arithmetic."""
+    from funcodec_b200 import get_config, init_state_dict
+    z = np.load(os.path.join(golden_dir, "freq_magphase_small_ds640.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    assert cfg.hop_length == 640
+    sd = init_state_dict(cfg, int(z["seed"]))
+    wav = torch.from_numpy(z["wav"])
+    r = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios))).inference(wav)
+    assert r["encoder_out"].shape[1] == cfg.frames(wav.shape[-1]) == z["codes"].shape[-1]
+    assert np.abs(r["encoder_out"].numpy() - z["encoder_out"]).max() <= 5e-6
+    assert np.array_equal(r["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert r["recon_speech"].shape == z["recon"].shape
+    assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 5e-6
+    assert min(wav.shape[-1], cfg.decoded_length(cfg.frames(wav.shape[-1]))) == z["recon"].shape[-1]

@@ -15,7 +15,7 @@ from ref_harness import import_reference  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
-def build(n_filters, dimension, K, nq, ratios, conv_group_ratio=-1, tr_conv_group_ratio=-1):
+def build(n_filters, dimension, K, nq, ratios, conv_group_ratio=-1, tr_conv_group_ratio=-1, hop=320):
     import_reference()
     from funcodec.models import codec_freq
     codec_freq.check_argument_types = lambda: True
@@ -29,7 +29,7 @@ def build(n_filters, dimension, K, nq, ratios, conv_group_ratio=-1, tr_conv_grou
                           norm_params={"num_groups": 1}, causal=False, dilation_base=1, conv_group_ratio=conv_group_ratio,
                           tr_conv_group_ratio=tr_conv_group_ratio)
     q = CostumeQuantizer(input_size=dimension, codebook_size=K, num_quantizers=nq, kmeans_init=False, sampling_rate=16000,
-                         encoder_hop_length=320, use_ddp=True)
+                         encoder_hop_length=hop, use_ddp=True)
     m = codec_freq.FreqCodec(input_size=3, odim=dimension, encoder=enc, quantizer=q, decoder=dec, discriminator=None,
                              target_sample_hz=16000, multi_spectral_window_powers_of_two=[], audio_normalize=True,
                              segment_dur=None, overlap_ratio=None, codec_domain=["mag_phase", "mag_phase"])
@@ -101,5 +101,25 @@ if __name__ == "__main__":
                quant=r["code_embeddings"][0][0].numpy(), scale=r["code_embeddings"][0][1].numpy(), recon=r["recon_speech"].numpy(),
                encoder_out=emb.numpy(), sd_checksum=float(sum(v.double().abs().sum().item() for v in sd.values())))
     path = os.path.join(OUT, "freq_magphase_small_grouped.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB", "codes", out["codes"].shape, "recon", out["recon"].shape)
+
+    # the ds640 ratio set of conf/freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml (time strides 2, 1, 2, 1), small widths
+    cfg = get_config("freq_small_ds640")
+    sd = init_state_dict(cfg, 0)
+    ratios640 = [[f, t] for f, t in zip(cfg.ratios_f, cfg.ratios)]
+    m = build(cfg.n_filters, cfg.dimension, cfg.codebook_size, cfg.num_quantizers, ratios640, hop=640)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.split(".")[-1] in ("cluster_size", "embed_avg", "inited", "window") for k in missing), (missing, unexpected)
+    m.quantizer.rq.model.inited.fill_(1)
+    g = torch.Generator().manual_seed(10)
+    wav = 0.1 * torch.randn(2, 6400 + 333, generator=g)
+    with torch.no_grad():
+        r = m.inference(wav, need_recon=True, bit_width=None, use_scale=True)
+        emb, scale = m._encode(wav.unsqueeze(1))[0]
+    out = dict(cfg_name=cfg.name, seed=0, wav=wav.numpy(), codes=r["code_indices"][0].numpy().astype(np.int16),
+               quant=r["code_embeddings"][0][0].numpy(), scale=r["code_embeddings"][0][1].numpy(), recon=r["recon_speech"].numpy(),
+               encoder_out=emb.numpy(), sd_checksum=float(sum(v.double().abs().sum().item() for v in sd.values())))
+    path = os.path.join(OUT, "freq_magphase_small_ds640.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB", "codes", out["codes"].shape, "recon", out["recon"].shape)
