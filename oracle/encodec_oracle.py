@@ -87,9 +87,10 @@ def elu(x):
     return F.elu(x, alpha=1.0)
 
 
-def resblock(x, p, prefix: str, res_kernel: int = 3):
-    """SEANetResnetBlock.forward (seanet_encoder.py:16-61): shortcut(x) + block(x), true_skip=False."""
-    h = sconv1d(elu(x), p, prefix + ".block.1")
+def resblock(x, p, prefix: str, res_kernel: int = 3, dilation: int = 1):
+    """SEANetResnetBlock.forward (seanet_encoder.py:16-61): shortcut(x) + block(x), true_skip=False; the first block conv
+    carries the dilation (dilations=[dilation_base ** j, 1], seanet_encoder.py:125)."""
+    h = sconv1d(elu(x), p, prefix + ".block.1", dilation=dilation)
     h = sconv1d(elu(h), p, prefix + ".block.3")
     return sconv1d(x, p, prefix + ".shortcut") + h
 
@@ -143,15 +144,19 @@ def sub_dict(p: Dict[str, torch.Tensor], head: str) -> Dict[str, torch.Tensor]:
     return {k[n:]: v for k, v in p.items() if k.startswith(head)}
 
 
-def seanet_encoder(x, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False):
+def seanet_encoder(x, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False,
+                   n_residual_layers: int = 1, dilation_base: int = 2):
     """SEANetEncoder.forward (seanet_encoder.py:108-162,171-185).  x: [B,1,L] -> [B,T',D].
-    `ratios` as given in the YAML; the encoder applies them reversed (seanet_encoder.py:102)."""
+    `ratios` as given in the YAML; the encoder applies them reversed (seanet_encoder.py:102).  n_residual_layers > 1 (the
+    soundstream_* YAMLs) stacks residual blocks with dilations dilation_base ** j (:122-128); lstm_layers = 0 is
+    `seq_model: none`."""
     h = sconv1d(x, p, "model.0")
     n = 1
     for r in reversed(list(ratios)):
-        h = resblock(h, p, f"model.{n}")
-        h = sconv1d(elu(h), p, f"model.{n + 2}", stride=r)
-        n += 3
+        for j in range(n_residual_layers):
+            h = resblock(h, p, f"model.{n + j}", dilation=dilation_base ** j)
+        h = sconv1d(elu(h), p, f"model.{n + n_residual_layers + 1}", stride=r)
+        n += n_residual_layers + 2
     if lstm_layers > 0:
         h = slstm(h, p, f"model.{n}", lstm_layers, manual_lstm)
         n += 1
@@ -159,7 +164,8 @@ def seanet_encoder(x, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lst
     return h.permute(0, 2, 1)
 
 
-def seanet_decoder(z, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False):
+def seanet_decoder(z, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False,
+                   n_residual_layers: int = 1, dilation_base: int = 2):
     """SEANetDecoder.forward (seanet_decoder.py:107-172,177-180).  z: [B,T',D] -> [B,1,T'*hop]."""
     h = sconv1d(z.permute(0, 2, 1), p, "model.0")
     n = 1
@@ -168,8 +174,9 @@ def seanet_decoder(z, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lst
         n = 2
     for r in ratios:
         h = sconvtr1d(elu(h), p, f"model.{n + 1}", stride=r)
-        h = resblock(h, p, f"model.{n + 2}")
-        n += 3
+        for j in range(n_residual_layers):
+            h = resblock(h, p, f"model.{n + 2 + j}", dilation=dilation_base ** j)
+        n += n_residual_layers + 2
     return sconv1d(elu(h), p, f"model.{n + 1}")
 
 

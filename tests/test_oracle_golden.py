@@ -197,3 +197,18 @@ def test_laura_call_patterns_on_the_oracle():
     assert tuple(r["gen_only_lm"].shape) == (1, 1, 13 * 320) == tuple(r["gen"].shape)
     # with exactly the predicted groups, decoding the codes and decoding their summed codewords are the same computation
     assert (r["gen_only_lm"] - r["gen"]).abs().max().item() <= 1e-5
+
+
+def test_soundstream_noncausal_topology(golden_dir):
+    """conf/soundstream_noncausal_16k_n32_600k_step.yaml's topology -- three residual blocks per stage with dilations 1 / 2 / 4
+    (seanet_encoder.py:122-128), no sequence model -- against the unmodified reference SEANetEncoder / SEANetDecoder
+    (tools/gen_golden_soundstream.py).  Oracle only: the CUDA engine does not build this topology yet."""
+    z = np.load(os.path.join(golden_dir, "soundstream_noncausal_small.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    ratios = [int(r) for r in z["ratios"]]
+    emb = O.seanet_encoder(torch.from_numpy(z["x"]), O.sub_dict(sd, "encoder."), ratios, lstm_layers=0, n_residual_layers=3)
+    assert emb.shape == z["emb"].shape
+    assert np.abs(emb.numpy() - z["emb"]).max() <= 2e-6
+    y = O.seanet_decoder(torch.from_numpy(z["emb"]), O.sub_dict(sd, "decoder."), ratios, lstm_layers=0, n_residual_layers=3)
+    assert y.shape == z["y"].shape
+    assert np.abs(y.numpy() - z["y"]).max() <= 2e-6
