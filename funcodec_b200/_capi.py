@@ -53,6 +53,7 @@ SYMBOLS = {
     "fcb_roundtrip": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
     "fcb_roundtrip_host": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "fcb_check_errors": (c_int32, [c_void_p, c_void_p]),
     "fcb_launch_count": (c_int64, [c_void_p]),
     "fcb_set_profiling": (c_int32, [c_void_p, c_int32]),
     "fcb_get_phase_ms": (c_int32, [c_void_p, POINTER(c_float)]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfuncodec_b200.so")
-SOURCES = ["engine.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_m256.cu", "conv2d_simt.cu", "lstm.cu", "rvq_simt.cu", "rvq_tc.cu", "misc.cu"]
+SOURCES = ["engine.cu", "conv_simt.cu", "conv_tc.cu", "conv2d_simt.cu", "lstm.cu", "rvq_simt.cu", "rvq_tc.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

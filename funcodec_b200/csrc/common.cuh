@@ -55,7 +55,7 @@ struct ConvParams {
     double* partials;        // [B][n_parts][2] (sum, sum of squares) or nullptr
     int cic;                 // input-channel chunk staged per iteration
     Freq2d fq;               // tensor-core 2-D mode (zero-initialised for 1-D layers)
-    int stage_in;            // EXPERIMENTAL (conv_tc.cu STAGE mode, "tc_stage" option): cp.async-staged producer loads
+    int dbg;                 // PROFILING ONLY (env FCB_TC_DBG, conv_tc.cu): knock-out mask; results are wrong when != 0
 };
 
 // ---- FreqCodec 2-D path (conv2d_simt.cu): raw activations are channels-last [B][F_raw][T_raw][C]

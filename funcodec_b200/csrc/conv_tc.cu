@@ -55,11 +55,10 @@ struct TcSmemLayout {
     int a_stage;       // bytes per A stage (hi + lo)
     int b_stage;       // bytes per B stage (hi + lo)
     int na, nb;        // ring depths
-    int off_b, off_stg, off_bar, total;
-    int stg_group;     // STAGE mode: bytes of raw-input staging per producer group (depth x n_in x a_rows x 128)
+    int off_b, off_bar, total;
 };
 
-__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb, int stg_inputs = 0, int stg_depth = 2) {
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb) {
     TcSmemLayout L;
     const int qmax = (K - 1) / S;
     L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
@@ -67,9 +66,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     L.b_stage = 2 * n_tile * 128;
     L.na = na; L.nb = nb;
     L.off_b = na * L.a_stage;
-    L.off_stg = L.off_b + nb * L.b_stage;
-    L.stg_group = stg_depth * stg_inputs * L.a_rows * 128;
-    L.off_bar = L.off_stg + 2 * L.stg_group;
+    L.off_bar = L.off_b + nb * L.b_stage;
     L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
     return L;
 }
@@ -92,17 +89,16 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
     return t;
 }
 
-template <int N_TILE, bool FREQ, bool STAGE>
+template <int N_TILE, bool FREQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles, const int w_resident, const int group_mmas,
-                                                                 const int stg_depth) {
+                                                                 const int n_tiles, const int w_resident, const int group_mmas) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, STAGE ? (has1 ? 2 : 1) : 0, stg_depth);
+    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_units = n_chunks * S;
     const int upg = tc_units_per_group(K, S, group_mmas);
@@ -134,149 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (STAGE && warp < 16) {
-        // =========================================================== producers, STAGE mode (experimental, off by default)
-        // The raw rows of a unit are fetched with per-thread cp.async (16 B each, zero-filled when out of range) into a
-        // staging ring of the group, stg_depth - 1 units AHEAD of the unit being transformed, so the global-load latency
-        // of the next units overlaps the transform of this one (the plain mode holds the rows in registers and serialises
-        // the two; per SM that caps the bytes in flight at ~34 KB, i.e. ~2.4 TB/s at ~2 us of loaded latency -- what the
-        // wide layers measure).  Every thread reads back only its own copies (cp.async.wait_group): no extra barrier.
-        const int grp = warp >> 3;
-        const int ptid = tid & (TC_PROD - 1);
-        const int jchunk = ptid & 7, rsub = ptid >> 3;
-        const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
-        const int pitch = FREQ ? p.fq.cin : C_in;
-        const uint32_t stg_in = (uint32_t)L.a_rows * 128u;                       // bytes per (stage, input)
-        const uint32_t stg_stage = (has1 ? 2u : 1u) * stg_in;         // bytes per staging slot
-        uint8_t* stg = smem_raw + L.off_stg + (uint32_t)grp * (uint32_t)L.stg_group + (uint32_t)jchunk * 16u;
-        constexpr int NR = 5;
-        // (tile, unit) -> this thread's source rows; returns the in-range mask of its NR rows
-        auto issue = [&](int tile, int unit, int st) -> uint32_t {
-            const TcTile tl = tc_tile(tile, n_nt, n_tt);
-            const int t0 = tl.tt * TC_M;
-            int b = tl.b, f_out = 0;
-            if (FREQ) { b = tl.b / p.fq.F_out; f_out = tl.b - b * p.fq.F_out; }
-            const int chunk = unit / S, ph = unit - chunk * S;
-            int c = chunk * TC_KC + jchunk * 4;
-            bool c_ok = c < C_in;
-            const float* xu0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * pitch;
-            const float* xu1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * pitch : nullptr;
-            if (FREQ) {
-                const int kf = c / pitch;
-                c -= kf * pitch;
-                int f_src = f_out * p.fq.SF + kf - p.fq.pad_f;
-                if (p.pad_zero) c_ok = c_ok && f_src >= 0 && f_src < p.fq.F_in;
-                else f_src = reflect_index(f_src, p.fq.F_in);
-                if (!c_ok) f_src = 0;
-                xu0 += (long long)(p.fq.f_off0 + f_src) * p.fq.T_raw0 * pitch;
-                if (has1) xu1 += (long long)(p.fq.f_off1 + f_src) * p.fq.T_raw1 * pitch;
-            }
-            uint8_t* dst = stg + (uint32_t)st * stg_stage;
-            uint32_t mask = 0;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const int u = rsub + 32 * i;
-                if (u < L.a_rows) {
-                    const int gt = (t0 + u) * S + ph - p.pad_l;
-                    bool ok = c_ok && gt <= gt_max;
-                    int src = gt;
-                    if (p.pad_zero) ok = ok && gt >= 0 && gt < p.T_in;
-                    else { src = reflect_index(gt, p.T_ext); ok = ok && src < p.T_in && src >= 0; }
-                    const long long off = ok ? (long long)src * pitch + c : 0;      // !ok: any valid address, 0 bytes read
-                    cp_async16_zfill(dst + (uint32_t)u * 128u, (ok ? xu0 : p.in0.x) + off, ok ? 16u : 0u);
-                    if (has1) cp_async16_zfill(dst + stg_in + (uint32_t)u * 128u, (ok ? xu1 : p.in1.x) + off, ok ? 16u : 0u);
-                    mask |= (ok ? 1u : 0u) << i;
-                }
-            }
-            cp_async_commit();
-            return mask;
-        };
-        auto advance = [&](int& tile, int& unit) {
-            unit += 2;
-            while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
-        };
-        // transform cursor (tile, unit) and issue cursor (itile, iunit), the latter stg_depth - 1 units ahead; the in-range
-        // masks of the units in flight are packed 5 bits per staging slot
-        int tile = blockIdx.x, unit = grp;
-        while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
-        int itile = tile, iunit = unit;
-        int as = grp % na_stages;
-        uint32_t aphase = 0;
-        int st = 0, ist = 0;
-        uint32_t masks = 0;
-        for (int d = 0; d < stg_depth - 1; ++d) {                     // prologue: fill the pipeline
-            if (itile < n_tiles) {
-                masks = (masks & ~(31u << (5 * ist))) | (issue(itile, iunit, ist) << (5 * ist));
-                advance(itile, iunit);
-            } else {
-                cp_async_commit();
-            }
-            if (++ist == stg_depth) ist = 0;
-        }
-        while (tile < n_tiles) {
-            if (itile < n_tiles) {
-                masks = (masks & ~(31u << (5 * ist))) | (issue(itile, iunit, ist) << (5 * ist));
-                advance(itile, iunit);
-            } else {
-                cp_async_commit();                                // empty group: keeps the wait_group count uniform
-            }
-            if (++ist == stg_depth) ist = 0;
-            // all but the stg_depth - 1 most recent groups are complete: this thread's copies of the CURRENT unit have landed
-            if (stg_depth == 2) cp_async_wait_group<1>();
-            else if (stg_depth == 3) cp_async_wait_group<2>();
-            else cp_async_wait_group<3>();
-            const uint32_t m_cur = (masks >> (5 * st)) & 31u;
-            {
-                const TcTile tl = tc_tile(tile, n_nt, n_tt);
-                int b = tl.b;
-                if (FREQ) b = tl.b / p.fq.F_out;
-                const int chunk = unit / S;
-                int c = chunk * TC_KC + jchunk * 4;
-                const bool c_in = c < C_in;
-                if (FREQ) c -= (c / pitch) * pitch;
-                const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
-                const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
-                float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
-                if (c_in && cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
-                if (c_in && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
-                uint8_t* hi = smA + as * L.a_stage;
-                uint8_t* lo = hi + L.a_rows * 128;
-                const uint8_t* srcb = stg + (uint32_t)st * stg_stage;
-                mbar_wait_backoff(a_empty + as, aphase ^ 1, 64);
-#pragma unroll
-                for (int i = 0; i < NR; ++i) {
-                    const int u = rsub + 32 * i;
-                    if (u < L.a_rows) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if ((m_cur >> i) & 1u) {
-                            const float4 xv = *reinterpret_cast<const float4*>(srcb + (uint32_t)u * 128u);
-                            v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
-                            v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
-                            if (has1) {
-                                const float4 yv = *reinterpret_cast<const float4*>(srcb + stg_in + (uint32_t)u * 128u);
-                                v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
-                                v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
-                            }
-                            if (p.elu) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
-                        }
-                        float4 h, l;
-                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                        const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
-                        *reinterpret_cast<float4*>(hi + o) = h;
-                        *reinterpret_cast<float4*>(lo + o) = l;
-                    }
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(a_full + as);
-                as += 2;
-                if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
-            }
-            advance(tile, unit);
-            if (++st == stg_depth) st = 0;
-        }
-        cp_async_wait_group<0>();
-    } else if (warp < 16) {
+    if (warp < 16) {
         // =========================================================== producers: transformed A slabs
         const int grp = warp >> 3;                  // this group takes the units with (global unit index) % 2 == grp
         const int ptid = tid & (TC_PROD - 1);
@@ -339,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     okr[i] = ok;
                     xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xb[i] = xa[i];
-                    if (ok) {
+                    if (ok && !(p.dbg & 1)) {
                         const long long off = (long long)src * pitch + c;
                         xa[i] = __ldg(reinterpret_cast<const float4*>(xu0 + off));
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(xu1 + off));
@@ -351,7 +205,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     const int u = rsub + 32 * i;
                     if (u < L.a_rows) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (okr[i]) {
+                        if (p.dbg & 2) v = xa[i];
+                        else if (okr[i]) {
                             const float4 xv = xa[i];
                             v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
                             v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
@@ -362,6 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                             }
                             if (p.elu) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
                         }
+                        if (p.dbg & 4) continue;
                         float4 h, l;
                         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
                         split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
@@ -433,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                             }
                             const uint32_t b_hi0 = b_base + bs * L.b_stage;
                             const uint32_t b_lo0 = b_hi0 + N_TILE * 128;
+                            if (!(p.dbg & 32))
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
@@ -511,7 +368,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
                                 s += (o.x + o.y) + (o.z + o.w);
                                 ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
-                                if (!FREQ) {
+                                if (p.dbg & 8) {
+                                } else if (!FREQ) {
                                     *reinterpret_cast<float4*>(orow + c0 + j) = o;
                                 } else {
                                     // phase (pf, pt) of a transposed conv lands on row f_out*FR + pf, column t*TR + pt
@@ -536,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 tc_fence_before_sync();
                 mbar_arrive(acc_empty + buf);
             }
-            if (p.partials) {
+            if (p.partials && !(p.dbg & 16)) {
                 double ds = (double)s, dss = (double)ss;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -587,30 +445,28 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1, g_stage_depth = 0, g_stage_na = 0;
+static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1, g_dbg = 0;
 
-template <int N_TILE, bool FREQ, bool STAGE>
-static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident, int depth) {
-    auto kern = conv1d_tc_kernel<N_TILE, FREQ, STAGE>;
+template <int N_TILE, bool FREQ>
+static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
+    auto kern = conv1d_tc_kernel<N_TILE, FREQ>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas, depth);
+    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);
     return cudaGetLastError();
 }
 
 template <int N_TILE>
-static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident,
-                                   bool freq, bool stage, int depth) {
-    if (freq) return stage ? launch_tc_n<N_TILE, true, true>(p, st, na, nb, smem, n_tiles, resident, depth)
-                           : launch_tc_n<N_TILE, true, false>(p, st, na, nb, smem, n_tiles, resident, depth);
-    return stage ? launch_tc_n<N_TILE, false, true>(p, st, na, nb, smem, n_tiles, resident, depth)
-                 : launch_tc_n<N_TILE, false, false>(p, st, na, nb, smem, n_tiles, resident, depth);
+static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident, bool freq) {
+    return freq ? launch_tc_n<N_TILE, true>(p, st, na, nb, smem, n_tiles, resident)
+                : launch_tc_n<N_TILE, false>(p, st, na, nb, smem, n_tiles, resident);
 }
 
-cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
+cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* nparts) {
+    ConvParams p = p_in;
     if (g_num_sms == 0) {
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
@@ -622,41 +478,17 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
         if (const char* v = getenv("FCB_TC_NA")) g_force_na = atoi(v);
         if (const char* v = getenv("FCB_TC_NB")) g_force_nb = atoi(v);
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
-        if (const char* v = getenv("FCB_TC_STAGE_DEPTH")) g_stage_depth = atoi(v);
-        if (const char* v = getenv("FCB_TC_STAGE_NA")) g_stage_na = atoi(v);
+        if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
     }
+    p.dbg = g_dbg;
     // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
     // (A even: the two producer groups alternate slots).
     const int n_slabs = ((p.C_in + TC_KC - 1) / TC_KC) * p.K;
     const int limit = 225 * 1024;
     int resident = 0, na = 4, nb = 4;
-    bool stage = false;
     TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
-    int depth = 2;
-    if (p.stage_in) {
-        // EXPERIMENTAL cp.async staging of the raw input (see the STAGE producer branch): needs room for `depth` raw slots
-        // per producer group next to the A ring.  Preference: more bytes in flight first (deeper staging with a 2-stage A
-        // ring), FCB_TC_STAGE_DEPTH / FCB_TC_STAGE_NA pin a configuration for sweeps; weights resident if they fit, else a
-        // ring of >= 3 slabs.
-        const int n_in = p.in1.x ? 2 : 1;
-        static const int pref[][2] = {{2, 4}, {2, 3}, {4, 2}, {2, 2}};        // (na, depth)
-        for (int c = 0; c < 4 && !stage; ++c) {
-            const int try_na = pref[c][0], try_d = pref[c][1];
-            if (g_stage_depth > 0 && try_d != g_stage_depth) continue;
-            if (g_stage_na > 0 && try_na != g_stage_na) continue;
-            TcSmemLayout Ls = tc_layout(p.K, p.S, p.n_tile, try_na, n_slabs, n_in, try_d);
-            if (n_slabs <= 64 && p.C_out == p.n_tile && Ls.total <= limit) {
-                stage = true; resident = 1; na = try_na; nb = n_slabs; depth = try_d; L = Ls;
-                break;
-            }
-            for (int try_nb = 6; try_nb >= 3; --try_nb) {
-                Ls = tc_layout(p.K, p.S, p.n_tile, try_na, try_nb, n_in, try_d);
-                if (Ls.total <= limit) { stage = true; na = try_na; nb = try_nb; depth = try_d; L = Ls; break; }
-            }
-        }
-    }
-    if (!stage) {
+    {
         if (n_slabs <= 64 && p.C_out == p.n_tile && L.total <= limit) { resident = 1; nb = n_slabs; }   // one n-tile only
         else {
             L = tc_layout(p.K, p.S, p.n_tile, na, nb);
@@ -681,10 +513,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* npa
     const int n_tiles = n_tt * n_nt * B;
     const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
     switch (p.n_tile) {
-        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
-        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
-        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
-        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq, stage, depth);
+        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq);
+        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq);
+        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq);
+        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq);
         default: return cudaErrorInvalidConfiguration;
     }
 }

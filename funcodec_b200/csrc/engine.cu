@@ -38,7 +38,6 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl
     float* beta = nullptr;   // [cout]
     float* w_tc = nullptr;   // tensor-core image: [n_tile idx][chunk][tap][hi|lo][n_tile rows x 128 B swizzled]
     int n_tile = 0;          // 0: no tensor-core image (layer runs on the SIMT kernel)
-    float* w_tc64 = nullptr; // EXPERIMENTAL ("tc_m256"): the same image with n_tile = 64 for conv_tc_m256.cu (deep layers)
 };
 
 struct LstmW {
@@ -83,14 +82,11 @@ struct fcb_handle {
     unsigned* lstm_barrier = nullptr;
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
-    int tc_m256 = 0;             // EXPERIMENTAL: deep conv layers on conv_tc_m256.cu ("tc_m256" option, before fcb_finalize)
-    int lstm_prefetch_poll = 0;  // EXPERIMENTAL: see LstmSeqParams::prefetch_poll
-    int stft_tc = 0;             // EXPERIMENTAL: STFT / iSTFT as tensor-core GEMMs ("stft_tc" option)
+    int stft_tc = 1;             // STFT / iSTFT as tensor-core GEMMs ("stft_tc" option; 0: the direct-DFT kernels)
     ConvW stft_w, istft_w;       // their basis matrices as conv_tc weight images (finalize_freq)
     bool stft_packed = false;
     int stft_ld = 0, istft_ld = 0;   // padded column counts: STFT output (2*n_bins -> x128), iSTFT input (2*n_bins -> x32)
-    int conv2d_small_cout = 0;   // EXPERIMENTAL: halo-tile SIMT kernel for the C_out <= 4 2-D conv ("conv2d_small_cout" option)
-    int tc_stage = 0;        // EXPERIMENTAL: cp.async-staged producer loads in conv_tc.cu ("tc_stage" option, FCB_TC_STAGE=1)
+    int conv2d_small_cout = 1;   // halo-tile SIMT kernel for the C_out <= 4 2-D conv ("conv2d_small_cout" option; 0: padded n-tile)
     std::vector<void*> dev_allocs;
     std::map<std::string, const ConvW*> by_name;   // reference module prefix -> packed layer (debug hook)
 
@@ -204,10 +200,6 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
     build_tc_image(wp, K, cin, cout_eff, n_tile, &img);
     FCB_TRY(upload(h, img, &o->w_tc));
     o->n_tile = n_tile;
-    if (h->tc_m256 && n_tile == 128 && conv_tc_m256_supported(cin, cout_eff, K, 1, 1)) {
-        build_tc_image(wp, K, cin, cout_eff, 64, &img);
-        FCB_TRY(upload(h, img, &o->w_tc64));
-    }
     return FCB_OK;
 }
 
@@ -411,17 +403,14 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
     p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile;
-    p.stage_in = h->tc_stage;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
-    const bool m2 = tc && h->tc_m256 && L.w_tc64 && conv_tc_m256_supported(p.C_in, p.C_out, p.K, p.S, 1);   // EXPERIMENTAL
-    if (m2) { p.w_tc = L.w_tc64; p.n_tile = 64; }
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
     o.owned = true;
     p.out = o.p;
     double* partials = nullptr;
     const bool c1 = !tc && conv_cout1_supported(p);
-    const int nparts = m2 ? conv_tc_m256_num_parts(p.T_out, p.C_out) : tc ? conv_tc_num_parts(p.T_out, p.C_out)
+    const int nparts = tc ? conv_tc_num_parts(p.T_out, p.C_out)
                           : (c1 ? conv_cout1_num_parts(p.T_out) : conv_num_parts(p.T_out, p.C_out, p.C_in, p.K, r.B));
     if (want_norm) {
         FCB_TRY(pool_alloc(r, (void**)&partials, (size_t)r.B * nparts * 2 * sizeof(double)));
@@ -431,8 +420,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     }
     p.partials = partials;
     int np2 = 0;
-    if (m2) FCB_CK(launch_conv_tc_m256(p, r.B, r.st, &np2));
-    else if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
+    if (tc) FCB_CK(launch_conv_tc(p, r.B, r.st, &np2));
     else if (c1) FCB_CK(launch_conv_cout1(p, r.B, r.st, &np2));
     else FCB_CK(launch_conv(p, r.B, r.st, &np2));
     h->launches++;
@@ -473,7 +461,6 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
         sp.skip = view_of(x);
         sp.barrier = h->lstm_barrier;
         sp.B = B; sp.T = T; sp.H = H;
-        sp.prefetch_poll = h->lstm_prefetch_poll;
         FCB_CK(launch_lstm_seq(sp, r.st));
         h->launches += 1;
         FCB_TRY(release(r, gx));
@@ -778,7 +765,7 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
     o.owned = true;
     p.out = o.p;
     // tensor-core path (conv_tc.cu, 2-D mode) when the layer has a slab image and its class is enabled
-    // EXPERIMENTAL halo-tile kernel for C_out <= 4 (the 32 -> 3 output conv), "conv2d_small_cout" option
+    // halo-tile SIMT kernel for C_out <= 4 (the 32 -> 3 output conv), "conv2d_small_cout" option (default on)
     const bool small = h->conv2d_small_cout && !L.transposed && conv2d_small_cout_supported(p);
     const bool tc = !small && h->use_tc && L.n_tile > 0 && L.w_tc && (h->use_tc2d & L.tc_class) != 0;
     // statistics partials per clip: the pseudo-clip kernels emit n per output frequency row
@@ -805,7 +792,6 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
         q.out = o.p; q.T_out = p.T_out; q.C_out = L.cout_tc;
         q.out_clip_stride = (long long)p.T_out * L.cout_tc;
         q.partials = partials;
-        q.stage_in = h->tc_stage;
         q.fq.KF = p.KF; q.fq.SF = p.SF; q.fq.pad_f = p.pad_f; q.fq.F_in = in0.F; q.fq.F_out = p.F_out; q.fq.cin = in0.C;
         q.fq.T_raw0 = in0.T_raw; q.fq.f_off0 = in0.f_off;
         q.fq.T_raw1 = in1 ? in1->T_raw : 0; q.fq.f_off1 = in1 ? in1->f_off : 0;
@@ -868,7 +854,7 @@ int run_encoder_freq(Run& r, const float* wav, int L, float* scale_out, Act* out
     FCB_TRY(alloc_f(r, &a.p, (size_t)B * n_bins * Ts * cfe));
     a.owned = true; a.F_raw = a.F = n_bins; a.T_raw = a.T = Ts; a.C = cfe;
     if (h->stft_tc && !h->stft_packed) { h->stft_packed = true; FCB_TRY(pack_stft_bases(h)); }   // lazily: the default path never builds them
-    if (h->stft_tc && h->stft_w.n_tile > 0) {       // EXPERIMENTAL: rows of 32 samples -> DFT-basis GEMM -> mag_phase features
+    if (h->stft_tc && h->stft_w.n_tile > 0) {       // rows of 32 samples -> DFT-basis GEMM -> mag_phase features
         const int n_rows = (L + c.n_fft + 31) / 32;
         float *rows = nullptr, *spec = nullptr;
         FCB_TRY(alloc_f(r, &rows, (size_t)B * n_rows * 32));
@@ -959,7 +945,7 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
     float* frames = nullptr;
     FCB_TRY(alloc_f(r, &frames, (size_t)r.B * f.T * c.n_fft));
     if (h->stft_tc && !h->stft_packed) { h->stft_packed = true; FCB_TRY(pack_stft_bases(h)); }
-    if (h->stft_tc && h->istft_w.n_tile > 0) {      // EXPERIMENTAL: softplus(mag)*(re, im) rows -> inverse-DFT GEMM -> overlap-add
+    if (h->stft_tc && h->istft_w.n_tile > 0) {      // softplus(mag)*(re, im) rows -> inverse-DFT GEMM -> overlap-add
         float* Y = nullptr;
         FCB_TRY(alloc_f(r, &Y, (size_t)r.B * f.T * h->istft_ld));
         FCB_CK(launch_spec_rows(f.p, f.coef, r.B, f.F_raw, f.T_raw, n_bins, f.T, h->istft_ld, Y, r.st));
@@ -977,7 +963,7 @@ int run_decoder_freq(Run& r, const float* emb, int n_frames, const float* scale,
     return FCB_OK;
 }
 
-// EXPERIMENTAL ("stft_tc"): the windowed DFT / inverse-DFT bases as tensor-core conv weight images.
+// "stft_tc" (default): the windowed DFT / inverse-DFT bases as tensor-core conv weight images.
 //  STFT : rows of 32 samples are the channels-last input, X[m][co] = sum_{k, ci} x[(m*s + k)*32 + ci] * Wf[k][ci][co] with
 //         Wf = hann[n] cos(2 pi co n / N) for co < n_bins, -hann[n] sin(2 pi (co - n_bins) n / N) for the next n_bins columns;
 //  iSTFT: frames[m][j] = sum_ci Y[m][ci] * Wi[ci][j], Wi = c_k cos(2 pi k j / N) hann[j] / N (ci = k), -c_k sin(.) hann[j] / N
@@ -1043,7 +1029,6 @@ int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, fl
     p.T_in = T_in; p.C_in = L.cin; p.K = L.k; p.S = L.s; p.D = 1; p.pad_l = 0; p.T_ext = T_in; p.pad_zero = 1;
     p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.bias = L.bias;
     p.out = out; p.T_out = T_out; p.C_out = L.cout; p.out_clip_stride = (long long)T_out * L.cout;
-    p.stage_in = h->tc_stage;
     int np = 0;
     FCB_CK(launch_conv_tc(p, r.B, r.st, &np));
     h->launches++;
@@ -1166,11 +1151,8 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     if (!h) return FCB_E_NOMEM;
     h->cfg = *cfg;
     { const char* e = getenv("FCB_DISABLE_TC"); if (e && e[0] == '1') h->use_tc = false; }
-    { const char* e = getenv("FCB_TC_STAGE"); if (e && e[0] == '1') h->tc_stage = 1; }
-    { const char* e = getenv("FCB_CONV2D_SMALL_COUT"); if (e && e[0] == '1') h->conv2d_small_cout = 1; }
-    { const char* e = getenv("FCB_STFT_TC"); if (e && e[0] == '1') h->stft_tc = 1; }
-    { const char* e = getenv("FCB_TC_M256"); if (e && e[0] == '1') h->tc_m256 = 1; }
-    { const char* e = getenv("FCB_LSTM_PREFETCH_POLL"); if (e && e[0] == '1') h->lstm_prefetch_poll = 1; }
+    { const char* e = getenv("FCB_CONV2D_SMALL_COUT"); if (e && (e[0] == '0' || e[0] == '1')) h->conv2d_small_cout = e[0] - '0'; }
+    { const char* e = getenv("FCB_STFT_TC"); if (e && (e[0] == '0' || e[0] == '1')) h->stft_tc = e[0] - '0'; }
     { const char* e = getenv("FCB_USE_TC2D"); if (e && e[0] >= '0' && e[0] <= '7' && !e[1]) h->use_tc2d = e[0] - '0'; }
     if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return FCB_E_CUDA; }
     // keep freed temporaries cached in the stream-ordered pool (no give-back between calls)
@@ -1556,6 +1538,19 @@ int fcb_roundtrip_host(fcb_handle* h, const float* wav_host, int32_t B, int32_t 
     return rc;
 }
 
+int fcb_check_errors(fcb_handle* h, void* stream) {
+    FCB_TRY(check_ready(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    int flag = 0;
+    FCB_CK(cudaMemcpyAsync(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FCB_CK(cudaStreamSynchronize(st));
+    if (flag) {
+        FCB_CK(cudaMemsetAsync(h->err_flag, 0, sizeof(int), st));
+        return fail(h, FCB_E_INVALID, "token index out of range [0, codebook_size) in fcb_decode_codes (the reference's F.embedding raises here)");
+    }
+    return FCB_OK;
+}
+
 int64_t fcb_launch_count(const fcb_handle* h) { return h ? h->launches : -1; }
 
 int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
@@ -1565,25 +1560,12 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
         h->use_tc = value != 0;
         return FCB_OK;
     }
-    if (strcmp(key, "tc_m256") == 0) {             // EXPERIMENTAL, not validated on hardware yet
-        if (h->finalized && value && !h->tc_m256) return fail(h, FCB_E_STATE, "tc_m256 can only be enabled before fcb_finalize");
-        h->tc_m256 = value != 0;
-        return FCB_OK;
-    }
-    if (strcmp(key, "lstm_prefetch_poll") == 0) {  // EXPERIMENTAL, not validated on hardware yet
-        h->lstm_prefetch_poll = value != 0;
-        return FCB_OK;
-    }
-    if (strcmp(key, "stft_tc") == 0) {             // EXPERIMENTAL, not validated on hardware yet
+    if (strcmp(key, "stft_tc") == 0) {             // STFT / iSTFT as tensor-core GEMMs (default) vs the direct-DFT kernels
         h->stft_tc = value != 0;
         return FCB_OK;
     }
-    if (strcmp(key, "conv2d_small_cout") == 0) {   // EXPERIMENTAL, not validated on hardware yet
+    if (strcmp(key, "conv2d_small_cout") == 0) {   // halo-tile SIMT kernel (default) vs the padded tensor-core n-tile
         h->conv2d_small_cout = value != 0;
-        return FCB_OK;
-    }
-    if (strcmp(key, "tc_stage") == 0) {     // EXPERIMENTAL, not validated on hardware yet: cp.async-staged conv producers
-        h->tc_stage = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "use_tc2d") == 0) {     // bit mask of 2-D layer classes on the tensor-core path (see Conv2W::tc_class)

@@ -29,15 +29,10 @@ int conv_tc_n_tile(int C_out_eff);
 int conv_tc_num_parts(int T_out, int C_out_eff);
 cudaError_t launch_conv_tc(const ConvParams& p, int B, cudaStream_t st, int* nparts);
 
-// conv_tc_m256.cu: EXPERIMENTAL deep-layer variant (M = 256 rows per CTA, N = 64; every weight slab feeds both halves)
-bool conv_tc_m256_supported(int C_in, int C_out_eff, int K, int S, int D);
-int conv_tc_m256_num_parts(int T_out, int C_out_eff);
-cudaError_t launch_conv_tc_m256(const ConvParams& p, int B, cudaStream_t st, int* nparts);
-
 // conv2d_simt.cu (FreqCodec 2-D path)
 int conv2d_num_parts(const Conv2dParams& p);
 cudaError_t launch_conv2d(const Conv2dParams& p, cudaStream_t st);
-bool conv2d_small_cout_supported(const Conv2dParams& p);          // EXPERIMENTAL: C_out <= 4 stride-1 conv (halo tile, FMA-bound)
+bool conv2d_small_cout_supported(const Conv2dParams& p);          // C_out <= 4 stride-1 conv (halo tile, FMA-bound)
 int conv2d_small_cout_num_parts(const Conv2dParams& p);
 cudaError_t launch_conv2d_small_cout(const Conv2dParams& p, cudaStream_t st);
 cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, int L, int n_fft, int hop, int n_frames,
@@ -45,7 +40,7 @@ cudaError_t launch_stft_magphase(const float* wav, const float* scale, int B, in
 cudaError_t launch_istft(const float* raw, const float* coef, int B, int F_raw, int T_raw, int n_fft, int hop, int n_frames,
                          const float* scale, float* frames, float* out, int out_len, cudaStream_t st);
 
-// EXPERIMENTAL STFT / iSTFT as tensor-core GEMMs ("stft_tc" option): the glue kernels around two conv_tc launches
+// STFT / iSTFT as tensor-core GEMMs ("stft_tc" option, default on): the glue kernels around two conv_tc launches
 cudaError_t launch_wave_rows(const float* wav, const float* scale, int B, int L, int n_fft, int n_rows, float* rows, cudaStream_t st);
 cudaError_t launch_magphase_from_spec(const float* spec, int ld, int B, int n_bins, int n_frames, int cpad, float* feats,
                                       cudaStream_t st);
@@ -63,7 +58,6 @@ struct LstmSeqParams {
     InView skip;          // the SLSTM input (normalised on load) when y_out != nullptr
     unsigned* barrier;    // device counter for the per-step grid barrier (zeroed by the launcher)
     int B, T, H;
-    int prefetch_poll;    // EXPERIMENTAL ("lstm_prefetch_poll" option): software-pipelined barrier polling in the loader warp
 };
 cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st);
 int lstm_pick_units(int H);

@@ -218,29 +218,19 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     } else {
         // ================================================================ loader warp
         if (lane == 0) {
-            // EXPERIMENTAL (p.prefetch_poll, off by default): the counter of the NEXT item's group is read right after this
-            // item's copies are issued, so its L2 round trip overlaps the wait for a free ring slot
-            unsigned pre = 0;
-            bool have_pre = false;
             for (int i = ng; i < n_items; ++i) {
                 const int t = i / ng, g = i - t * ng;
                 const int n = i - ng, hb = n % LSTM_NBUF;
                 const int b0 = g * GB;
                 const int nb = min(GB, B - b0);
                 tc::mbar_wait_backoff(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1, 64);
-                unsigned seen = have_pre ? pre : ld_acquire_u32(p.barrier + g);
+                unsigned seen = ld_acquire_u32(p.barrier + g);
                 while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
                 float* dst = Hs + hb * GB * H;
                 for (int bb = 0; bb < nb; ++bb)
                     tc::bulk_g2s(dst + bb * H, p.h_seq + ((long long)(b0 + bb) * T + (t - 1)) * H, (uint32_t)(H * 4), hs_full + hb);
-                have_pre = false;
-                if (p.prefetch_poll && i + 1 < n_items) {
-                    const int t1 = (i + 1) / ng;
-                    pre = ld_acquire_u32(p.barrier + ((i + 1) - t1 * ng));
-                    have_pre = true;
-                }
             }
         }
     }

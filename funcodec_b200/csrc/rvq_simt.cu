@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256, 2) rvq_kernel(const RvqParams p) {
                 const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
                 if (ov < v || (ov == v && oi < ix)) { v = ov; ix = oi; }
             }
-            if (lane == 0) best[warp * 4 + i] = ix;
+            // a row whose distances are all NaN never replaces the sentinel: the reference's max() returns index 0 there
+            if (lane == 0) best[warp * 4 + i] = (ix < 0 || ix >= K) ? 0 : ix;
         }
         __syncthreads();
         // ---- dequantize + residual update (ddp_core_vq.py:407-408)

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const float xx = xx_s[myrow];
             float v1 = 3.402823466e38f, v2 = 3.402823466e38f;
-            int i1 = 0x7fffffff, i2 = 0x7fffffff;
+            int i1 = 0, i2 = -1;       // a NaN row replaces nothing: index 0, like the reference's max() over NaNs; no OOB gather
             for (int nt = 0; nt < n_nt; ++nt, ++tcount) {
                 const int buf = (int)(tcount & 1);
                 mbar_wait_backoff(acc_full + buf, (uint32_t)((tcount >> 1) & 1), 64);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rvq_tc_kernel(const RvqParams p
             }
             // ---- exact fp32 re-scoring of near-ties (sequential fmaf chain == rvq_simt.cu)
             int best = i1;
-            if (row0 + myrow < M && v2 - v1 < RQ_RESCORE_TOL + 2e-5f * fabsf(v1) && i2 < K) {
+            if (row0 + myrow < M && v2 - v1 < RQ_RESCORE_TOL + 2e-5f * fabsf(v1) && i2 >= 0) {
                 float d1 = 0.f, d2 = 0.f;
                 const float* c1 = E + (long long)i1 * D;
                 const float* c2 = E + (long long)i2 * D;

@@ -276,6 +276,9 @@ class B200Encodec:
         with torch.cuda.device(self.device):
             self._ck(self._lib.fcb_decode_codes(self._h, _ptr(tok), B, Tf, n_q, _ptr(emb), _ptr(recon), Lo,
                                                 self._stream()), "fcb_decode_codes")
+            # out-of-range tokens: F.embedding raises in the reference (ddp_core_vq.py:190-192); here the device flags them
+            if self._lib.fcb_check_errors(self._h, self._stream()) < 0:
+                raise IndexError(self._lib.fcb_last_error(self._h).decode())
         return dict(recon_speech=recon if need_recon else None, code_indices=None,
                     code_embeddings=[(emb, None)], sub_quants=None)
 

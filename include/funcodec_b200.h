@@ -124,6 +124,13 @@ FCB_API int fcb_decode_emb(fcb_handle* h, const float* emb, int32_t B, int32_t n
 FCB_API int fcb_decode_codes(fcb_handle* h, const int64_t* codes, int32_t B, int32_t n_frames, int32_t n_q,
                      float* emb_out, float* wav_out, int32_t out_len, void* stream);
 
+/* Deferred data errors.  fcb_decode_codes validates token ids ON THE DEVICE (a token < 0 or >= codebook_size is skipped and
+ * raises a sticky flag) so that the call stays asynchronous; the reference's F.embedding raises for such a token
+ * (ddp_core_vq.py:190-192, e.g. the -1 quantize-dropout indices or a codecs.txt of a larger codebook).  fcb_check_errors
+ * synchronises `stream`, reads and clears the flag and returns FCB_E_INVALID (with fcb_last_error text) when any call since the
+ * previous check saw an out-of-range token.  B200Encodec.inference_decoding calls it and raises IndexError. */
+FCB_API int fcb_check_errors(fcb_handle* h, void* stream);
+
 /* Encodec.inference (codec_basic.py:670-718) with need_recon=True in one call: fcb_encode followed by
  * decode of the quantized embeddings, recon dev [B, L].  use_scale as in the reference. */
 FCB_API int fcb_roundtrip(fcb_handle* h, const float* wav, int32_t B, int32_t L, int32_t n_q, int32_t use_scale,
@@ -182,16 +189,11 @@ FCB_API int fcb_get_phase_ms(fcb_handle* h, float* ms_out /* [FCB_NUM_PHASES] */
 /* "use_tc2d" (FreqCodec, arch 1): bit mask of the 2-D layer classes that run on the tensor-core path -- 1: C_in % 32 == 0,
  * 2: C_in < 32 (several frequency taps per 32-channel chunk), 4: C_out padded to 16 (the 32 -> 3 output conv); default 7,
  * 0 = every 2-D conv on the fp32 SIMT kernel.  May be changed at any time; env FCB_USE_TC2D=<mask> sets the default. */
-/* "tc_m256" 1/0 (default 0; before fcb_finalize; env FCB_TC_M256=1): EXPERIMENTAL deep-layer conv kernel (C_in >= 256): 256 time rows
- * per CTA share every weight slab (conv_tc_m256.cu).
- * "lstm_prefetch_poll" 1/0 (default 0): EXPERIMENTAL software-pipelined barrier polling in the LSTM kernel's loader warp.
- * "stft_tc" 1/0 (default 0): EXPERIMENTAL STFT / iSTFT of the FreqCodec front / back end as two tensor-core GEMMs (windowed DFT
- * bases as conv weight images) instead of the direct-DFT kernels; needs n_fft and hop to be multiples of 32.
- * "conv2d_small_cout" 1/0 (default 0): EXPERIMENTAL halo-tile SIMT kernel for 2-D convs with C_out <= 4 (FreqCodec's 32 -> 3
- * output conv) instead of the padded tensor-core n-tile; written for round 2, not yet validated on hardware.
- * "tc_stage" 1/0 (default 0; env FCB_TC_STAGE=1): EXPERIMENTAL producer mode of the tensor-core conv kernel that stages the
- * raw input rows one unit ahead with cp.async; written for round 2, not yet validated on hardware, tests opt in with
- * FCB_EXPERIMENTAL=1. */
+/* "stft_tc" 1/0 (default 1; env FCB_STFT_TC): STFT / iSTFT of the FreqCodec front / back end as two tensor-core GEMMs (windowed
+ * DFT bases as conv weight images; needs n_fft and hop to be multiples of 32) instead of the direct-DFT kernels.
+ * "conv2d_small_cout" 1/0 (default 1; env FCB_CONV2D_SMALL_COUT): halo-tile SIMT kernel for 2-D convs with C_out <= 4 (FreqCodec's
+ * 32 -> 3 output conv) instead of the padded tensor-core n-tile.  Both were validated and A/B-timed on a B200 in round 2
+ * (profiles/ab_bringup_r2a.txt). */
 FCB_API int fcb_set_option(fcb_handle* h, const char* key, int32_t value);
 
 /* TEST HOOK (tests/test_gpu_layers.py): run ONE packed conv layer, addressed by its reference module prefix

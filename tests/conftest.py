@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the parity records the tests collected (parity_utils.RECORDS): measured exact-match rates, margins, errors."""
+    try:
+        import parity_utils
+        parity_utils.dump_records(os.path.join(ROOT, "gpurun_out", "parity_records.json"))
+    except Exception:
+        pass

@@ -5,7 +5,34 @@ fp32 ulp of the distance -- so a mismatch is accepted only when the ORACLE's own
 first diverging stage of that frame is below `margin_tol`; later stages of the frame are excluded
 (the residual differs after a flip).
 """
+import json
+import os
+
 import numpy as np
+
+# Every comparison a test makes is also RECORDED (tests/conftest.py dumps the list at session end to
+# gpurun_out/parity_records.json; the committed copy of the last B200 run is profiles/parity_r2.json).
+RECORDS = []
+
+
+def record_parity(what, **fields):
+    """Append one measured parity record (plain numbers only) -- frames / exact / near-tie counts, worst accepted margin,
+    waveform max-abs error ... -- so that the bars asserted in the tests can be compared with what was measured."""
+    rec = dict(what=str(what))
+    for k, v in fields.items():
+        if isinstance(v, (np.floating, np.integer)):
+            v = v.item()
+        rec[k] = v
+    RECORDS.append(rec)
+    return rec
+
+
+def dump_records(path):
+    if not RECORDS:
+        return
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(RECORDS, f, indent=1)
 
 
 def classify_codes(codes_test, codes_ref, margins_ref, margin_tol):
@@ -33,8 +60,16 @@ def classify_codes(codes_test, codes_ref, margins_ref, margin_tol):
                 exact_rate=exact / total, first_stage=first)
 
 
-def assert_codes_parity(codes_test, codes_ref, margins_ref, margin_tol, min_exact_rate=0.97, what=""):
+def assert_codes_parity(codes_test, codes_ref, margins_ref, margin_tol, min_exact_rate=0.97, what="", **extra):
     r = classify_codes(codes_test, codes_ref, margins_ref, margin_tol)
+    n_q = int(np.asarray(codes_ref).shape[0])
+    first = r["first_stage"]
+    # stage-level exact count: every (stage, frame) before a frame's first divergence matches by construction
+    stages_exact = int(np.where(first >= 0, first, n_q).sum())
+    record_parity(what, kind="codes", frames=r["total_frames"], exact_frames=r["exact_frames"], exact_rate=r["exact_rate"],
+                  near_tie_frames=r["near_tie_frames"], bad_frames=r["bad_frames"], worst_accepted_margin=r["worst_margin"],
+                  margin_tol=margin_tol, min_exact_rate_asserted=min_exact_rate, n_q=n_q,
+                  code_stage_exact_rate=stages_exact / max(1, n_q * r["total_frames"]), **extra)
     assert r["bad_frames"] == 0, f"{what}: {r['bad_frames']} frames differ with oracle margin > {margin_tol} " \
                                   f"(worst {r['worst_margin']:.3e}); exact {r['exact_frames']}/{r['total_frames']}"
     assert r["exact_rate"] >= min_exact_rate, f"{what}: exact-match rate {r['exact_rate']:.4f} < {min_exact_rate}"

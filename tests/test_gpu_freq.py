@@ -227,3 +227,90 @@ def test_conv2d_layer(layer, cin, F, T, elu, tc2d):
 def test_conv2d_layer_small_channels(golden_dir, layer, cin, F, T, elu, tc2d):
     z, cfg, sd, model, _ = _small(golden_dir)
     _check_conv2d_layer(model, sd, layer, cin, F, T, elu, tc2d)
+
+
+# ---------------------------------------------------------------------------------------------- alternative kernel paths
+def test_output_conv_padded_tile_path(golden_dir):
+    """`conv2d_small_cout` = 0: the 32 -> 3 output conv on the padded tensor-core n-tile (class 4) instead of the default
+    halo-tile SIMT kernel -- both stay covered."""
+    cfg, sd, model, oracle = _full()
+    model.set_option("conv2d_small_cout", 0)
+    try:
+        for layer, cin, F, T, elu in [("decoder.model.16", 32, 40, 150, True), ("decoder.model.16", 32, 257, 11, True),
+                                      ("decoder.model.16", 32, 9, 333, False)]:
+            _check_conv2d_layer(model, sd, layer, cin, F, T, elu, 7)
+    finally:
+        model.set_option("conv2d_small_cout", 1)
+
+
+@pytest.mark.parametrize("stft_tc", [1, 0])
+def test_stft_paths(golden_dir, stft_tc):
+    """STFT / iSTFT as tensor-core GEMMs (default) and as the direct-DFT kernels (`stft_tc` = 0) against the oracle
+    (torch.stft / istft): config-4 architecture and the small golden model, encoder output and decode-only waveform."""
+    from parity_utils import record_parity
+    for getter in (_full, lambda: _small(golden_dir)[1:]):
+        cfg, sd, model, oracle = getter()
+        model.set_option("stft_tc", stft_tc)
+        try:
+            g = torch.Generator().manual_seed(9)
+            wav = 0.1 * torch.randn(2, 160 * 33 + 17, generator=g)
+            ora = oracle.inference(wav, want_margin=True)
+            r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
+            err = (r["encoder_out"].cpu() - ora["encoder_out"]).abs().max().item()
+            quant = ora["code_embeddings"][0][0]
+            d = model.inference_decoding_emb(quant)
+            dref = oracle.decode_frame(quant, None)
+            derr = (d["recon_speech"].cpu() - dref).abs().max().item()
+            record_parity(f"stft_tc={stft_tc} {cfg.name}", kind="stft", encoder_out_max_abs=err, decode_only_max_abs_unscaled=derr)
+            assert err <= EMB_TOL
+            assert derr <= WAV_TOL * 10                  # un-scaled output (~10x amplitude)
+        finally:
+            model.set_option("stft_tc", 1)
+
+
+def _golden_model_check(golden_dir, fname, what, min_exact_rate=0.9):
+    from funcodec_b200.encodec import B200Encodec
+    from parity_utils import record_parity
+    z = np.load(os.path.join(golden_dir, fname))
+    cfg = get_config(str(z["cfg_name"]))
+    sd = init_state_dict(cfg, int(z["seed"]))
+    model = B200Encodec(cfg, sd, "cuda:0")
+    wav = torch.from_numpy(z["wav"])
+    oracle = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)))
+    ora = oracle.inference(wav, want_margin=True)
+    r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
+    enc_err = np.abs(r["encoder_out"].cpu().numpy() - z["encoder_out"]).max()
+    assert enc_err <= EMB_TOL, enc_err
+    res = assert_codes_parity(r["code_indices"][0].cpu().numpy(), z["codes"], ora["margins"].numpy(), MARGIN,
+                              min_exact_rate=min_exact_rate, what=what, encoder_out_max_abs=float(enc_err))
+    assert tuple(r["recon_speech"].shape) == tuple(z["recon"].shape)
+    ok_clip = ~(res["first_stage"] >= 0).any(axis=1)
+    recon = r["recon_speech"].cpu().numpy()
+    werr = 0.0
+    for b in np.nonzero(ok_clip)[0]:
+        werr = max(werr, float(np.abs(recon[b] - z["recon"][b]).max()))
+    # decode-only (no flips involved): the reference's own quantized embeddings through the decoder
+    d = model.inference_decoding_emb(torch.from_numpy(z["quant"]))
+    dref = oracle.decode_frame(torch.from_numpy(z["quant"]), None)
+    derr = (d["recon_speech"].cpu() - dref).abs().max().item()
+    record_parity(what, kind="waveform", clips_without_flips=int(ok_clip.sum()), clips=int(ok_clip.size), recon_max_abs=werr,
+                  decode_only_max_abs_unscaled=derr)
+    assert werr <= WAV_TOL, werr
+    assert derr <= WAV_TOL * 10
+    return model, cfg
+
+
+def test_grouped_freq_model(golden_dir):
+    """conv_group_ratio / tr_conv_group_ratio > 0 on the small model against vectors of the unmodified grouped reference."""
+    _golden_model_check(golden_dir, "freq_magphase_small_grouped.npz", "freq grouped small golden")
+
+
+def test_config4_gr8_arch_golden(golden_dir):
+    """BASELINE config 4 AS NAMED (gr8: conv_group_ratio = tr_conv_group_ratio = 8, full widths) against vectors of the
+    unmodified grouped reference FreqCodec (tools/gen_golden_freq_gr8.py)."""
+    _golden_model_check(golden_dir, "freq_magphase_config4_gr8_arch.npz", "config-4 gr8 golden")
+
+
+def test_freq_ds640_ratio_set(golden_dir):
+    """conf/freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml's ratio set (time strides 2, 1, 2, 1) against the reference."""
+    _golden_model_check(golden_dir, "freq_magphase_small_ds640.npz", "freq ds640 ratio set golden")

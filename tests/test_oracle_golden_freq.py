@@ -141,3 +141,23 @@ def test_freqcodec_ds640_ratios_oracle_vs_reference(golden_dir):
     assert r["recon_speech"].shape == z["recon"].shape
     assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 5e-6
     assert min(wav.shape[-1], cfg.decoded_length(cfg.frames(wav.shape[-1]))) == z["recon"].shape[-1]
+
+
+def test_freqcodec_config4_gr8_architecture_oracle_vs_reference(golden_dir):
+    """BASELINE config 4 AS NAMED ("gr8": conv_group_ratio = tr_conv_group_ratio = 8 at the full widths): the oracle against
+    the unmodified grouped reference FreqCodec (tools/gen_golden_freq_gr8.py); weights = init_state_dict(cfg, 0)."""
+    from funcodec_b200 import get_config, init_state_dict
+    z = np.load(os.path.join(golden_dir, "freq_magphase_config4_gr8_arch.npz"))
+    cfg = get_config(str(z["cfg_name"]))
+    assert cfg.conv_group_ratio == 8 and cfg.tr_conv_group_ratio == 8
+    sd = init_state_dict(cfg, int(z["seed"]))
+    assert abs(float(sum(v.double().abs().sum().item() for v in sd.values())) - float(z["sd_checksum"])) <= 1e-6 * float(z["sd_checksum"])
+    # e.g. the 256-wide resblock: groups = 128 // 2 // 8 = 8 -> 16 input channels per group
+    assert sd["encoder.model.10.block.1.conv.conv.weight"].shape[1] == 256 // cfg.conv_groups(128)
+    o = OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)))
+    r = o.inference(torch.from_numpy(z["wav"]), want_margin=True)
+    assert np.abs(r["encoder_out"].numpy() - z["encoder_out"]).max() <= 1e-5
+    assert np.array_equal(r["code_indices"][0].numpy(), z["codes"].astype(np.int64))
+    assert np.abs(r["code_embeddings"][0][0].numpy() - z["quant"]).max() <= 1e-5
+    assert r["recon_speech"].shape == z["recon"].shape
+    assert np.abs(r["recon_speech"].numpy() - z["recon"]).max() <= 1e-5
