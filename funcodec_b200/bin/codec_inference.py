@@ -1,15 +1,20 @@
-"""CLI with the flag names of `python -m funcodec.bin.codec_inference` that `egs/LibriTTS/codec/encoding_decoding.sh`
-passes (funcodec/bin/codec_inference.py:428-558), backed by the CUDA library.
+"""Drop-in for `python -m funcodec.bin.codec_inference` (funcodec/bin/codec_inference.py:428-575) backed by the CUDA library:
+the same flag set, so the command lines of `egs/LibriTTS/codec/encoding_decoding.sh:80-98,124-143,168-187` (stages 1-3) run
+unchanged with the module path swapped:
 
-    python -m funcodec_b200.bin.codec_inference --run_mod encode --config_file config.yaml --model_file model.pth \
-        --data_path_and_name_and_type wav.scp,speech,sound --output_dir out --batch_size 16 --bit_width 8000
-    python -m funcodec_b200.bin.codec_inference --run_mod decode --data_path_and_name_and_type out/codecs.txt,speech,codec_json ...
+    python -m funcodec_b200.bin.codec_inference --batch_size 16 --num_workers 4 --ngpu 1 --gpuid_list 0,1 \
+        --data_path_and_name_and_type wav.scp,speech,sound --key_file logdir/keys.1.scp \
+        --config_file exp/model/config.yaml --model_file exp/model/model.pth --output_dir logdir/output.1 \
+        --sampling_rate 16000 --file_sampling_rate 16000 --bit_width 16000 --need_indices true --need_sub_quants false \
+        --use_scale false --indices_save_type text --run_mod encode
 
-`config.yaml` is the training config the reference saves (encoder_conf / quantizer_conf / decoder_conf / model_conf);
-`model.pth` is the plain state_dict.  Only the configurations listed in DESIGN.md §9 are accepted.
+`config.yaml` is the training config the reference saves (encoder_conf / quantizer_conf / decoder_conf / model_conf, time-domain
+Encodec or mag_phase FreqCodec); `model.pth` is the plain state_dict.  Unsupported configurations are refused loudly (no fallback
+to a PyTorch path).  Defaults equal the reference parser's (`--use_scale true`, `--bit_width 16000`, `--batch_size 1`).
 """
 import argparse
 import math
+import os
 import sys
 
 import torch
@@ -17,51 +22,173 @@ import yaml
 
 from funcodec_b200.config import CodecConfig
 from funcodec_b200.encodec import B200Encodec
-from funcodec_b200.pipeline import run_decode, run_encode
+from funcodec_b200.pipeline import run_decode, run_decode_emb, run_encode
 from funcodec_b200.speech2token import Speech2Token
 
 
-def config_from_yaml(path: str) -> CodecConfig:
+def str2bool(v: str) -> bool:
+    """funcodec.utils.types.str2bool."""
+    if v.lower() in ("true", "1", "yes", "y", "t"):
+        return True
+    if v.lower() in ("false", "0", "no", "n", "f"):
+        return False
+    raise argparse.ArgumentTypeError(f"not a boolean: {v}")
+
+
+def str_or_none(v: str):
+    return None if v.lower() in ("none", "null", "nil", "") else v
+
+
+def str2triple_str(v: str):
+    parts = [x.strip() for x in v.strip().strip("()[]").split(",")]
+    if len(parts) != 3:
+        raise argparse.ArgumentTypeError(f"expected path,name,type: {v}")
+    return tuple(parts)
+
+
+def config_from_yaml(path: str):
+    """-> (CodecConfig, segment_dur, overlap_ratio) from the reference's training YAML
+    (egs/LibriTTS/codec/conf/*.yaml; gan_speech_codec.py:301-358 feeds these dicts to the model classes)."""
     with open(path, "rt", encoding="utf-8") as f:
         a = yaml.safe_load(f)
     enc, dec, q, m = a.get("encoder_conf", {}), a.get("decoder_conf", {}), a.get("quantizer_conf", {}), a.get("model_conf", {})
-    if enc.get("norm") != "time_group_norm" or enc.get("causal", False) or m.get("segment_dur") is not None:
-        raise SystemExit("unsupported configuration (needs norm: time_group_norm, causal: false, segment_dur: null)")
-    ratios = tuple(dec.get("ratios", [8, 5, 4, 2]))
-    if tuple(enc.get("ratios", [8, 5, 4, 2])) != ratios:
-        raise SystemExit("encoder and decoder ratios differ")
-    if int(q.get("encoder_hop_length", 320)) != math.prod(ratios):
-        raise SystemExit("quantizer_conf.encoder_hop_length != prod(ratios)")
-    return CodecConfig(name="from_yaml", ratios=ratios, n_filters=int(enc.get("n_filters", 32)),
-                       dimension=int(m.get("odim", 128)), codebook_size=int(q.get("codebook_size", 1024)),
-                       num_quantizers=int(q.get("num_quantizers", 32)), sample_rate=int(q.get("sampling_rate", 16000)),
-                       audio_normalize=bool(m.get("audio_normalize", True)),
-                       lstm_layers=int(enc.get("seq_layer_num", 2)))
+
+    def refuse(msg):
+        raise SystemExit(f"unsupported configuration: {msg}")
+
+    for side, conf in (("encoder_conf", enc), ("decoder_conf", dec)):
+        if conf.get("norm", "none") != "time_group_norm":
+            refuse(f"{side}.norm must be time_group_norm")
+        if conf.get("causal", False):
+            refuse(f"{side}.causal must be false")
+        if conf.get("dilation_base", 2) != 1 and conf.get("n_residual_layers", 1) > 1:
+            refuse(f"{side}: stacked dilated residual layers are not supported")
+        if conf.get("n_residual_layers", 1) != 1:
+            refuse(f"{side}.n_residual_layers must be 1")
+        if conf.get("seq_model", "lstm") not in ("lstm",):
+            refuse(f"{side}.seq_model must be lstm")
+        if conf.get("activation", "ELU") != "ELU" or conf.get("pad_mode", "reflect") != "reflect":
+            refuse(f"{side}: activation must be ELU and pad_mode reflect")
+    if q.get("codec_dim") is not None or q.get("codec_range") is not None:
+        refuse("quantizer projections / codec_range")
+    if int(q.get("q0_ds_ratio", 1) or 1) != 1:
+        refuse("quantizer_conf.q0_ds_ratio must be 1")
+    ratios = dec.get("ratios", [8, 5, 4, 2])
+    if enc.get("ratios", [8, 5, 4, 2]) != ratios:
+        refuse("encoder and decoder ratios differ")
+    domain = m.get("codec_domain", None)
+    kw = {}
+    if a.get("model", "encodec") == "freq_codec" or (ratios and isinstance(ratios[0], (list, tuple))):
+        if list(domain or []) != ["mag_phase", "mag_phase"]:
+            refuse("FreqCodec codec_domain must be ['mag_phase', 'mag_phase']")
+        dconf = m.get("domain_conf", {}) or {}
+        kw = dict(arch=1, ratios_f=tuple(int(r[0]) for r in ratios), n_fft=int(dconf.get("n_fft", 512)),
+                  stft_hop=int(dconf.get("hop_length", 160)), conv_group_ratio=int(enc.get("conv_group_ratio", -1)),
+                  tr_conv_group_ratio=int(dec.get("tr_conv_group_ratio", -1)))
+        if int(dec.get("conv_group_ratio", enc.get("conv_group_ratio", -1))) != kw["conv_group_ratio"]:
+            refuse("encoder / decoder conv_group_ratio differ")
+        ratios = [int(r[1]) for r in ratios]
+        if m.get("segment_dur") is not None:
+            refuse("segment_dur must be null for FreqCodec")
+    elif domain not in (None, "time", ["time", "time"]):
+        refuse(f"codec_domain {domain}")
+    cfg = CodecConfig(name="from_yaml", ratios=tuple(int(r) for r in ratios), n_filters=int(enc.get("n_filters", 32)),
+                      dimension=int(m.get("odim", 128)), kernel_size=int(enc.get("kernel_size", 7)),
+                      last_kernel_size=int(enc.get("last_kernel_size", 7)),
+                      residual_kernel_size=int(enc.get("residual_kernel_size", 3)),
+                      codebook_size=int(q.get("codebook_size", 1024)), num_quantizers=int(q.get("num_quantizers", 32)),
+                      sample_rate=int(q.get("sampling_rate", 16000)), audio_normalize=bool(m.get("audio_normalize", True)),
+                      lstm_layers=int(enc.get("seq_layer_num", 2)), **kw)
+    if int(q.get("encoder_hop_length", cfg.hop_length)) != cfg.hop_length:
+        refuse("quantizer_conf.encoder_hop_length != hop of the ratios")
+    return cfg, m.get("segment_dur"), m.get("overlap_ratio")
+
+
+def get_parser():
+    """Same flags, types and defaults as the reference's get_parser (codec_inference.py:428-558)."""
+    p = argparse.ArgumentParser(description="Speech Tokenizer (B200)", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("--log_level", type=lambda x: x.upper(), default="INFO",
+                   choices=("CRITICAL", "ERROR", "WARNING", "INFO", "DEBUG", "NOTSET"))
+    p.add_argument("--output_dir", type=str, required=False)
+    p.add_argument("--ngpu", type=int, default=0, help="accepted for compatibility; this implementation always runs on a GPU")
+    p.add_argument("--gpuid_list", type=str, default="")
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--dtype", default="float32", choices=["float16", "float32", "float64"])
+    p.add_argument("--num_workers", type=int, default=0, help="accepted for compatibility (host I/O is in-process)")
+    g = p.add_argument_group("Input data related")
+    g.add_argument("--data_path_and_name_and_type", type=str2triple_str, required=False, action="append")
+    g.add_argument("--key_file", type=str_or_none)
+    g.add_argument("--allow_variable_data_keys", type=str2bool, default=False)
+    g = p.add_argument_group("The model configuration related")
+    g.add_argument("--config_file", type=str)
+    g.add_argument("--model_file", type=str)
+    g.add_argument("--model_tag", type=str)
+    p.add_argument("--batch_size", type=int, default=1)
+    p.add_argument("--sampling_rate", type=int, default=24_000)
+    p.add_argument("--file_sampling_rate", type=int, default=None)
+    p.add_argument("--bit_width", type=int, default=16_000)
+    p.add_argument("--use_scale", type=str2bool, default=True)
+    g.add_argument("--need_indices", type=str2bool)
+    g.add_argument("--indices_save_type", type=str, default="text")
+    g.add_argument("--need_sub_quants", type=str2bool)
+    g.add_argument("--run_mod", type=str, choices=["inference", "encode", "decode", "decode_emb"], default="inference")
+    g.add_argument("--stat_flops", type=str2bool, default=False)
+    return p
+
+
+def pick_gpu(output_dir, gpuid_list: str) -> int:
+    """codec_inference.py:565-575: the job id is the suffix of `--output_dir` (`.../output.JOB`) and selects the GPU
+    round-robin from `--gpuid_list`."""
+    ids = [x for x in gpuid_list.split(",") if x != ""] or ["0"]
+    jobid = 1
+    if output_dir is not None:
+        try:
+            jobid = int(str(output_dir).split(".")[-1])
+        except ValueError:
+            jobid = 1
+    return int(ids[(jobid - 1) % len(ids)])
 
 
 def main(argv=None):
-    p = argparse.ArgumentParser(description="Speech Tokenizer (B200)")
-    p.add_argument("--output_dir", required=True)
-    p.add_argument("--config_file", required=True)
-    p.add_argument("--model_file", required=True)
-    p.add_argument("--data_path_and_name_and_type", required=True, help="path,name,type (sound | codec_json)")
-    p.add_argument("--run_mod", default="inference", choices=["inference", "encode", "decode"])
-    p.add_argument("--batch_size", type=int, default=16)
-    p.add_argument("--bit_width", type=int, default=None)
-    p.add_argument("--use_scale", type=lambda s: s.lower() in ("1", "true"), default=False)
-    p.add_argument("--gpuid_list", default="0")
-    args = p.parse_args(argv)
-    path = args.data_path_and_name_and_type.split(",")[0]
-    device = f"cuda:{args.gpuid_list.split(',')[0] or 0}"
-    cfg = config_from_yaml(args.config_file)
+    args = get_parser().parse_args(argv)
+    if args.file_sampling_rate is None:
+        args.file_sampling_rate = args.sampling_rate
+    if args.dtype != "float32":
+        raise SystemExit("--dtype: only float32 is implemented (fp32-parity kernels)")
+    if args.model_tag:
+        raise SystemExit("--model_tag (model hub download) is not available; pass --config_file / --model_file")
+    if args.file_sampling_rate != args.sampling_rate:
+        raise SystemExit("--file_sampling_rate != --sampling_rate: resampling is out of scope of this path")
+    if not args.data_path_and_name_and_type:
+        raise SystemExit("--data_path_and_name_and_type is required")
+    if args.output_dir is None:
+        raise SystemExit("--output_dir is required (raw_inputs mode is a Python API: funcodec_b200.speech2token)")
+    path, _name, dtype = args.data_path_and_name_and_type[0]
+    device = f"cuda:{pick_gpu(args.output_dir, args.gpuid_list)}"
+    cfg, segment_dur, overlap_ratio = config_from_yaml(args.config_file)
+    if cfg.sample_rate != args.sampling_rate:
+        raise SystemExit(f"--sampling_rate {args.sampling_rate} != model rate {cfg.sample_rate}")
     sd = torch.load(args.model_file, map_location="cpu")
-    s2t = Speech2Token(B200Encodec(cfg, sd, device), device)
+    if isinstance(sd, dict) and "state_dict" in sd and not any(k.startswith("encoder.") for k in sd):
+        sd = sd["state_dict"]
+    model = B200Encodec(cfg, sd, device, segment_dur=segment_dur, overlap_ratio=overlap_ratio)
+    s2t = Speech2Token(model, device, need_sub_quants=bool(args.need_sub_quants))
     if args.run_mod == "decode":
-        n = run_decode(s2t, path, args.output_dir, args.batch_size, args.bit_width)
+        if dtype not in ("codec_json", "text"):
+            raise SystemExit(f"--run_mod decode reads codec_json, got {dtype}")
+        n = run_decode(s2t, path, args.output_dir, args.batch_size, args.bit_width, key_file=args.key_file)
+    elif args.run_mod == "decode_emb":
+        if dtype not in ("kaldi_ark",):
+            raise SystemExit(f"--run_mod decode_emb reads kaldi_ark, got {dtype}")
+        n = run_decode_emb(s2t, path, args.output_dir, args.batch_size, key_file=args.key_file)
     else:
+        if dtype != "sound":
+            raise SystemExit(f"--run_mod {args.run_mod} reads sound, got {dtype}")
         n = run_encode(s2t, path, args.output_dir, args.batch_size, args.bit_width, args.run_mod, args.use_scale,
-                       save_recon=(args.run_mod == "inference"))
-    print(f"processed {n} utterances -> {args.output_dir}")
+                       key_file=args.key_file, need_indices=bool(args.need_indices),
+                       indices_save_type=args.indices_save_type, need_sub_quants=bool(args.need_sub_quants))
+    print(f"processed {n} utterances -> {args.output_dir}", file=sys.stderr)
+    return n
 
 
 if __name__ == "__main__":

@@ -1169,8 +1169,12 @@ int fcb_set_tensor(fcb_handle* h, const char* name, const float* data, int32_t n
     if (!h || !name || !data || ndim < 0 || ndim > 4) return FCB_E_INVALID;
     if (h->finalized) return fail(h, FCB_E_STATE, "fcb_set_tensor after fcb_finalize");
     std::string n(name);
+    // codebooks: stacked buffer of DistributedResidualVectorQuantization (use_ddp: true, ddp_core_vq.py:349-352) or the
+    // per-layer buffers of ResidualVectorQuantization (use_ddp: false, core_vq.py:147-150) -- assembled in fcb_finalize
+    const bool per_layer_embed = n.rfind("quantizer.rq.model.layers.", 0) == 0 && n.size() > 16 &&
+                                 n.compare(n.size() - 16, 16, "._codebook.embed") == 0;
     const bool known = n.rfind("encoder.model.", 0) == 0 || n.rfind("decoder.model.", 0) == 0 ||
-                       n == "quantizer.rq.model.embed";
+                       n == "quantizer.rq.model.embed" || per_layer_embed;
     if (!known) return 1;   // ignored (discriminator, EMA buffers, ...), like filter_state_dict
     HostTensor t;
     size_t cnt = 1;
@@ -1221,6 +1225,17 @@ int fcb_finalize(fcb_handle* h) {
     FCB_TRY(pack_conv(h, "decoder.model." + std::to_string(n + 1), nf, 1, c.last_kernel_size, 1, &h->dec_final));
     }
 
+    if (!find(h, "quantizer.rq.model.embed") && find(h, "quantizer.rq.model.layers.0._codebook.embed")) {
+        // use_ddp: false checkpoints (core_vq.py:147-150): one [K][D] buffer per stage, same semantics as the stacked tensor
+        HostTensor st;
+        st.shape = {c.num_quantizers, c.codebook_size, D};
+        for (int q = 0; q < c.num_quantizers; ++q) {
+            const HostTensor* e;
+            FCB_TRY(need(h, "quantizer.rq.model.layers." + std::to_string(q) + "._codebook.embed", {c.codebook_size, D}, &e));
+            st.data.insert(st.data.end(), e->data.begin(), e->data.end());
+        }
+        h->host["quantizer.rq.model.embed"] = std::move(st);
+    }
     const HostTensor* emb;
     FCB_TRY(need(h, "quantizer.rq.model.embed", {c.num_quantizers, c.codebook_size, D}, &emb));
     FCB_TRY(upload(h, emb->data, &h->embed));

@@ -42,9 +42,10 @@ def config_from_reference_model(model) -> CodecConfig:
         raise UnsupportedReferenceModel("segment_dur must be null for FreqCodec (whole-utterance processing)")
     if getattr(q, "input_proj", None) is not None or getattr(q, "input_act", None) is not None:
         raise UnsupportedReferenceModel("quantizer projections / codec_range are not supported")
-    if "quantizer.rq.model.embed" not in sd:
-        raise UnsupportedReferenceModel("quantizer must use use_ddp: true (stacked codebook buffers)")
-    embed = sd["quantizer.rq.model.embed"]
+    _check_module_options(model)
+    embed = stacked_codebooks(sd)
+    if embed is None:
+        raise UnsupportedReferenceModel("no codebook buffers found (quantizer.rq.model.embed or ...layers.N._codebook.embed)")
     w0 = sd["encoder.model.0.conv.conv.weight"]
     n_lstm = len([k for k in sd if k.startswith("decoder.model.1.lstm.weight_ih_l")])
     last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.model."))
@@ -75,6 +76,47 @@ def config_from_reference_model(model) -> CodecConfig:
                     return cand
         raise UnsupportedReferenceModel("2-D conv weight shapes match no conv_group_ratio / tr_conv_group_ratio")
     return cfg
+
+
+def stacked_codebooks(sd):
+    """[n_q, K, D] codebooks of either RVQ flavour: the stacked buffer of `use_ddp: true`
+    (ddp_core_vq.py:349-352) or the per-layer buffers of `use_ddp: false` (core_vq.py:147-150) -- same semantics."""
+    if "quantizer.rq.model.embed" in sd:
+        return sd["quantizer.rq.model.embed"]
+    per = []
+    while f"quantizer.rq.model.layers.{len(per)}._codebook.embed" in sd:
+        per.append(sd[f"quantizer.rq.model.layers.{len(per)}._codebook.embed"])
+    return torch.stack(per, dim=0) if per else None
+
+
+def _check_module_options(model) -> None:
+    """Options that change the maths but not the parameter names / shapes: inspect the module attributes
+    (conv.py:240-241,275-276; lstm.py:19; ddp_core_vq.py:354-356; seanet_encoder.py:49-61) and refuse anything else."""
+    import torch.nn as nn
+    for side in ("encoder", "decoder"):
+        net = getattr(model, side)
+        if not hasattr(net, "modules"):       # not an nn.Module (a plain description object): nothing to inspect
+            continue
+        for mod in net.modules():
+            name = type(mod).__name__
+            if name in ("SConv1d", "SConv2d", "SConvTranspose1d", "SConvTranspose2d"):
+                if getattr(mod, "causal", False):
+                    raise UnsupportedReferenceModel(f"{side}: causal convolutions are not supported")
+                if getattr(mod, "pad_mode", "reflect") != "reflect":
+                    raise UnsupportedReferenceModel(f"{side}: pad_mode must be reflect")
+                norm_conv = getattr(mod, "conv", None) if hasattr(mod, "conv") else getattr(mod, "convtr", None)
+                inner = getattr(norm_conv, "conv", None) if hasattr(norm_conv, "conv") else getattr(norm_conv, "convtr", None)
+                dil = getattr(inner, "dilation", (1,))
+                if any(int(d) != 1 for d in dil):
+                    raise UnsupportedReferenceModel(f"{side}: dilated convolutions are not supported")
+            elif name == "SLSTM" and not getattr(mod, "skip", True):
+                raise UnsupportedReferenceModel(f"{side}: SLSTM must use the skip connection (res_seq: true)")
+            elif name in ("Snake1d", "Snake", "PReLU", "ReLU", "LeakyReLU", "GELU", "Tanh") or \
+                    (isinstance(mod, nn.ELU) and float(mod.alpha) != 1.0):
+                raise UnsupportedReferenceModel(f"{side}: activation must be ELU(alpha=1)")
+    rq = getattr(getattr(model.quantizer, "rq", None), "model", None)
+    if rq is not None and int(getattr(rq, "q0_ds_ratio", 1)) != 1:
+        raise UnsupportedReferenceModel("quantizer q0_ds_ratio must be 1")
 
 
 def wrap_reference_encodec(model, device: str = "cuda:0"):

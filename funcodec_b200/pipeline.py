@@ -85,15 +85,82 @@ def batches(items: Sequence, batch_size: int) -> Iterator[Sequence]:
         yield items[i: i + batch_size]
 
 
+def select_keys(items: Sequence[Tuple[str, object]], key_file: Optional[str]) -> List[Tuple[str, object]]:
+    """`--key_file` (codec_inference.py:479 -> IterableESPnetDataset): iterate over the keys of `key_file` (first column),
+    each looked up in the data scp -- this is how `encoding_decoding.sh:79-86` shards one wav.scp over JOB processes."""
+    if not key_file:
+        return list(items)
+    table = dict(items)
+    out = []
+    with open(key_file, "rt", encoding="utf-8") as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            k = line.split(maxsplit=1)[0]
+            if k not in table:
+                raise KeyError(f"key_file entry {k!r} is not in the data file")
+            out.append((k, table[k]))
+    return out
+
+
+class IndicesWriter:
+    """`write_indices` (codec_inference.py:277-299): `codecs.txt` JSONL (`--indices_save_type text`) or a Kaldi
+    `indices.ark/.scp` float matrix [T', n_q] per utterance (`ark`).  Disabled when `--need_indices` is false."""
+
+    def __init__(self, output_dir: str, enabled: bool, save_type: str = "text"):
+        self.fout, self.ark = None, None
+        if not enabled:
+            return
+        if save_type == "ark":
+            from .kaldi_io import ArkScpWriter
+            self.ark = ArkScpWriter(os.path.join(output_dir, "indices"))
+        else:
+            self.fout = open(os.path.join(output_dir, "codecs.txt"), "wt")
+
+    def write(self, key: str, code_indices: List[torch.Tensor], batch_id: int, length: int) -> None:
+        if self.ark is not None:
+            mats = [x[:, batch_id, :length].cpu().float().numpy().T for x in code_indices]
+            self.ark(key, np.concatenate(mats, axis=0))
+        elif self.fout is not None:
+            self.fout.write(format_indices_line(key, code_indices, batch_id, length))
+
+    def close(self) -> None:
+        if self.ark is not None:
+            self.ark.close()
+        if self.fout is not None:
+            self.fout.close()
+
+
+def sub_quants_matrix(sub_quants: List[torch.Tensor], batch_id: int, length: int) -> np.ndarray:
+    """`write_sub_quants` (codec_inference.py:301-311): list of [n_q, B, D, T'] -> [T', n_q * D]."""
+    x = torch.cat(sub_quants, dim=-1).permute(1, 3, 0, 2)[batch_id][:length]
+    return x.reshape(x.shape[0], -1).cpu().numpy()
+
+
+def _wav_name(output_dir: str, key: str) -> str:
+    return os.path.join(output_dir, key if key.endswith(".wav") else key + ".wav")
+
+
 def run_encode(s2t, wav_scp: str, output_dir: str, batch_size: int = 16, bit_width: Optional[int] = None,
-               run_mod: str = "encode", use_scale: bool = False, save_recon: bool = False) -> int:
-    """`--run_mod encode|inference`: wav.scp -> codecs.txt (+ reconstructed wavs).  Returns the number of utterances."""
+               run_mod: str = "encode", use_scale: bool = True, save_recon: Optional[bool] = None,
+               key_file: Optional[str] = None, need_indices: bool = True, indices_save_type: str = "text",
+               need_sub_quants: bool = False) -> int:
+    """`--run_mod encode|inference`: wav.scp -> codecs.txt / indices.ark (+ codec_emb.ark, + reconstructed wavs in
+    `inference` mode).  Returns the number of utterances."""
     os.makedirs(output_dir, exist_ok=True)
     hop = s2t.model.quantizer.encoder_hop_length
     sr_model = s2t.model.quantizer.sampling_rate
+    if save_recon is None:
+        save_recon = run_mod == "inference"
+    writer = IndicesWriter(output_dir, need_indices, indices_save_type)
+    sq_writer = None
+    if need_sub_quants:
+        from .kaldi_io import ArkScpWriter
+        sq_writer = ArkScpWriter(os.path.join(output_dir, "codec_emb"))
     n = 0
-    with open(os.path.join(output_dir, "codecs.txt"), "wt") as fout:
-        for group in batches(read_scp(wav_scp), batch_size):
+    try:
+        for group in batches(select_keys(read_scp(wav_scp), key_file), batch_size):
             clips = []
             for key, path in group:
                 x, sr = load_wav(path)
@@ -101,34 +168,56 @@ def run_encode(s2t, wav_scp: str, output_dir: str, batch_size: int = 16, bit_wid
                     raise ValueError(f"{key}: sample rate {sr} != model rate {sr_model} (resampling is out of scope)")
                 clips.append(x)
             speech, lengths = wrap_pad_batch(clips)
-            codes, _, recon, _ = s2t(speech, need_recon=True, bit_width=bit_width, use_scale=use_scale, run_mod=run_mod)
+            codes, _, recon, sub = s2t(speech, need_recon=True, bit_width=bit_width, use_scale=use_scale, run_mod=run_mod)
             for i, (key, _) in enumerate(group):
                 ilen = int(lengths[i])
                 codec_len = -(-ilen // hop)
-                fout.write(format_indices_line(key, codes, i, codec_len))
                 if save_recon and recon is not None:
-                    save_wav_pcm16(os.path.join(output_dir, key if key.endswith(".wav") else key + ".wav"),
-                                   recon[i].cpu()[:, :ilen], sr_model, rescale=True)
+                    save_wav_pcm16(_wav_name(output_dir, key), recon[i].cpu()[:, :ilen], sr_model, rescale=True)
+                if codes is not None:
+                    writer.write(key, codes, i, codec_len)
+                if sq_writer is not None and sub is not None and sub[0] is not None:
+                    sq_writer(key, sub_quants_matrix(sub, i, codec_len))
                 n += 1
+    finally:
+        writer.close()
+        if sq_writer is not None:
+            sq_writer.close()
     return n
 
 
-def run_decode(s2t, codecs_txt: str, output_dir: str, batch_size: int = 16, bit_width: Optional[int] = None) -> int:
-    """`--run_mod decode`: codecs.txt -> wavs.  Code sequences of different lengths are wrap-padded like the reference's
-    collate (int arrays) and the output is trimmed to codec_len * hop."""
-    os.makedirs(output_dir, exist_ok=True)
+def _decode_groups(s2t, items, output_dir, batch_size, bit_width, run_mod, to_tensor) -> int:
     hop = s2t.model.quantizer.encoder_hop_length
     sr_model = s2t.model.quantizer.sampling_rate
-    with open(codecs_txt, "rt") as f:
-        items = [parse_indices_line(line) for line in f if line.strip()]
     n = 0
     for group in batches(items, batch_size):
         lens = [c.shape[0] for _, c in group]
         tmax = max(lens)
         toks = np.stack([np.pad(c, ((0, tmax - c.shape[0]), (0, 0)), mode="wrap") for _, c in group], axis=0)
-        _, _, recon, _ = s2t(torch.from_numpy(toks.astype(np.int64)), bit_width=bit_width, run_mod="decode")
+        _, _, recon, _ = s2t(to_tensor(toks), bit_width=bit_width, run_mod=run_mod)
         for i, (key, _) in enumerate(group):
-            save_wav_pcm16(os.path.join(output_dir, key if key.endswith(".wav") else key + ".wav"),
-                           recon[i].cpu()[:, : lens[i] * hop], sr_model, rescale=True)
+            save_wav_pcm16(_wav_name(output_dir, key), recon[i].cpu()[:, : lens[i] * hop], sr_model, rescale=True)
             n += 1
     return n
+
+
+def run_decode(s2t, codecs_txt: str, output_dir: str, batch_size: int = 16, bit_width: Optional[int] = None,
+               key_file: Optional[str] = None) -> int:
+    """`--run_mod decode`: codecs.txt (`codec_json`) -> wavs.  Code sequences of different lengths are wrap-padded like the
+    reference's collate (int arrays) and the output is trimmed to codec_len * hop (codec_inference.py:358-361)."""
+    os.makedirs(output_dir, exist_ok=True)
+    with open(codecs_txt, "rt") as f:
+        items = [parse_indices_line(line) for line in f if line.strip()]
+    items = select_keys(items, key_file)
+    return _decode_groups(s2t, items, output_dir, batch_size, bit_width, "decode",
+                          lambda a: torch.from_numpy(a.astype(np.int64)))
+
+
+def run_decode_emb(s2t, emb_scp: str, output_dir: str, batch_size: int = 16, key_file: Optional[str] = None) -> int:
+    """`--run_mod decode_emb` (codec_inference.py:118-119; encoding_decoding.sh stage 3): a Kaldi scp of [T', D] embedding
+    matrices (`kaldi_ark`) -> wavs through `inference_decoding_emb`."""
+    from .kaldi_io import read_mat
+    os.makedirs(output_dir, exist_ok=True)
+    items = [(k, read_mat(spec)) for k, spec in select_keys(read_scp(emb_scp), key_file)]
+    return _decode_groups(s2t, items, output_dir, batch_size, None, "decode_emb",
+                          lambda a: torch.from_numpy(a.astype(np.float32)))

@@ -11,9 +11,12 @@ from .encodec import B200Encodec
 
 
 class Speech2Token:
-    def __init__(self, model: B200Encodec, device: str = "cuda:0"):
+    def __init__(self, model: B200Encodec, device: str = "cuda:0", need_sub_quants: bool = True):
         self.model = model
         self.device = device
+        # the reference always materialises sub_quants [n_q, B, D, T']; the CLI only reads them under --need_sub_quants
+        # (codec_inference.py:282-286), so the driver may switch the extra tensor off
+        self.need_sub_quants = need_sub_quants
 
     @classmethod
     def from_state_dict(cls, cfg: CodecConfig, state_dict, device: str = "cuda:0"):
@@ -29,9 +32,10 @@ class Speech2Token:
             speech = torch.from_numpy(speech)
         m = self.model
         if run_mod == "inference":
-            ret = m.inference(speech, need_recon=need_recon, bit_width=bit_width, use_scale=use_scale)
+            ret = m.inference(speech, need_recon=need_recon, bit_width=bit_width, use_scale=use_scale,
+                              need_sub_quants=self.need_sub_quants)
         elif run_mod == "encode":
-            ret = m.inference_encoding(speech, need_recon=False, bit_width=bit_width)
+            ret = m.inference_encoding(speech, need_recon=False, bit_width=bit_width, need_sub_quants=self.need_sub_quants)
         elif run_mod == "decode_emb":
             ret = m.inference_decoding_emb(speech)
         else:
