@@ -35,10 +35,17 @@ WORKLOADS = {
     # for the transposed convs too); the engine runs the grouped weights as dense block-diagonal matrices
     "config4_gr8": ("freqcodec_magphase_16k_n32_ds320_gr8", 32, 160000, None),
 }
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of ONE step
+def load_ncu_traffic(workload):
+    """profiles/conv_traffic.json = {workload: {"bytes": dram read + write of one step's conv launches, "source": file}},
+    written by tools/summarize_ncu_raw.py from the latest `ncu --set full` capture (never a constant in this file)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        e = d.get(workload)
+        return (float(e["bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return (None, None)
 # SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the 48 conv launches of ONE config-2 step, from the
-# `ncu --set full` capture summarised in profiles/conv_ncu_r1n.txt (11.74 GB read + 6.98 GB written)
-NCU_CONV_TRAFFIC = {"config2": 18.72e9}
 ALGO = {
     "encodec_16k_n32_ds640": dict(conv_bytes_per_10s=1066.6e6, conv_gmac_per_10s=33.10, lstm_gmac_per_10s=8.39,
                                   rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
@@ -56,7 +63,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops", 0)), source="measured")
+        # the conv / RVQ kernels are timed inside a long step: the SUSTAINED dense bf16 figure is the tensor denominator
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0))),
+                    source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
 
 
@@ -130,13 +139,13 @@ def pick_cpu_threads(run_once):
     return best
 
 
-def make_oracle(cfg, sd):
+def make_oracle(cfg, sd, device="cpu"):
     """The CPU port of the reference model for this config (time-domain Encodec or mag_phase FreqCodec)."""
     if cfg.arch == 1:
         from oracle.freqcodec_oracle import OracleFreqCodec
         return OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)), cfg.sample_rate, cfg.lstm_layers, cfg.n_fft, cfg.stft_hop)
     from oracle.encodec_oracle import OracleEncodec
-    return OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    return OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers, device=device)
 
 
 def cpu_oracle_time(cfg, sd, B, L, bit_width, reps, warm):
@@ -167,24 +176,27 @@ def run_reference(args):
     cfg_name, B, L, bw = WORKLOADS[args.workload]
     cfg = get_config(cfg_name)
     sd = init_state_dict(cfg, 0)
-    sample_B = min(B, 2)            # bounded sample: 2 clips of the workload's length per step
+    # one step = the workload's own batch when a CPU pass of it fits the time budget (config 2: 16 x 10 s, ~6 s per pass on
+    # 16 threads -> same_config), otherwise a bounded sample of ~2.56 M samples of audio per step
+    sample_B = max(1, min(B, 2_560_000 // L))
+    probe_B = min(sample_B, 2)
     o = make_oracle(cfg, sd)
     g = torch.Generator().manual_seed(1235)
     wav = 0.1 * torch.randn(sample_B, L, generator=g)
 
-    def batched():
-        o.inference(wav, need_recon=True, bit_width=bw)
+    def batched(n=None):
+        o.inference(wav[:n or sample_B], need_recon=True, bit_width=bw)
 
-    def per_clip():
-        for i in range(sample_B):
+    def per_clip(n=None):
+        for i in range(n or sample_B):
             o.inference(wav[i:i + 1], need_recon=True, bit_width=bw)
 
-    # give the CPU path its best configuration: fastest of {batched, clip-by-clip} x {8,16,32,64} threads
+    # give the CPU path its best configuration: fastest of {batched, clip-by-clip} x {8,16,32,64} threads, probed on 2 clips
     best = None
     for mode in (batched, per_clip):
-        n = pick_cpu_threads(mode)
+        n = pick_cpu_threads(lambda: mode(probe_B))
         t0 = time.perf_counter()
-        mode()
+        mode(probe_B)
         dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, mode, n)
@@ -198,16 +210,122 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     frames = sample_B * cfg.frames(L) * args.steps
     value = frames / dt
-    sample = f"{sample_B} x {L / cfg.sample_rate:.0f} s clips per step ({run_step.__name__}; bounded sample of batch {B}), {cores} torch threads (fastest of 8/16/32/64 on {os.cpu_count()} host cores)"
+    what = "the full batch" if sample_B == B else f"bounded sample of batch {B}"
+    sample = f"{sample_B} x {L / cfg.sample_rate:.0f} s clips per step ({run_step.__name__}; {what}), {cores} torch threads (fastest of 8/16/32/64 on {os.cpu_count()} host cores)"
     line = dict(metric="codec frames/sec (encode+RVQ+decode)", value=value, unit="frames/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 rtf=dt / (sample_B * L / cfg.sample_rate * args.steps),
-                config=dict(workload=f"{cfg_name} B={B} L={L} n_q={cfg.num_quantizers_for_bandwidth(bw)} (BASELINE {args.workload})",
-                            sample=sample),
+                config=dict(workload=f"{cfg_name} B={B}/GPU L={L} n_q={cfg.num_quantizers_for_bandwidth(bw)} (BASELINE {args.workload})",
+                            global_batch=args.gpus * B, clip_seconds=L / cfg.sample_rate, sample=sample,
+                            same_config=bool(sample_B == B and args.gpus == 1)),
                 cpu_baseline=dict(value=value, unit="frames/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def config5_extra(model, cfg, dev, rank, world, steps=5):
+    """BASELINE config 5 as named: ONE batch of 64 x world clips (10 s, ds640, n_q = 32) held by one process and sharded over
+    the GPUs of the box.  Three timings (CUDA events, max over ranks): device-resident shards; end to end with the batch in
+    a shared pinned host buffer that every rank DMA-reads / writes over its own PCIe link (parallel.SharedHostBatch, no
+    data-path collective); end to end through rank 0's GPU with NCCL scatter / gather (parallel.ShardedCodec)."""
+    import torch
+    import torch.distributed as dist
+    from funcodec_b200.encodec import _ptr
+    from funcodec_b200.parallel import ShardedCodec, SharedHostBatch
+    B, L = 64, 160000
+    GB = world * B
+    n_q, Tf = cfg.num_quantizers, cfg.frames(L)
+    g = torch.Generator().manual_seed(4321 + rank)
+    wavs = [(0.1 * torch.randn(B, L, generator=g)).to(dev) for _ in range(4)]      # 4 x 41 MB per rank > L2
+    codes = torch.empty((n_q, B, Tf), dtype=torch.int64, device=dev)
+    recon = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run_dev(x):
+        model._ck(model._lib.fcb_roundtrip(model._h, _ptr(x), x.shape[0], L, n_q, 1, _ptr(codes), None, None, None, _ptr(recon),
+                                           model._stream()), "fcb_roundtrip")
+        return codes, recon
+
+    def timed(fn, n):
+        for i in range(2):
+            fn(i)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            fn(2 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    out = {}
+    ms = timed(lambda i: run_dev(wavs[i % 4]), steps)
+    out["device_resident"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3))
+    # shared pinned host batch, one PCIe link per GPU
+    shb = SharedHostBatch(f"fcb_bench_{os.environ.get('MASTER_PORT', '0')}", GB, L, n_q, Tf, rank, world, create=(rank == 0))
+    dist.barrier()
+    shb.map()
+    if rank == 0:
+        shb.wav.copy_(0.1 * torch.randn(GB, L, generator=g))
+    dist.barrier()
+    lo, hi = shb.shard()
+    ms = timed(lambda i: model.roundtrip_host(shb.wav[lo:hi], shb.codes[rank], shb.recon[lo:hi]), steps)
+    out["e2e_shared_host"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3), h2d_bytes_per_step=GB * L * 4,
+                                  d2h_bytes_per_step=n_q * GB * Tf * 8 + GB * L * 4,
+                                  path="one /dev/shm batch page-locked by every rank; each rank fcb_roundtrip_host on its shard")
+    # NCCL scatter / gather through rank 0's GPU
+    sharded = ShardedCodec(run_dev)
+    hw = hc = hr = dw = None
+    if rank == 0:
+        hw = shb.wav
+        hc = torch.empty((n_q, GB, Tf), dtype=torch.int64).pin_memory()
+        hr = shb.recon
+        dw = torch.empty((GB, L), dtype=torch.float32, device=dev)
+
+    def scatter_step(i):
+        if rank == 0:
+            dw.copy_(hw, non_blocking=True)
+            o = sharded(dw, GB, L, dev)
+            hc.copy_(o[0], non_blocking=True)
+            hr.copy_(o[1], non_blocking=True)
+        else:
+            sharded(None, GB, L, dev)
+        torch.cuda.synchronize()
+
+    ms = timed(scatter_step, steps)
+    out["e2e_nccl_scatter"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3),
+                                   path="rank0 pinned host -> H2D -> NCCL scatter -> fcb_roundtrip -> NCCL gather -> D2H")
+    out["workload"] = f"encodec_16k_n32_ds640 B={GB} ({B}/GPU) L={L} n_q={n_q} (BASELINE config 5 on {world} GPUs)"
+    dist.barrier()
+    shb.close()
+    return out
+
+
+def cuda_eager_reference(cfg, sd, B, L, dev, reps=3):
+    """Context only (BASELINE.md 'secondary comparison'): the oracle's torch functional restatement of the reference modules
+    run on the SAME GPU in eager mode with TF32 off (cuDNN / cuBLAS fp32 kernels), device-resident input."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    o = make_oracle(cfg, sd, device=dev)
+    wav = 0.1 * torch.randn(B, L, device=dev)
+    with torch.no_grad():
+        o.inference(wav, need_recon=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            o.inference(wav, need_recon=True)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return dict(ms_per_step=ms, frames_per_s=B * cfg.frames(L) / (ms * 1e-3), what="oracle (torch functional ops = the ATen/cuDNN "
+                "kernels the reference modules call) on cuda, eager, allow_tf32=False, same batch; context, not the reference arm")
 
 
 def main():
@@ -220,6 +338,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): skip the host-buffer leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (config-5 block at N > 1, CUDA-eager context at N = 1)")
     ap.add_argument("--e2e-mode", choices=["sharded-host", "scatter"], default="sharded-host",
                     help="N > 1 end-to-end leg: every rank round-trips its own pinned host shard (default; the reference's "
                          "multi-process inference), or rank 0 holds the whole batch and scatters / gathers it over NCCL")
@@ -239,8 +358,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: everything else this process (and NCCL, whose NCCL_DEBUG the caller controls and
+    # which logs to stdout) prints is routed to stderr by swapping the file descriptors; the line is written to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FCB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_name, B, L, bw = WORKLOADS[args.workload]
@@ -390,6 +513,16 @@ def main():
         d2h = n_q * GB * Tf * 8 + GB * L * 4
     e2e_value = world * B * Tf * e2e_steps / (e2e_ms * 1e-3)
 
+    extra = {}
+    if not args.no_extras and not args.skip_e2e and not args.batch:
+        try:
+            if world > 1 and args.workload == "config2" and cfg.arch == 0:
+                extra["config5"] = config5_extra(model, cfg, dev, rank, world)
+            elif world == 1 and cfg.arch == 0:
+                extra["reference_cuda_eager"] = cuda_eager_reference(cfg, sd, B, L, dev)
+        except Exception as exc:            # an extra leg must never take the headline line down
+            extra["error"] = f"{type(exc).__name__}: {exc}"
+
     if rank == 0:
         algo = ALGO[cfg_name]
         clip10 = L / 160000.0
@@ -397,14 +530,26 @@ def main():
         conv_bytes = algo["conv_bytes_per_10s"] * clip10 * B + algo["weight_bytes"]
         achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
         conv_tflops = 2 * algo["conv_gmac_per_10s"] * clip10 * B / (conv_ms * 1e-3) / 1e3 if conv_ms > 0 else 0.0
+        traffic, traffic_src = load_ncu_traffic(args.workload) if not args.batch else (None, None)
+        # tensor-pipe view (north_star: "tensor-pipe utilisation (RVQ distance)"): fp32-equivalent FLOPs x 3 passes of the split
+        # operands, against the measured dense bf16/fp16 rate (conv: kind::f16) or half of it (RVQ: kind::tf32)
+        f16_peak = peaks["bf16_tflops"]
+        conv_tensor_tflops = 3 * conv_tflops
+        rvq_ms = phases.get("rvq", 0.0)
+        rvq_tflops = 3 * algo["rvq_gflop_per_10s_nq32"] * (n_q / 32.0) * clip10 * B / (rvq_ms * 1e-3) / 1e3 if rvq_ms > 0 else 0.0
+        tensor = dict(conv=dict(achieved=conv_tensor_tflops, peak=f16_peak, unit="TFLOP/s", frac=conv_tensor_tflops / f16_peak if f16_peak else None,
+                                note="3 kind::f16 MMAs per fp32-equivalent product (fp16 hi/lo split); peak = measured dense bf16"),
+                      rvq=dict(achieved=rvq_tflops, peak=f16_peak / 2, unit="TFLOP/s", frac=rvq_tflops / (f16_peak / 2) if f16_peak else None,
+                               kernel_ms_per_step=rvq_ms,
+                               note="rvq_tc_kernel: 3 kind::tf32 MMAs per product; peak = measured dense bf16 / 2 (tf32 rate); "
+                                    "includes the argmin / re-scoring / residual-update epilogues of all stages"))
         roofline = dict(bound="hbm", kernel="conv1d_tc_kernel<N> (+ conv1d_cl / conv1d_cout1 for the 3 layers that do not fit "
                                             "the tensor cores): all SEANet conv/convtr launches of one step = "
                                             "encoder_conv + decoder_conv phases",
                         achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                        traffic=NCU_CONV_TRAFFIC.get(args.workload) if not args.batch else None,
-                        traffic_source="profiles/conv_ncu_r1n.txt (ncu --set full, 48 conv launches of one step)",
+                        traffic=traffic, traffic_source=traffic_src,
                         peak_source=peaks["source"], algorithmic_bytes=conv_bytes,
-                        kernel_ms_per_step=conv_ms, conv_fp32_tflops=conv_tflops)
+                        kernel_ms_per_step=conv_ms, conv_fp32_tflops=conv_tflops, tensor=tensor)
         cpu = None
         if not args.no_cpu_baseline:
             v, sec, cores = cpu_oracle_time(cfg, sd, 1, 160000, None, reps=5, warm=1)
@@ -426,8 +571,11 @@ def main():
                              path="fcb_roundtrip_host (pinned host buffers, one shard per rank)"
                                   if (world == 1 or args.e2e_mode == "sharded-host") else
                                   "rank0 pinned host -> H2D -> NCCL scatter -> fcb_roundtrip -> NCCL gather -> D2H"),
-                    roofline=roofline, cpu_baseline=cpu, phase_ms_last_step=phases)
-        print(json.dumps(line))
+                    roofline=roofline, cpu_baseline=cpu, phase_ms_last_step=phases, extra=extra,
+                    reference_arm_note=("the --impl reference arm is ONE CPU process (rank 0) at every N: a ratio of this N-GPU "
+                                        "aggregate to it scales with N by construction" if world > 1 else None))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -48,6 +48,10 @@ struct ConvParams {
     const float* w;          // packed [K][C_in][C_out]
     const float* w_tc;       // tensor-core image (conv_tc.cu) or nullptr
     int n_tile;              // output channels per CTA on the tensor-core path
+    float tc_w_scale;        // power-of-two scale baked into the w_tc image (engine.cu build_tc_image_f16)
+    float tc_in_scale;       // tensor-core path: power-of-two scale of the fp16-split activation operand (0 -> default 16)
+    float tc_out_scale;      // 1 / (tc_in_scale * weight scale of the layer's image): applied to the accumulator in the epilogue
+    float tc_elu_k;          // log2(e) / tc_in_scale (set by launch_conv_tc)
     const float* bias;       // [C_out]
     float* out;              // raw [B][T_out][C_out]
     int T_out, C_out;

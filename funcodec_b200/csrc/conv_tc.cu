@@ -1,5 +1,9 @@
-// Implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM),
-// fp32-faithful through the 3xTF32 split (x = hi + lo, D += lo*hi + hi*lo + hi*hi).
+// Implicit-GEMM Conv1d on the 5th-generation tensor cores (tcgen05.mma kind::f16, accumulators in TMEM),
+// fp32-faithful through a 3-term FP16 split: both operands are pre-scaled by a power of two (activations x16, weights
+// per layer so that max|w| lands in [2^13, 2^14)), x = hi + lo with hi = fp16(x), lo = fp16(x - hi), and
+// D += lo*hi + hi*lo + hi*hi in fp32; the epilogue multiplies by the (exact) inverse scale.  Same accuracy as the
+// 3xTF32 split it replaces (both drop the lo*lo term, ~2^-22 relative), at twice the tensor throughput and half the
+// shared-memory operand bytes per MAC (K = 16 per MMA instead of 8; a 128-byte swizzle row holds 64 channels).
 //
 // Same contract as conv_simt.cu (fused [GroupNorm apply + resblock add + ELU + reflect pad] on the input,
 // bias + raw store + GroupNorm partial statistics on the output), reference semantics
@@ -9,7 +13,9 @@
 //     D[t (M = 128 time rows), co (N = n_tile)] = sum_{tap k} sum_{ci} X[t*S + k - pad_l][ci] * W[k][ci][co]
 //   * A (activations): one "unit" = (32-channel chunk, stride phase p): the rows {(t0+u)*S + p - pad_l}
 //     are transformed by a producer group and written (hi and lo slabs) into the canonical SWIZZLE_128B
-//     K-major layout; every tap k = q*S + p of that phase is then just a ROW-SHIFTED view (start address
+//     K-major layout; a ring stage holds a 64-channel chunk, i.e. two units side by side (the two producer groups
+//     each fill one half; layers with a single 32-channel chunk fill half a stage and the groups alternate stages);
+//     every tap k = q*S + p of that phase is then just a ROW-SHIFTED view (start address
 //     + q*128 B; the hardware swizzle works on absolute address bits) of the same slab -- no im2col copy.
 //   * B (weights): pre-split, pre-swizzled slab images in HBM (engine.cu pack_tc), one cp.async.bulk
 //     (TMA engine, 1-D) per (chunk, tap) into a ring, completion on an mbarrier.
@@ -23,7 +29,7 @@
 //     warp ping-pongs between two TMEM accumulators and the accumulator warps fold each finished group into
 //     a third TMEM region (running totals) with round-to-nearest CUDA-core adds, then run the epilogue
 //     (bias, channels-last store, GroupNorm partial sums) on the last group.
-// Roofline: tensor pipe (3 MMAs per fp32-equivalent product) for C_in*K >= 128; HBM for the C <= 64 layers.
+// Roofline: tensor pipe (3 MMAs per fp32-equivalent product) for the deep layers; HBM for the C <= 64 layers.
 //
 // FREQ = true is the FreqCodec 2-D mode (SConv2d / SConvTranspose2d, conv.py:317-447): a "clip" of the tile list is a
 // pseudo-clip (clip b, output frequency row f_out) and the gathered input channel cg = kf*cin + c of a chunk comes from
@@ -41,7 +47,7 @@ namespace fcb {
 using namespace tc;
 
 constexpr int TC_M = 128;          // time rows per tile
-constexpr int TC_KC = 32;          // channels per chunk (one 128-byte swizzle row)
+constexpr int TC_KC = 32;          // channels per producer unit (half of a 128-byte fp16 swizzle row)
 constexpr int TC_THREADS = 704;    // 16 producer warps (2 groups), copy warp, MMA warp, 4 accumulator warps
 constexpr int TC_PROD = 256;       // producer threads per group (one unit)
 constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TMEM before the fp32 fold
@@ -49,6 +55,9 @@ constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TM
 // ELU with the hardware exponential (ex2.approx): |error| <= ~2e-7 on the (0, 1] range of exp(x), the same order as
 // one fp32 rounding of the reference's exp(x) - 1.  (The SIMT path keeps expf.)
 __device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : (__expf(v) - 1.0f); }
+// the same on a value pre-multiplied by the operand scale s (a power of two): s*elu(v) from vs = s*v with k = log2(e)/s.
+// Scaling by a power of two commutes with every rounding involved, so this equals s * elu_fast(v) bit for bit.
+__device__ __forceinline__ float elu_scaled(float vs, float k, float s) { return vs > 0.f ? vs : fmaf(exp2f_approx(vs * k), s, -s); }
 
 struct TcSmemLayout {
     int a_rows;        // rows per A slab (multiple of 8)
@@ -71,7 +80,7 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     return L;
 }
 
-// units (chunk, phase) chained in one TMEM accumulation group
+// ring stages (64-channel chunk, phase) chained in one TMEM accumulation group
 __host__ __device__ inline int tc_units_per_group(int K, int S, int group_mmas) {
     const int taps = (K + S - 1) / S;                  // max taps of a phase
     int g = group_mmas / (12 * taps);
@@ -100,7 +109,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     const bool has1 = p.in1.x != nullptr;
     const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
-    const int n_units = n_chunks * S;
+    const int n_sc = (n_chunks + 1) >> 1;                 // 64-channel stage chunks
+    const bool split = n_chunks > 1;                      // both producer groups fill one stage (32 channels each)
+    const int n_units = n_sc * S;                         // ring stages per tile
     const int upg = tc_units_per_group(K, S, group_mmas);
     const int n_groups = (n_units + upg - 1) / upg;
     const int n_tt = (p.T_out + TC_M - 1) / TC_M;
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     double* red = reinterpret_cast<double*>(tmem_ptr + 2);       // [4][2] statistics scratch
 
     if (tid == 0) {
-        for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, TC_PROD); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, split ? 2 * TC_PROD : TC_PROD); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
         mbar_fence_init();
@@ -132,16 +143,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
 
     if (warp < 16) {
         // =========================================================== producers: transformed A slabs
-        const int grp = warp >> 3;                  // this group takes the units with (global unit index) % 2 == grp
+        const int grp = warp >> 3;
         const int ptid = tid & (TC_PROD - 1);
-        const int jchunk = ptid & 7;                // 16-byte chunk (4 channels) inside the 128-byte row
-        const int rsub = ptid >> 3;                 // 32 rows per pass
+        const int jchunk = ptid & 7;                // 4 channels (16 bytes of fp32 in HBM, 8 bytes of fp16 in the slab)
+        // rows of a warp: {b, b+1, b+4, b+5}: its four 64-byte half rows land on all 32 banks (2 wavefronts per 8-byte store)
+        const int wq = (ptid >> 5), lq = (lane >> 3);
+        const int rsub = ((wq >> 1) << 3) + ((wq & 1) << 1) + (lq & 1) + ((lq >> 1) << 2);      // 32 rows per pass
         const int gt_max = (p.T_out - 1) * S - p.pad_l + (K - 1);
-        // this group's cursor over the CTA's global unit sequence (tile-major); it advances two units at a time and its
-        // ring slot two slots at a time (na is even), so no division / modulo is needed in the loop
-        int tile = blockIdx.x, unit = grp;
-        int as = grp % na_stages;
+        // this group's cursor over the CTA's global stage sequence (tile-major).  split: both groups fill every stage (group g
+        // writes the 32-channel half g); otherwise (one 32-channel chunk) the groups take alternate stages and the ring slot
+        // advances two at a time (na is even), so no division / modulo is needed in the loop
+        const int step = split ? 1 : 2;
+        const int half = split ? grp : 0;
+        int tile = blockIdx.x, unit = split ? 0 : grp;
+        int as = unit % na_stages;
         uint32_t aphase = 0;
+        const float in_scale = p.tc_in_scale;
         while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
         while (tile < n_tiles) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
@@ -155,10 +172,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
             for (; unit < n_units && tile == cur_tile; ) {
-                const int chunk = unit / S, ph = unit - chunk * S;
+                const int sc = unit / S, ph = unit - sc * S;
+                const int chunk = 2 * sc + half;               // 32-channel chunk of this group (may not exist: odd n_chunks)
                 const uint32_t par = aphase ^ 1;
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
+                if (chunk < n_chunks) {
                 int c = chunk * TC_KC + jchunk * 4;
                 bool c_ok = c < C_in;
                 const float* xu0 = x0;
@@ -174,10 +193,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     xu0 = x0 + (long long)(p.fq.f_off0 + f_src) * p.fq.T_raw0 * pitch;
                     if (has1) xu1 = x1 + (long long)(p.fq.f_off1 + f_src) * p.fq.T_raw1 * pitch;
                 }
-                float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+                // the operand scale (a power of two: exact) is folded into the deferred-GroupNorm affine
+                float4 a0 = make_float4(in_scale, in_scale, in_scale, in_scale), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
                 if (!c_ok) { a0 = b0; a1 = b0; }
-                else if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
-                if (c_ok && cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
+                else if (cf0) {
+                    a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c));
+                    a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
+                    b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
+                }
+                if (c_ok && cf1) {
+                    a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c));
+                    a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
+                    b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
+                }
                 // all row loads of the unit are issued before the ring slot is waited for
                 constexpr int NR = 5;                      // a_rows <= 160 = 5 passes of 32 rows
                 float4 xa[NR], xb[NR];
@@ -200,6 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     }
                 }
                 mbar_wait_backoff(a_empty + as, par, 64);
+                const uint32_t c16 = (uint32_t)(half * 4 + (jchunk >> 1)), sub8 = (uint32_t)((jchunk & 1) << 3);
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 32 * i;
@@ -215,22 +244,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
                                 v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
                             }
-                            if (p.elu) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
+                            if (p.elu) {
+                                v.x = elu_scaled(v.x, p.tc_elu_k, in_scale); v.y = elu_scaled(v.y, p.tc_elu_k, in_scale);
+                                v.z = elu_scaled(v.z, p.tc_elu_k, in_scale); v.w = elu_scaled(v.w, p.tc_elu_k, in_scale);
+                            }
                         }
                         if (p.dbg & 4) continue;
-                        float4 h, l;
-                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                        const uint32_t o = (uint32_t)u * 128u + (uint32_t)((jchunk ^ (u & 7)) << 4);
-                        *reinterpret_cast<float4*>(hi + o) = h;
-                        *reinterpret_cast<float4*>(lo + o) = l;
+                        uint2 h, l;
+                        split_f16x2(v.x, v.y, h.x, l.x);
+                        split_f16x2(v.z, v.w, h.y, l.y);
+                        const uint32_t o = (uint32_t)u * 128u + ((c16 ^ (uint32_t)(u & 7)) << 4) + sub8;
+                        *reinterpret_cast<uint2*>(hi + o) = h;
+                        *reinterpret_cast<uint2*>(lo + o) = l;
                     }
                 }
                 fence_proxy_async_smem();
+                } else {
+                    mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
+                }
                 mbar_arrive(a_full + as);
-                as += 2;
+                as += step;
                 if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
-                unit += 2;
+                unit += step;
             }
             while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
         }
@@ -244,8 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 if (w_resident && !first) break;                       // whole layer image already resident
                 const TcTile tl = tc_tile(tile, n_nt, n_tt);
-                const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)tl.nt * n_chunks * K * bytes;
-                int chunk = 0, ph = 0;
+                const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w_tc) + (long long)tl.nt * n_sc * K * bytes;
+                int chunk = 0, ph = 0;                                 // chunk: 64-channel stage chunk
                 for (int unit = 0; unit < n_units; ++unit) {
                     for (int k = ph; k < K; k += S) {
                         if (!w_resident) mbar_wait_backoff(b_empty + bs, bphase ^ 1, 64);
@@ -261,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     } else if (warp == 17) {
         // =========================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_M, N_TILE);
+            const uint32_t idesc = make_idesc_f16(TC_M, N_TILE);
             const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0, gcount = 0;
@@ -281,6 +316,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         tc_fence_after_sync();
                         const uint32_t a_hi0 = a_base + as * L.a_stage;
                         const uint32_t a_lo0 = a_hi0 + L.a_rows * 128;
+                        // K steps of 16 channels: 4 for a full 64-channel stage, 2 when only its first half exists
+                        const int ksteps = (2 * (unit / S) + 1 < n_chunks) ? 4 : 2;
                         int q = 0;
                         for (int k = ph; k < K; k += S, ++q) {
                             if (!w_resident || first) {
@@ -292,14 +329,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                             if (!(p.dbg & 32))
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
-                                const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
-                                const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
-                                const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
-                                mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, accum);
-                                accum = 1;
-                                mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
-                                mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, 1);
+                                if (ks < ksteps) {
+                                    const uint64_t da_hi = make_desc_k_sw128(a_hi0 + q * 128 + ks * 32);
+                                    const uint64_t da_lo = make_desc_k_sw128(a_lo0 + q * 128 + ks * 32);
+                                    const uint64_t db_hi = make_desc_k_sw128(b_hi0 + ks * 32);
+                                    const uint64_t db_lo = make_desc_k_sw128(b_lo0 + ks * 32);
+                                    mma_f16_ss(d_tmem, da_lo, db_hi, idesc, accum);
+                                    accum = 1;
+                                    mma_f16_ss(d_tmem, da_hi, db_lo, idesc, 1);
+                                    mma_f16_ss(d_tmem, da_hi, db_hi, idesc, 1);
+                                }
                             }
                             if (!w_resident) mma_commit(b_empty + bs);
                             if (++bs == nb_stages) { bs = 0; bphase ^= 1; }
@@ -319,6 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(2 * BUF_COLS);
         uint32_t gcount = 0;
+        const float out_scale = p.tc_out_scale;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
             const int t = tl.tt * TC_M + quad * 32 + lane;
@@ -362,10 +402,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         for (int j = 0; j < 32; j += 4) {
                             if (c0 + j < N_TILE) {
                                 float4 o;
-                                o.x = __uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0);
-                                o.y = __uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1);
-                                o.z = __uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2);
-                                o.w = __uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3);
+                                // exact power-of-two rescale + bias in one rounding (== fl(acc / scale + bias))
+                                o.x = fmaf(__uint_as_float(v[j + 0]), out_scale, __ldg(bias + c0 + j + 0));
+                                o.y = fmaf(__uint_as_float(v[j + 1]), out_scale, __ldg(bias + c0 + j + 1));
+                                o.z = fmaf(__uint_as_float(v[j + 2]), out_scale, __ldg(bias + c0 + j + 2));
+                                o.w = fmaf(__uint_as_float(v[j + 3]), out_scale, __ldg(bias + c0 + j + 3));
                                 s += (o.x + o.y) + (o.z + o.w);
                                 ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
                                 if (p.dbg & 8) {
@@ -481,10 +522,14 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
     }
     p.dbg = g_dbg;
+    if (!(p.tc_in_scale > 0.f)) p.tc_in_scale = 16.f;           // post-GroupNorm activations are O(1): 16 x keeps |x| < 4094 finite
+    if (!(p.tc_w_scale > 0.f)) p.tc_w_scale = 1.f;
+    p.tc_out_scale = 1.0f / (p.tc_in_scale * p.tc_w_scale);     // powers of two: exact
+    p.tc_elu_k = 1.4426950408889634f / p.tc_in_scale;
     // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
     // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
     // (A even: the two producer groups alternate slots).
-    const int n_slabs = ((p.C_in + TC_KC - 1) / TC_KC) * p.K;
+    const int n_slabs = ((p.C_in + 2 * TC_KC - 1) / (2 * TC_KC)) * p.K;   // (64-channel stage chunk, tap) weight slabs per n-tile
     const int limit = 225 * 1024;
     int resident = 0, na = 4, nb = 4;
     TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);

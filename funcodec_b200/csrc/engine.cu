@@ -36,7 +36,8 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl
     float* bias = nullptr;   // [cout_eff]
     float* gamma = nullptr;  // [cout]
     float* beta = nullptr;   // [cout]
-    float* w_tc = nullptr;   // tensor-core image: [n_tile idx][chunk][tap][hi|lo][n_tile rows x 128 B swizzled]
+    float* w_tc = nullptr;   // tensor-core image: [n_tile idx][64-ch chunk][tap][hi|lo][n_tile rows x 128 B swizzled fp16]
+    float tc_scale = 1.f;    // power-of-two scale baked into w_tc (build_tc_image_f16)
     int n_tile = 0;          // 0: no tensor-core image (layer runs on the SIMT kernel)
 };
 
@@ -80,6 +81,7 @@ struct fcb_handle {
     float* embed_tc = nullptr; // tensor-core image of the codebooks (rvq_tc.cu)
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
+    unsigned long long* lstm_trace = nullptr;   // PROFILING ONLY (env FCB_LSTM_TRACE): managed buffer, dumped by fcb_destroy
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
     int stft_tc = 1;             // STFT / iSTFT as tensor-core GEMMs ("stft_tc" option; 0: the direct-DFT kernels)
@@ -98,6 +100,7 @@ struct fcb_handle {
         float* w = nullptr; float* bias = nullptr; float* gamma = nullptr; float* beta = nullptr;
         // tensor-core image (conv_tc.cu 2-D mode) of [kt][kf*cin][cout_tc]; cout_tc = C_out_eff rounded up to 16
         float* w_tc = nullptr; float* bias_tc = nullptr;
+        float tc_scale = 1.f;
         int n_tile = 0, cout_tc = 0;
         int tc_class = 0;    // 1: cin % 32 == 0; 2: cin < 32 (several frequency taps per chunk); 4: padded C_out
         int out_pad[2][2] = {{0, 0}, {0, 0}};   // transposed conv out_padding {{f_l, f_r}, {t_l, t_r}} (conv.py:410-445)
@@ -163,11 +166,87 @@ int need(fcb_handle* h, const std::string& name, std::vector<int64_t> shape, con
     return FCB_OK;
 }
 
-// Tensor-core weight image (conv_tc.cu): for every (n-tile, 32-channel chunk, tap) one hi slab and one lo
-// slab of [n_tile rows (output channels) x 32 tf32] in the canonical K-major SWIZZLE_128B layout, so that a
-// single 1-D bulk copy drops it into shared memory ready for tcgen05.mma.  hi/lo = 3xTF32 split.
-void build_tc_image(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, int n_tile,
-                    std::vector<float>* img_out) {
+// fp32 -> fp16 bits, round-to-nearest-even, saturating to +-65504 (the device side uses cvt.rn.satfinite.f16x2.f32)
+uint16_t f32_to_f16_bits(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    u &= 0x7FFFFFFFu;
+    if (u >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);            // >= 65520 (rounds past the largest finite) or inf / nan
+    if (u < 0x38800000u) {                                               // < 2^-14: subnormal result, multiples of 2^-24
+        float ax;
+        memcpy(&ax, &u, 4);
+        const float r = ax * 16777216.0f;                                // exact (power of two); |r| < 1024
+        const float rr = nearbyintf(r);                                  // default rounding mode: nearest even
+        return (uint16_t)(sign | (uint32_t)rr);
+    }
+    const uint32_t mant = u & 0x7FFFFFu, exp = (u >> 23) - 112u;         // rebias 127 -> 15
+    uint32_t h = (exp << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;              // carries into the exponent correctly
+    return (uint16_t)(sign | h);
+}
+
+float f16_bits_to_f32(uint16_t hb) {
+    const uint32_t sign = (uint32_t)(hb & 0x8000u) << 16, e = (hb >> 10) & 0x1Fu, m = hb & 0x3FFu;
+    float out;
+    if (e == 0) {
+        out = (float)m * (1.0f / 16777216.0f);
+    } else {
+        const uint32_t u = ((e + 112u) << 23) | (m << 13);
+        memcpy(&out, &u, 4);
+    }
+    uint32_t u;
+    memcpy(&u, &out, 4);
+    u |= sign;
+    memcpy(&out, &u, 4);
+    return out;
+}
+
+// Tensor-core weight image (conv_tc.cu): for every (n-tile, 64-channel chunk, tap) one hi slab and one lo slab of
+// [n_tile rows (output channels) x 64 fp16] in the canonical K-major SWIZZLE_128B layout, so that a single 1-D bulk copy
+// drops it into shared memory ready for tcgen05.mma kind::f16.  The weights are multiplied by *scale_out = 2^e chosen so that
+// max|w| lands in [2^13, 2^14) (well inside fp16, and the lo terms of all but negligible weights stay normal numbers);
+// hi = fp16(w * scale), lo = fp16(w * scale - hi).  The image is returned as packed 32-bit words (two fp16 each).
+void build_tc_image_f16(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, int n_tile,
+                        std::vector<float>* img_out, float* scale_out) {
+    float mx = 0.f;
+    for (float v : wp) { const float a = fabsf(v); if (a > mx && a < INFINITY) mx = a; }
+    float scale = 1.f;
+    if (mx > 0.f) {
+        int e = 0;
+        frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+        int sh = 14 - e;                      // mx * 2^sh in [2^13, 2^14)
+        if (sh > 40) sh = 40;
+        if (sh < -40) sh = -40;
+        scale = ldexpf(1.f, sh);
+    }
+    *scale_out = scale;
+    const int n_chunks = (cin + 63) / 64, n_nt = cout_eff / n_tile;   // a partial last chunk is zero-padded
+    const size_t slab = (size_t)n_tile * 32;                 // 32-bit words per hi (or lo) slab: n_tile rows x 128 bytes
+    std::vector<float>& img = *img_out;
+    img.assign((size_t)n_nt * n_chunks * K * 2 * slab, 0.f);
+    for (int nt = 0; nt < n_nt; ++nt)
+        for (int c = 0; c < n_chunks; ++c)
+            for (int k = 0; k < K; ++k) {
+                uint16_t* hi = reinterpret_cast<uint16_t*>(img.data() + (((size_t)nt * n_chunks + c) * K + k) * 2 * slab);
+                uint16_t* lo = hi + 2 * slab;
+                for (int n = 0; n < n_tile; ++n)
+                    for (int col = 0; col < 64; ++col) {
+                        const float x = (c * 64 + col < cin) ? wp[((size_t)k * cin + c * 64 + col) * cout_eff + nt * n_tile + n] * scale : 0.f;
+                        const uint16_t xh = f32_to_f16_bits(x);
+                        const uint16_t xl = f32_to_f16_bits(x - f16_bits_to_f32(xh));
+                        const size_t off = (size_t)n * 64 + ((((col >> 3) ^ (n & 7)) << 3) | (col & 7));   // 16-byte chunk ^ (row & 7)
+                        hi[off] = xh;
+                        lo[off] = xl;
+                    }
+            }
+}
+
+// tf32 variant (rvq_tc.cu codebook slabs): for every (n-tile, 32-channel chunk, tap) one hi slab and one lo
+// slab of [n_tile rows (output channels) x 32 tf32] in the canonical K-major SWIZZLE_128B layout.  hi/lo = 3xTF32 split.
+void build_tc_image_tf32(const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, int n_tile,
+                          std::vector<float>* img_out) {
     const int n_chunks = (cin + 31) / 32, n_nt = cout_eff / n_tile;   // a partial last chunk is zero-padded
     const size_t slab = (size_t)n_tile * 32;                 // floats per hi (or lo) slab
     std::vector<float>& img = *img_out;
@@ -197,7 +276,7 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
     if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, 1)) return FCB_OK;
     const int n_tile = conv_tc_n_tile(cout_eff);
     std::vector<float> img;
-    build_tc_image(wp, K, cin, cout_eff, n_tile, &img);
+    build_tc_image_f16(wp, K, cin, cout_eff, n_tile, &img, &o->tc_scale);
     FCB_TRY(upload(h, img, &o->w_tc));
     o->n_tile = n_tile;
     return FCB_OK;
@@ -402,7 +481,7 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         const int pr = padding_total / 2, pl = padding_total - pr;
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
-    p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile;
+    p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.tc_w_scale = L.tc_scale;
     p.out_clip_stride = (long long)p.T_out * p.C_out;
     const bool tc = h->use_tc && L.n_tile > 0 && L.w_tc && !div_scale;
     FCB_TRY(alloc_f(r, &o.p, (size_t)r.B * p.out_clip_stride));
@@ -460,6 +539,7 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
         sp.y_out = last ? y.p : nullptr;
         sp.skip = view_of(x);
         sp.barrier = h->lstm_barrier;
+        sp.trace = h->lstm_trace;
         sp.B = B; sp.T = T; sp.H = H;
         FCB_CK(launch_lstm_seq(sp, r.st));
         h->launches += 1;
@@ -594,14 +674,14 @@ int pack_tc2d(fcb_handle* h, const std::vector<float>& wp, const std::vector<flo
     std::vector<float> img;
     const int n_tile = conv_tc_n_tile(cout_tc);
     if (cout_tc == cout_eff) {
-        build_tc_image(wp, kt, ck, cout_eff, n_tile, &img);
+        build_tc_image_f16(wp, kt, ck, cout_eff, n_tile, &img, &o->tc_scale);
         o->bias_tc = nullptr;
     } else {
         std::vector<float> wpad((size_t)kt * ck * cout_tc, 0.f), bpad(cout_tc, 0.f);
         for (size_t r = 0; r < (size_t)kt * ck; ++r)
             for (int co = 0; co < cout_eff; ++co) wpad[r * cout_tc + co] = wp[r * cout_eff + co];
         for (int co = 0; co < cout_eff; ++co) bpad[co] = bias[co];
-        build_tc_image(wpad, kt, ck, cout_tc, n_tile, &img);
+        build_tc_image_f16(wpad, kt, ck, cout_tc, n_tile, &img, &o->tc_scale);
         FCB_TRY(upload(h, bpad, &o->bias_tc));
     }
     FCB_TRY(upload(h, img, &o->w_tc));
@@ -788,7 +868,7 @@ int run_conv2d(Run& r, const Act2& in0, const Act2* in1, bool elu, const Conv2W&
         q.elu = p.elu;
         q.T_in = in0.T; q.C_in = p.KF * in0.C;
         q.K = p.KT; q.S = p.ST; q.D = 1; q.pad_l = p.pad_t; q.T_ext = in0.T; q.pad_zero = p.pad_zero;
-        q.w_tc = L.w_tc; q.n_tile = L.n_tile; q.bias = L.bias_tc ? L.bias_tc : L.bias;
+        q.w_tc = L.w_tc; q.n_tile = L.n_tile; q.tc_w_scale = L.tc_scale; q.bias = L.bias_tc ? L.bias_tc : L.bias;
         q.out = o.p; q.T_out = p.T_out; q.C_out = L.cout_tc;
         q.out_clip_stride = (long long)p.T_out * L.cout_tc;
         q.partials = partials;
@@ -990,7 +1070,7 @@ int pack_stft_bases(fcb_handle* h) {
         o.cin = 32; o.cout = cout; o.k = K; o.s = hop / 32;
         std::vector<float> img;
         const int n_tile = conv_tc_n_tile(cout);
-        build_tc_image(wp, K, 32, cout, n_tile, &img);
+        build_tc_image_f16(wp, K, 32, cout, n_tile, &img, &o.tc_scale);
         FCB_TRY(upload(h, img, &o.w_tc));
         FCB_TRY(upload(h, bias, &o.bias));
         o.n_tile = n_tile;
@@ -1012,7 +1092,7 @@ int pack_stft_bases(fcb_handle* h) {
         o.cin = cin; o.cout = cout; o.k = 1; o.s = 1;
         std::vector<float> img;
         const int n_tile = conv_tc_n_tile(cout);
-        build_tc_image(wp, 1, cin, cout, n_tile, &img);
+        build_tc_image_f16(wp, 1, cin, cout, n_tile, &img, &o.tc_scale);
         FCB_TRY(upload(h, img, &o.w_tc));
         FCB_TRY(upload(h, bias, &o.bias));
         o.n_tile = n_tile;
@@ -1027,7 +1107,7 @@ int run_plain_tc(Run& r, const float* x, int T_in, const ConvW& L, int T_out, fl
     ConvParams p{};
     p.in0.x = x; p.in0.clip_stride = (long long)T_in * L.cin;
     p.T_in = T_in; p.C_in = L.cin; p.K = L.k; p.S = L.s; p.D = 1; p.pad_l = 0; p.T_ext = T_in; p.pad_zero = 1;
-    p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.bias = L.bias;
+    p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.tc_w_scale = L.tc_scale; p.bias = L.bias;
     p.out = out; p.T_out = T_out; p.C_out = L.cout; p.out_clip_stride = (long long)T_out * L.cout;
     int np = 0;
     FCB_CK(launch_conv_tc(p, r.B, r.st, &np));
@@ -1246,7 +1326,7 @@ int fcb_finalize(fcb_handle* h) {
             const float* e = emb->data.data() + (size_t)q * c.codebook_size * D;
             for (int k = 0; k < c.codebook_size; ++k)
                 for (int d = 0; d < D; ++d) wp[(size_t)d * c.codebook_size + k] = e[(size_t)k * D + d];
-            build_tc_image(wp, 1, D, c.codebook_size, RVQ_TC_N, &img);
+            build_tc_image_tf32(wp, 1, D, c.codebook_size, RVQ_TC_N, &img);
             all.insert(all.end(), img.begin(), img.end());
         }
         FCB_TRY(upload(h, all, &h->embed_tc));
@@ -1258,6 +1338,11 @@ int fcb_finalize(fcb_handle* h) {
     FCB_CK(cudaMemset(h->err_flag, 0, sizeof(int)));
     FCB_CK(cudaMalloc((void**)&h->lstm_barrier, 64 * sizeof(unsigned)));
     h->dev_allocs.push_back(h->lstm_barrier);
+    if (getenv("FCB_LSTM_TRACE")) {
+        FCB_CK(cudaMallocManaged((void**)&h->lstm_trace, LSTM_TRACE_ITEMS * 8 * sizeof(unsigned long long)));
+        FCB_CK(cudaMemset(h->lstm_trace, 0, LSTM_TRACE_ITEMS * 8 * sizeof(unsigned long long)));
+        h->dev_allocs.push_back(h->lstm_trace);
+    }
     FCB_CK(launch_code_norms(h->embed, h->cnorm, c.num_quantizers * c.codebook_size, D, 0));
     h->launches++;
     FCB_CK(cudaDeviceSynchronize());
@@ -1666,6 +1751,18 @@ const char* fcb_last_error(const fcb_handle* h) { return h ? h->err.c_str() : "n
 
 void fcb_destroy(fcb_handle* h) {
     if (!h) return;
+    if (h->lstm_trace) {      // PROFILING ONLY: the last LSTM layer launch's per-item stamps of CTA 0 (ns, relative)
+        cudaDeviceSynchronize();
+        const unsigned long long* tr = h->lstm_trace;
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < LSTM_TRACE_ITEMS * 8; ++i) if (tr[i] && tr[i] < t0) t0 = tr[i];
+        fprintf(stderr, "LSTM trace (CTA 0, ns since first stamp): item | hs_empty poll_ok | h_in fma_done red_out | red_in published\n");
+        for (int i = 0; i < LSTM_TRACE_ITEMS; ++i) {
+            fprintf(stderr, "item %3d |", i);
+            for (int e = 0; e < 7; ++e) fprintf(stderr, " %8lld", tr[i * 8 + e] ? (long long)(tr[i * 8 + e] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+    }
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->ev_created)
         for (int i = 0; i < FCB_NUM_PHASES; ++i)

@@ -58,7 +58,9 @@ struct LstmSeqParams {
     InView skip;          // the SLSTM input (normalised on load) when y_out != nullptr
     unsigned* barrier;    // device counter for the per-step grid barrier (zeroed by the launcher)
     int B, T, H;
+    unsigned long long* trace;   // PROFILING ONLY (env FCB_LSTM_TRACE): [LSTM_TRACE_ITEMS][8] %globaltimer stamps of CTA 0, or nullptr
 };
+constexpr int LSTM_TRACE_ITEMS = 64, LSTM_TRACE_FIRST_STEP = 100;
 cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st);
 int lstm_pick_units(int H);
 

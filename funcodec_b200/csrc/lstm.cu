@@ -17,6 +17,7 @@
 //     shuffles + one shared-memory pass, and UNITS*8 threads do the cell update.
 // Latency-bound by construction (T' dependent steps); FLOPs = 2*B*T*4H*H per layer.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -25,11 +26,25 @@
 namespace fcb {
 
 constexpr int LSTM_GB_MAX = 8;    // clips per work item (accumulator tile): 8, or 4 for small batches (more items in flight)
-constexpr int LSTM_NBUF = 2;      // h ring depth
+constexpr int LSTM_NBUF_MAX = 8;  // h ring depth: 2 .. 8 slots, as many as shared memory holds (more independent clip groups in flight)
 constexpr int LSTM_THREADS = 416; // 8 compute warps, 2 x 2 cell warps (alternate items), 1 loader warp
 constexpr int LSTM_MAX_GROUPS = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// PROFILING ONLY: CTA 0 stamps event e of work item i (items of the steps from LSTM_TRACE_FIRST_STEP on)
+#define LSTM_TRACE(i, e)                                                                             \
+    do {                                                                                             \
+        if (p.trace && blockIdx.x == 0) {                                                            \
+            const int ti__ = (i) - LSTM_TRACE_FIRST_STEP * ng;                                       \
+            if (ti__ >= 0 && ti__ < LSTM_TRACE_ITEMS) p.trace[ti__ * 8 + (e)] = gtimer();            \
+        }                                                                                            \
+    } while (0)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -48,7 +63,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
 template <int UNITS, int GB>
-__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p) {
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
     constexpr int NSLICE = 8 * KS_PER_WARP;    // K slices per CTA (interleaved in groups of 4 k)
@@ -56,14 +71,14 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     extern __shared__ __align__(128) float smem[];
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                                   // [H][COLS]
-    float* Hs = Ws + (size_t)H * COLS;                  // [LSTM_NBUF][GB][H]
-    float* red = Hs + LSTM_NBUF * GB * H;          // [2][8 warps][GB][COLS]
+    float* Hs = Ws + (size_t)H * COLS;                  // [nbuf][GB][H]
+    float* red = Hs + nbuf * GB * H;               // [2][8 warps][GB][COLS]
     float* cS = red + 2 * 8 * GB * COLS;           // [ng][GB][UNITS] cell state
     const int ng = (B + GB - 1) / GB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * GB * UNITS + 3) & ~3));
-    uint64_t* hs_full = bars;                           // [NBUF] tx
-    uint64_t* hs_empty = hs_full + LSTM_NBUF;           // [NBUF] 8 compute-warp arrivals
-    uint64_t* red_full = hs_empty + LSTM_NBUF;          // [2]    8 compute-warp arrivals
+    uint64_t* hs_full = bars;                           // [nbuf] tx
+    uint64_t* hs_empty = hs_full + nbuf;                // [nbuf] 8 compute-warp arrivals
+    uint64_t* red_full = hs_empty + nbuf;               // [2]    8 compute-warp arrivals
     uint64_t* red_empty = red_full + 2;                 // [2]    64 cell-thread arrivals
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = blockIdx.x * UNITS;
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
     for (int e = tid; e < ng * GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
     if (tid == 0) {
-        for (int i = 0; i < LSTM_NBUF; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
+        for (int i = 0; i < nbuf; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
         tc::mbar_fence_init();
     }
@@ -93,8 +108,9 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         const int slice = warp * KS_PER_WARP + ks;
         for (int i = ng; i < n_items; ++i) {            // items with t == 0 need no recurrent term
             const int n = i - ng;
-            const int hb = n % LSTM_NBUF, rb = n & 1;
-            tc::mbar_wait(hs_full + hb, (uint32_t)((n / LSTM_NBUF) & 1));
+            const int hb = n % nbuf, rb = n & 1;
+            tc::mbar_wait(hs_full + hb, (uint32_t)((n / nbuf) & 1));
+            if (tid == 0) LSTM_TRACE(i, 2);
             const float* Hc = Hs + hb * GB * H;
             // packed fp32 FMAs (FFMA2): even-k and odd-k partial sums live in the two halves of a register pair
             float2 acc2[4][GB];
@@ -128,6 +144,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
 #pragma unroll
                 for (int bb = 0; bb < GB; ++bb) acc[gg][bb] = acc2[gg][bb].x + acc2[gg][bb].y;
             __syncwarp();
+            if (tid == 0) LSTM_TRACE(i, 3);
             if (lane == 0) tc::mbar_arrive(hs_empty + hb);           // this warp is done with the h slot
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
@@ -148,6 +165,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(red_full + rb);
+            if (tid == 0) LSTM_TRACE(i, 4);
         }
     } else if (warp < 12) {
         // ================================================================ cell warps: two pairs take alternate items
@@ -176,6 +194,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             if (t > 0) {
                 const int n = i - ng, rb = n & 1;
                 tc::mbar_wait_backoff(red_full + rb, (uint32_t)((n >> 1) & 1), 64);
+                if (ftid == 0) LSTM_TRACE(i, 5);
                 if (mine) {
                     const float* rd = red + (size_t)rb * 8 * GB * COLS;
                     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -213,6 +232,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             else asm volatile("bar.sync 4, 64;" ::: "memory");
             if (ftid == 0 && t + 1 < T)
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier + g), "r"(1u) : "memory");
+            if (ftid == 0) LSTM_TRACE(i, 6);
             gxv = gx_next;
         }
     } else {
@@ -220,12 +240,14 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         if (lane == 0) {
             for (int i = ng; i < n_items; ++i) {
                 const int t = i / ng, g = i - t * ng;
-                const int n = i - ng, hb = n % LSTM_NBUF;
+                const int n = i - ng, hb = n % nbuf;
                 const int b0 = g * GB;
                 const int nb = min(GB, B - b0);
-                tc::mbar_wait_backoff(hs_empty + hb, (uint32_t)((n / LSTM_NBUF) & 1) ^ 1, 64);
+                tc::mbar_wait_backoff(hs_empty + hb, (uint32_t)((n / nbuf) & 1) ^ 1, 64);
+                LSTM_TRACE(i, 0);
                 unsigned seen = ld_acquire_u32(p.barrier + g);
                 while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
+                LSTM_TRACE(i, 1);
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
                 float* dst = Hs + hb * GB * H;
@@ -236,11 +258,21 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
 }
 
-size_t lstm_seq_smem_bytes(int H, int B, int units, int gb) {
+size_t lstm_seq_smem_bytes(int H, int B, int units, int gb, int nbuf = 2) {
     const int ng = (B + gb - 1) / gb;
     const size_t cs = ((size_t)ng * gb * units + 3) & ~(size_t)3;
-    return ((size_t)H * 4 * units + (size_t)LSTM_NBUF * gb * H + 2 * 8 * 4 * units * gb + cs) * sizeof(float) +
-           (2 * LSTM_NBUF + 4) * 8 + 64;
+    return ((size_t)H * 4 * units + (size_t)nbuf * gb * H + 2 * 8 * 4 * units * gb + cs) * sizeof(float) +
+           (2 * nbuf + 4) * 8 + 64;
+}
+
+// h ring depth: one slot per independent clip group (their barrier / broadcast latencies overlap), 2 .. LSTM_NBUF_MAX,
+// limited by shared memory (H = 1024: the 128 KB W_hh slice leaves room for 2 slots of 32 KB)
+static int lstm_pick_nbuf(int H, int B, int units, int gb) {
+    const int ng = (B + gb - 1) / gb;
+    int nbuf = ng < 2 ? 2 : (ng > LSTM_NBUF_MAX ? LSTM_NBUF_MAX : ng);
+    while (nbuf > 2 && lstm_seq_smem_bytes(H, B, units, gb, nbuf) > 220 * 1024) --nbuf;
+    if (const char* v = getenv("FCB_LSTM_NBUF")) { const int f = atoi(v); if (f >= 2 && f <= nbuf) nbuf = f; }   // experiments
+    return nbuf;
 }
 
 // clip-group size: 8.  (4-clip groups for small batches were measured: no gain, the per-item fixed costs dominate.)
@@ -255,7 +287,8 @@ int lstm_pick_units(int H) {
 
 template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
-    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB);
+    int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
+    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf);
     auto kern = lstm_seq_kernel<UNITS, GB>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
@@ -267,7 +300,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     dim3 grid(p.H / UNITS), block(LSTM_THREADS);
     LstmSeqParams pc = p;
-    void* args[] = {&pc};
+    void* args[] = {&pc, &nbuf};
     return cudaLaunchCooperativeKernel((void*)kern, grid, block, args, smem, st);
 }
 

@@ -76,6 +76,15 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t desc_a, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all previously issued MMAs of this thread -> arrive on the mbarrier when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -139,6 +148,30 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            | (0u << 15) | (0u << 16)      // a_major = K, b_major = K
            | ((uint32_t)(N >> 3) << 17)   // n_dim
            | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, dense, no negate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4)                      // c_format = F32
+           | (0u << 7)                    // a_format = F16
+           | (0u << 10)                   // b_format = F16
+           | (0u << 15) | (0u << 16)      // a_major = K, b_major = K
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// FP16 split of two (pre-scaled) fp32 values: hi = fp16(x) round-to-nearest, lo = fp16(x - hi) (x - hi is exact in fp32);
+// element 0 in the low half.  Saturating conversions: |x| beyond the fp16 range clamps instead of producing inf.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float f0, f1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f0), "=f"(f1) : "r"(hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f1), "f"(x0 - f0));
+}
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // 3xTF32 split: hi = x with the low 13 mantissa bits cleared after round-to-nearest on the tf32 grid,

@@ -272,10 +272,11 @@ class OracleEncodec:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], ratios: Sequence[int], sample_rate: int = 16000,
                  lstm_layers: int = 2, audio_normalize: bool = True, dtype=torch.float32,
-                 manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01):
+                 manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01, device="cpu"):
         self.segment_dur = segment_dur
         self.overlap_ratio = overlap_ratio
-        sd = {k: v.detach().to("cpu", dtype) if v.is_floating_point() else v.detach().cpu()
+        # device != "cpu" is only used by bench.py's labelled CUDA-eager context leg (same ATen ops on the GPU)
+        sd = {k: v.detach().to(device, dtype) if v.is_floating_point() else v.detach().to(device)
               for k, v in state_dict.items()}
         self.enc = sub_dict(sd, "encoder.")
         self.dec = sub_dict(sd, "decoder.")

@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_clips, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_clips", [5, 2, 1])
+@pytest.mark.parametrize("n_clips", [5, 4, 2, 1])
 def test_sharded_codec_world2(n_clips):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
@@ -65,3 +65,52 @@ def test_shard_bounds():
     assert shard_bounds(512, 8) == [(64 * i, 64 * i + 64) for i in range(8)]
     assert shard_bounds(5, 2) == [(0, 3), (3, 5)]
     assert shard_bounds(1, 2) == [(0, 1), (1, 1)]
+
+
+def _shared_host_worker(rank, world, port, n_clips, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from funcodec_b200 import get_config, init_state_dict
+    from funcodec_b200.parallel import SharedHostBatch
+    from oracle.encodec_oracle import OracleEncodec
+    cfg = get_config("tiny_ds40")
+    oracle = OracleEncodec(init_state_dict(cfg, 3), cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    L = 40 * 9
+    tf = cfg.frames(L)
+    shb = SharedHostBatch(f"fcb_test_{port}", n_clips, L, cfg.num_quantizers, tf, rank, world, create=(rank == 0))
+    dist.barrier()
+    shb.map()
+    if rank == 0:
+        g = torch.Generator().manual_seed(42)
+        shb.wav.copy_(0.1 * torch.randn(n_clips, L, generator=g))
+    dist.barrier()
+    lo, hi = shb.shard()
+    r = oracle.inference(shb.wav[lo:hi].clone(), need_recon=True)
+    shb.codes[rank].copy_(r["code_indices"][0])
+    shb.recon[lo:hi].copy_(r["recon_speech"])
+    dist.barrier()
+    if rank == 0:
+        ref = oracle.inference(shb.wav.clone(), need_recon=True)
+        codes = shb.codes.permute(1, 0, 2, 3).reshape(cfg.num_quantizers, n_clips, tf)
+        ret.put(bool(torch.equal(codes, ref["code_indices"][0]) and torch.allclose(shb.recon, ref["recon_speech"], atol=1e-6)))
+    dist.barrier()
+    shb.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_batch_world2():
+    """SharedHostBatch: one /dev/shm batch mapped by both ranks, each rank reads its shard and writes its results in place
+    (the cudaHostRegister step only happens when CUDA is available)."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_shared_host_worker, args=(r, 2, port, 4, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
