@@ -78,3 +78,46 @@ def test_segment_plan_matches_the_reference_arithmetic():
         assert [plan.tail_frames[i] * hop for i in range(n_tail)] == dec[plan.n_full:]
         assert plan.total_frames == sum(d // hop for d in dec)
     assert seen_ok > 50 and seen_bad > 10, (seen_ok, seen_bad)
+
+
+def test_packed_codes_format_roundtrip(tmp_path):
+    """funcodec_b200/codes_format.py: 10-bit packed container <-> codecs.txt, bit-exact both ways, ragged
+    lengths, several codebook sizes, LSB-first packing order, corruption is detected."""
+    import io
+    from funcodec_b200 import codes_format as CF
+    rng = np.random.default_rng(0)
+    assert CF.bits_for_codebook(1024) == 10 and CF.bits_for_codebook(1000) == 10 and CF.bits_for_codebook(2) == 1
+    # known answer: indices 1 and 2 at 10 bits, LSB first -> 0x01, 0x08 (bit 11), 0x00
+    assert CF.pack_indices(np.array([[1, 2]]), 10) == bytes([0x01, 0x08, 0x00])
+    for K in (1024, 64, 2, 4096, 1000):
+        buf = io.BytesIO()
+        items = []
+        for i, (nq, T) in enumerate([(32, 250), (8, 1), (1, 17), (4, 0)]):
+            c = rng.integers(0, K, size=(nq, T))
+            items.append((f"utt-{K}-{i}", c))
+            CF.write_record(buf, items[-1][0], c, K)
+        buf.seek(0)
+        got = list(CF.read_records(buf))
+        assert [k for k, _ in got] == [k for k, _ in items]
+        for (_, a), (_, b) in zip(got, items):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    # codecs.txt -> packed -> codecs.txt is the identity on the parsed arrays; 10 bits/index vs JSON
+    txt = os.path.join(tmp_path, "codecs.txt")
+    codes = torch.from_numpy(rng.integers(0, 1024, size=(32, 3, 250)))
+    with open(txt, "wt") as f:
+        for b in range(3):
+            f.write(P.format_indices_line(f"u{b}", [codes], b, 250 - 10 * b))
+    n, tbytes, pbytes = CF.codecs_txt_to_packed(txt, os.path.join(tmp_path, "codes.fcb"))
+    assert n == 3 and pbytes < tbytes / 3
+    assert CF.packed_to_codecs_txt(os.path.join(tmp_path, "codes.fcb"), os.path.join(tmp_path, "back.txt")) == 3
+    a = [P.parse_indices_line(l) for l in open(txt)]
+    b = [P.parse_indices_line(l) for l in open(os.path.join(tmp_path, "back.txt"))]
+    assert all(ka == kb and np.array_equal(xa, xb) for (ka, xa), (kb, xb) in zip(a, b))
+    import pytest
+    with pytest.raises(ValueError):
+        list(CF.read_records(io.BytesIO(b"XXXX" + bytes(8))))
+    with pytest.raises(ValueError):
+        CF.pack_indices(np.array([[1024]]), 10)
+    raw = open(os.path.join(tmp_path, "codes.fcb"), "rb").read()
+    with pytest.raises(ValueError):
+        list(CF.read_records(io.BytesIO(raw[:-3])))
