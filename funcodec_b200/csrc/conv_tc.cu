@@ -64,7 +64,7 @@ struct TcSmemLayout {
     int a_stage;       // bytes per A stage (hi + lo)
     int b_stage;       // bytes per B stage (hi + lo)
     int na, nb;        // ring depths
-    int off_b, off_bar, total;
+    int off_b, off_stg, off_bar, total;
 };
 
 __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb) {
@@ -75,7 +75,8 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     L.b_stage = 2 * n_tile * 128;
     L.na = na; L.nb = nb;
     L.off_b = na * L.a_stage;
-    L.off_bar = L.off_b + nb * L.b_stage;
+    L.off_stg = L.off_b + nb * L.b_stage;                  // epilogue staging: 4 warps x (32 rows x 128 B), swizzled
+    L.off_bar = L.off_stg + 4 * 4096;
     L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
     return L;
 }
@@ -177,7 +178,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 const uint32_t par = aphase ^ 1;
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
-                if (chunk < n_chunks) {
+                if (p.dbg & 512) {
+                    if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);
+                } else if (chunk < n_chunks) {
                 int c = chunk * TC_KC + jchunk * 4;
                 bool c_ok = c < C_in;
                 const float* xu0 = x0;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
                 fence_proxy_async_smem();
                 } else {
-                    mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
+                    if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
                 }
                 mbar_arrive(a_full + as);
                 as += step;
@@ -283,9 +286,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 int chunk = 0, ph = 0;                                 // chunk: 64-channel stage chunk
                 for (int unit = 0; unit < n_units; ++unit) {
                     for (int k = ph; k < K; k += S) {
-                        if (!w_resident) mbar_wait_backoff(b_empty + bs, bphase ^ 1, 64);
-                        mbar_arrive_expect_tx(b_full + bs, bytes);
-                        bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+                        if (!w_resident) { if (p.dbg & 64) mbar_wait(b_empty + bs, bphase ^ 1); else mbar_wait_backoff(b_empty + bs, bphase ^ 1, 64); }
+                        if (p.dbg & 256) { mbar_arrive(b_full + bs); }
+                        else {
+                            mbar_arrive_expect_tx(b_full + bs, bytes);
+                            bulk_g2s(smB + bs * L.b_stage, wbase + ((long long)chunk * K + k) * bytes, bytes, b_full + bs);
+                        }
                         if (++bs == nb_stages) { bs = 0; bphase ^= 1; }
                     }
                     if (++ph == S) { ph = 0; ++chunk; }
@@ -374,8 +380,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             for (int g = 0; g < n_groups; ++g, ++gcount) {
                 const int buf = (int)(gcount & 1);
                 const bool last = (g == n_groups - 1);
-                mbar_wait_backoff(acc_full + buf, (gcount >> 1) & 1, 128);
+                if (p.dbg & 64) mbar_wait(acc_full + buf, (gcount >> 1) & 1); else mbar_wait_backoff(acc_full + buf, (gcount >> 1) & 1, 128);
                 tc_fence_after_sync();
+                if (!(p.dbg & 128))
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                     uint32_t v[32];
@@ -391,9 +398,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     }
                     if (!last) {
                         tmem_st_32x32b_x32(tot_base + (uint32_t)c0, v);
+                    } else if (!FREQ) {
+                        // bias + statistics in registers, then through a swizzled staging tile so that every global store
+                        // instruction of the warp writes whole rows (4 rows x 128 B = 4 L1 wavefronts instead of 32)
+                        uint8_t* stg = smem_raw + L.off_stg + quad * 4096;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (c0 + j < N_TILE) {
+                                float4 o;
+                                o.x = fmaf(__uint_as_float(v[j + 0]), out_scale, __ldg(bias + c0 + j + 0));
+                                o.y = fmaf(__uint_as_float(v[j + 1]), out_scale, __ldg(bias + c0 + j + 1));
+                                o.z = fmaf(__uint_as_float(v[j + 2]), out_scale, __ldg(bias + c0 + j + 2));
+                                o.w = fmaf(__uint_as_float(v[j + 3]), out_scale, __ldg(bias + c0 + j + 3));
+                                if (row_ok) {
+                                    s += (o.x + o.y) + (o.z + o.w);
+                                    ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
+                                }
+                                *reinterpret_cast<float4*>(stg + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) = o;
+                            }
+                        }
+                        __syncwarp();
+                        if (!(p.dbg & 8)) {
+                            const int cc = lane & 7;
+                            if (c0 + cc * 4 < N_TILE) {
+                                float* obase = p.out + (long long)tl.b * p.out_clip_stride + (long long)tl.nt * N_TILE + c0 + cc * 4;
+                                const int trow0 = tl.tt * TC_M + quad * 32;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int rr = i * 4 + (lane >> 3);
+                                    if (trow0 + rr < p.T_out)
+                                        *reinterpret_cast<float4*>(obase + (long long)(trow0 + rr) * p.C_out) =
+                                            *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                                }
+                            }
+                        }
+                        __syncwarp();
                     } else if (row_ok) {
                         int ph = 0, cch = 0;                          // FREQ: phase and channel of output column c0 + j
-                        if (FREQ) {
+                        {
                             const int co = tl.nt * N_TILE + c0;
                             ph = co / p.fq.Cc;
                             cch = co - ph * p.fq.Cc;
@@ -410,8 +452,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                                 s += (o.x + o.y) + (o.z + o.w);
                                 ss = fmaf(o.x, o.x, ss); ss = fmaf(o.y, o.y, ss); ss = fmaf(o.z, o.z, ss); ss = fmaf(o.w, o.w, ss);
                                 if (p.dbg & 8) {
-                                } else if (!FREQ) {
-                                    *reinterpret_cast<float4*>(orow + c0 + j) = o;
                                 } else {
                                     // phase (pf, pt) of a transposed conv lands on row f_out*FR + pf, column t*TR + pt
                                     const int pf = ph / p.fq.TR, pt = ph - pf * p.fq.TR;

@@ -183,13 +183,24 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             }
             return v;
         };
+        auto load_skip = [&](int i) -> float {       // raw SLSTM input of this thread's (clip, unit) for item i (last layer only)
+            float v = 0.f;
+            if (p.y_out && i < n_items) {
+                const int t = i / ng, g = i - t * ng;
+                const int b = g * GB + fbb;
+                if (active && b < B) v = __ldcs(p.skip.x + (long long)b * p.skip.clip_stride + ((long long)(p.skip.row_off + t)) * H + j0 + fu);
+            }
+            return v;
+        };
         float4 gxv = load_gx(pair);
+        float skv = load_skip(pair);
         for (int i = pair; i < n_items; i += 2) {
             const int t = i / ng, g = i - t * ng;
             const int b0 = g * GB;
             const int nb = min(GB, B - b0);
             const bool mine = active && fbb < nb;
             const float4 gx_next = load_gx(i + 2);               // in flight while this item is reduced
+            const float sk_next = load_skip(i + 2);
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
             if (t > 0) {
                 const int n = i - ng, rb = n & 1;
@@ -207,33 +218,37 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 }
                 tc::mbar_arrive(red_empty + rb);
             }
+            float h = 0.f;
+            long long o = 0;
             if (mine) {
                 const int b = b0 + fbb, j = j0 + fu;
                 const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
                 float* cp = cS + (g * GB + fbb) * UNITS + fu;
                 const float c = fg * (*cp) + ig * gg;
                 *cp = c;
-                const float h = og * tanhf(c);
-                const long long o = ((long long)b * T + t) * H + j;
+                h = og * tanhf(c);
+                o = ((long long)b * T + t) * H + j;
                 __stcg(p.h_seq + o, h);
-                if (p.y_out) {
-                    const long long xo = (long long)b * p.skip.clip_stride + ((long long)(p.skip.row_off + t)) * H + j;
-                    float xv = p.skip.x[xo];
-                    if (p.skip.stats) {
-                        const float mean = p.skip.stats[2 * b], rstd = p.skip.stats[2 * b + 1];
-                        const float a = rstd * p.skip.gamma[j];
-                        xv = fmaf(xv, a, p.skip.beta[j] - a * mean);
-                    }
-                    p.y_out[o] = h + xv;
-                }
             }
-            // publish h_t of this group: the pair's stores -> named barrier -> one gpu-scope release add
+            // publish h_t of this group FIRST (it heads every other CTA's critical path): the pair's stores -> named barrier ->
+            // one gpu-scope release add; the skip output below is off the recurrence
             if (pair == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
             else asm volatile("bar.sync 4, 64;" ::: "memory");
             if (ftid == 0 && t + 1 < T)
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier + g), "r"(1u) : "memory");
             if (ftid == 0) LSTM_TRACE(i, 6);
+            if (mine && p.y_out) {
+                const int b = b0 + fbb, j = j0 + fu;
+                float xv = skv;
+                if (p.skip.stats) {
+                    const float mean = p.skip.stats[2 * b], rstd = p.skip.stats[2 * b + 1];
+                    const float a = rstd * p.skip.gamma[j];
+                    xv = fmaf(xv, a, p.skip.beta[j] - a * mean);
+                }
+                p.y_out[o] = h + xv;
+            }
             gxv = gx_next;
+            skv = sk_next;
         }
     } else {
         // ================================================================ loader warp
@@ -275,8 +290,14 @@ static int lstm_pick_nbuf(int H, int B, int units, int gb) {
     return nbuf;
 }
 
-// clip-group size: 8.  (4-clip groups for small batches were measured: no gain, the per-item fixed costs dominate.)
-static int lstm_pick_gb(int B) { (void)B; return 8; }
+// clip-group size: 8 clips per work item; 4 when that yields at least 4 independent groups for a small batch (B <= 16): a
+// timestep is one group's dependency chain (bulk copy -> gate GEMM -> cell -> publish -> poll), which only OTHER groups can hide,
+// and the h ring now holds one slot per group (round 1 measured "no gain" with 4-clip groups on a 2-slot ring).
+static int lstm_pick_gb(int B) {
+    int gb = (B > 4 && B <= 16) ? 4 : 8;
+    if (const char* v = getenv("FCB_LSTM_GB")) { const int f = atoi(v); if (f == 4 || f == 8) gb = f; }   // experiments
+    return gb;
+}
 
 int lstm_pick_units(int H) {
     // largest slice that fits shared memory while keeping >= 96 CTAs busy when H allows it
