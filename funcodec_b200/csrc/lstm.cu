@@ -290,11 +290,12 @@ static int lstm_pick_nbuf(int H, int B, int units, int gb) {
     return nbuf;
 }
 
-// clip-group size: 8 clips per work item; 4 when that yields at least 4 independent groups for a small batch (B <= 16): a
-// timestep is one group's dependency chain (bulk copy -> gate GEMM -> cell -> publish -> poll), which only OTHER groups can hide,
-// and the h ring now holds one slot per group (round 1 measured "no gain" with 4-clip groups on a 2-slot ring).
+// clip-group size: 8 clips per work item.  4-clip groups (4 independent chains for B = 16) were measured twice: on the 2-slot
+// ring of round 1 (no gain) and with one ring slot per group (r2d: 3.67 vs 3.32 ms per SLSTM at config 2) -- the per-item
+// fixed costs (poll, bulk copy, reduction, publish) outweigh the shorter gate GEMM.
 static int lstm_pick_gb(int B) {
-    int gb = (B > 4 && B <= 16) ? 4 : 8;
+    (void)B;
+    int gb = 8;
     if (const char* v = getenv("FCB_LSTM_GB")) { const int f = atoi(v); if (f == 4 || f == 8) gb = f; }   // experiments
     return gb;
 }
