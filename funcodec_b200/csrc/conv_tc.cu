@@ -37,6 +37,7 @@
 // 32/cin frequency taps (cin < 32) or a 32-channel slice of one tap; everything downstream of the producers (weight
 // slabs [tap kt][cg][co], MMA issue, folding) is the 1-D machinery.  The epilogue scatters the phases of a transposed
 // conv (co -> (pf, pt, channel)) and can store fewer channels than the padded n-tile (the 32 -> 3 output conv).
+#include <cuda.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_sm100.cuh"
@@ -48,7 +49,8 @@ using namespace tc;
 
 constexpr int TC_M = 128;          // time rows per tile
 constexpr int TC_KC = 32;          // channels per producer unit (half of a 128-byte fp16 swizzle row)
-constexpr int TC_THREADS = 704;    // 16 producer warps (2 groups), copy warp, MMA warp, 4 accumulator warps
+constexpr int TC_THREADS = 736;    // 16 producer warps (2 groups), copy warp, MMA warp, 4 accumulator warps, raw-tile TMA warp
+constexpr int TC_RAW_MAX = 8;      // raw activation ring (TMA-staged units): at most 8 slots
 constexpr int TC_PROD = 256;       // producer threads per group (one unit)
 constexpr int TC_GROUP_MMAS = 48;  // target number of tcgen05.mma chained in TMEM before the fp32 fold
 
@@ -64,10 +66,12 @@ struct TcSmemLayout {
     int a_stage;       // bytes per A stage (hi + lo)
     int b_stage;       // bytes per B stage (hi + lo)
     int na, nb;        // ring depths
-    int off_b, off_stg, off_bar, total;
+    int nraw, raw_slot, raw_in1, raw_cf;   // raw activation ring: slots, bytes per slot, offsets of in1 / coefficients in a slot
+    int off_b, off_stg, off_raw, off_bar, total;
 };
 
-__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb) {
+__host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int na, int nb, int nraw = 0, int raw_pitch = 128,
+                                                   int has1 = 0) {
     TcSmemLayout L;
     const int qmax = (K - 1) / S;
     L.a_rows = ((TC_M + qmax + 7) / 8) * 8;
@@ -76,8 +80,14 @@ __host__ __device__ inline TcSmemLayout tc_layout(int K, int S, int n_tile, int 
     L.na = na; L.nb = nb;
     L.off_b = na * L.a_stage;
     L.off_stg = L.off_b + nb * L.b_stage;                  // epilogue staging: 4 warps x (32 rows x 128 B), swizzled
-    L.off_bar = L.off_stg + 4 * 4096;
-    L.total = L.off_bar + 8 * (2 * na + 2 * nb + 4) + 96;
+    // raw slot: [in0 rows][in1 rows][a0 | b0 | a1 | b1 coefficient slices of the unit's 32 channels (4 x 128 B)]
+    L.nraw = nraw;
+    L.raw_in1 = L.a_rows * raw_pitch;
+    L.raw_cf = (1 + has1) * L.a_rows * raw_pitch;
+    L.raw_slot = (L.raw_cf + 512 + 127) / 128 * 128;
+    L.off_raw = L.off_stg + 4 * 4096;
+    L.off_bar = L.off_raw + nraw * L.raw_slot;
+    L.total = L.off_bar + 8 * (2 * na + 2 * nb + 16 + 2 * TC_RAW_MAX) + 96;
     return L;
 }
 
@@ -101,14 +111,18 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 
 template <int N_TILE, bool FREQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles, const int w_resident, const int group_mmas) {
+                                                                 const int n_tiles, const int w_resident, const int group_mmas,
+                                                                 const int nraw, const __grid_constant__ CUtensorMap tm0,
+                                                                 const __grid_constant__ CUtensorMap tm1) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
-    constexpr uint32_t TMEM_COLS = (3 * BUF_COLS <= 128) ? 128 : (3 * BUF_COLS <= 256 ? 256 : 512);
+    constexpr uint32_t TMEM_COLS = 512;                          // the whole TMEM: one CTA per SM
+    constexpr int ACC_MAX = 8;                                   // accumulator ring: up to 8 tiles between MMA issue and epilogue
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages);
+    const int raw_pitch = (C_in < TC_KC ? C_in : TC_KC) * 4;         // bytes per row of a raw (TMA-staged) unit
+    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, nraw, raw_pitch, has1 ? 1 : 0);
     const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
     const int n_sc = (n_chunks + 1) >> 1;                 // 64-channel stage chunks
     const bool split = n_chunks > 1;                      // both producer groups fill one stage (32 channels each)
@@ -125,15 +139,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     uint64_t* a_empty = a_full + na_stages;        // [na]   tcgen05.commit
     uint64_t* b_full = a_empty + na_stages;        // [nb]   expect_tx
     uint64_t* b_empty = b_full + nb_stages;        // [nb]   tcgen05.commit
-    uint64_t* acc_full = b_empty + nb_stages;      // [2]    tcgen05.commit
-    uint64_t* acc_empty = acc_full + 2;            // [2]    128 accumulator-warp arrivals
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_full = b_empty + nb_stages;      // [ACC_MAX] tcgen05.commit
+    uint64_t* acc_empty = acc_full + ACC_MAX;      // [ACC_MAX] 128 accumulator-warp arrivals
+    uint64_t* raw_full = acc_empty + ACC_MAX;      // [TC_RAW_MAX] expect_tx (TMA tile + coefficient slices)
+    uint64_t* raw_empty = raw_full + TC_RAW_MAX;   // [TC_RAW_MAX] 256 arrivals of the consuming producer group
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_empty + TC_RAW_MAX);
+    uint8_t* smR = smem_raw + L.off_raw;
+    // TMA-staged units (nraw > 0, 1-D layers): an INTERIOR tile needs only rows inside [0, rows covered by the tensor map) -- no
+    // reflection, no zero padding -- so its units arrive as dense [a_rows][32 channel] boxes through the raw ring; the first / last
+    // tiles of a clip keep the per-thread global loads (the index map lives there).  Units of a tile in ring order:
+    // stage-major, half-minor; every role derives the slot from the same running count.
+    const int units_per_tile = n_chunks * S;
+    const int tq_rows = p.T_in / S;                                    // rows per phase the tensor map exposes
+    auto tile_interior = [&](int t0) -> bool {
+        if (nraw == 0) return false;
+        const int lo = t0 * S - p.pad_l;                                // first / last input row a valid output of the tile needs
+        const int hi = (t0 + TC_M - 1) * S - p.pad_l + (K - 1);
+        return lo >= 0 && hi < tq_rows * S && t0 + TC_M <= p.T_out;
+    };
+    // accumulator ring depth.  The MMA -> commit -> epilogue -> release hand-off costs ~2000 cycles per tile pair (measured: the
+    // pure barrier skeleton of the small-tile layers), so layers whose tile is one accumulation group keep up to 8 tiles in
+    // flight; layers that fold groups (deep K) ping-pong between up to 3 accumulators next to the running totals.
+    const int acc_fit = (int)TMEM_COLS / BUF_COLS;
+    const int n_acc = n_groups == 1 ? (acc_fit < ACC_MAX ? acc_fit : ACC_MAX) : (acc_fit - 1 < 3 ? acc_fit - 1 : 3);
     double* red = reinterpret_cast<double*>(tmem_ptr + 2);       // [4][2] statistics scratch
 
     if (tid == 0) {
         for (int i = 0; i < na_stages; ++i) { mbar_init(a_full + i, split ? 2 * TC_PROD : TC_PROD); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < nb_stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+        for (int i = 0; i < ACC_MAX; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 128); }
+        for (int i = 0; i < TC_RAW_MAX; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, TC_PROD); }
         mbar_fence_init();
     }
     if (warp == 16) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -160,7 +195,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         int as = unit % na_stages;
         uint32_t aphase = 0;
         const float in_scale = p.tc_in_scale;
-        while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+        int rawbase = 0;                            // raw-ring units of the interior tiles this CTA has passed
+        while (unit >= n_units && tile < n_tiles) {
+            if (tile_interior(tc_tile(tile, n_nt, n_tt).tt * TC_M)) rawbase += units_per_tile;
+            unit -= n_units; tile += gridDim.x;
+        }
         while (tile < n_tiles) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
             const int t0 = tl.tt * TC_M;
@@ -172,6 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
+            const bool interior = tile_interior(t0);
             for (; unit < n_units && tile == cur_tile; ) {
                 const int sc = unit / S, ph = unit - sc * S;
                 const int chunk = 2 * sc + half;               // 32-channel chunk of this group (may not exist: odd n_chunks)
@@ -198,21 +238,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
                 // the operand scale (a power of two: exact) is folded into the deferred-GroupNorm affine
                 float4 a0 = make_float4(in_scale, in_scale, in_scale, in_scale), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
-                if (!c_ok) { a0 = b0; a1 = b0; }
-                else if (cf0) {
-                    a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c));
-                    a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
-                    b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
-                }
-                if (c_ok && cf1) {
-                    a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c));
-                    a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
-                    b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
-                }
-                // all row loads of the unit are issued before the ring slot is waited for
                 constexpr int NR = 5;                      // a_rows <= 160 = 5 passes of 32 rows
                 float4 xa[NR], xb[NR];
                 bool okr[NR];
+                int rslot = -1;
+                if (!FREQ && interior) {
+                    // ---- TMA-staged unit: dense [a_rows][32 ch] boxes (+ the coefficient slices) wait in the raw ring
+                    const int idx = 2 * S * sc + ((2 * sc + 1 < n_chunks) ? 2 * ph + half : ph);
+                    const int rc = rawbase + (split ? idx : ph);
+                    rslot = rc % nraw;
+                    mbar_wait(raw_full + rslot, (uint32_t)((rc / nraw) & 1));
+                    const uint8_t* rb = smR + rslot * L.raw_slot;
+                    if (!c_ok) { a0 = b0; a1 = b0; }
+                    else {
+                        if (cf0) { a0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + jchunk * 16); b0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 128 + jchunk * 16); }
+                        if (cf1) { a1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 256 + jchunk * 16); b1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 384 + jchunk * 16); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int u = rsub + 32 * i;
+                        const bool ok = c_ok && u < L.a_rows;
+                        okr[i] = ok;
+                        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        xb[i] = xa[i];
+                        if (ok) {
+                            xa[i] = *reinterpret_cast<const float4*>(rb + u * raw_pitch + jchunk * 16);
+                            if (has1) xb[i] = *reinterpret_cast<const float4*>(rb + L.raw_in1 + u * raw_pitch + jchunk * 16);
+                        }
+                    }
+                } else {
+                if (!c_ok) { a0 = b0; a1 = b0; }
+                else {
+                    if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
+                    if (cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
+                }
+                // all row loads of the unit are issued before the ring slot is waited for
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 32 * i;
@@ -230,7 +290,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(xu1 + off));
                     }
                 }
-                mbar_wait_backoff(a_empty + as, par, 64);
+                }
+                if (c_ok && cf0) {
+                    a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
+                    b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
+                }
+                if (c_ok && cf1) {
+                    a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
+                    b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
+                }
+                if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);
                 const uint32_t c16 = (uint32_t)(half * 4 + (jchunk >> 1)), sub8 = (uint32_t)((jchunk & 1) << 3);
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
@@ -261,6 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         *reinterpret_cast<uint2*>(lo + o) = l;
                     }
                 }
+                if (rslot >= 0) mbar_arrive(raw_empty + rslot);        // the raw rows are in registers / consumed
                 fence_proxy_async_smem();
                 } else {
                     if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
@@ -270,7 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 if (as >= na_stages) { as -= na_stages; aphase ^= 1; }
                 unit += step;
             }
-            while (unit >= n_units && tile < n_tiles) { unit -= n_units; tile += gridDim.x; }
+            while (unit >= n_units && tile < n_tiles) {
+                if (tile_interior(tc_tile(tile, n_nt, n_tt).tt * TC_M)) rawbase += units_per_tile;
+                unit -= n_units; tile += gridDim.x;
+            }
         }
     } else if (warp == 16) {
         // =========================================================== weight slabs via the bulk-copy engine
@@ -304,15 +377,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(TC_M, N_TILE);
             const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
-            int as = 0, bs = 0;
-            uint32_t aphase = 0, bphase = 0, gcount = 0;
+            int as = 0, bs = 0, buf = 0;
+            uint32_t aphase = 0, bphase = 0, cphase = 0;
             bool first = true;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 int ph = 0;
                 if (w_resident) bs = 0;
-                for (int g = 0; g < n_groups; ++g, ++gcount) {
-                    const int buf = (int)(gcount & 1);
-                    mbar_wait(acc_empty + buf, ((gcount >> 1) & 1) ^ 1);
+                for (int g = 0; g < n_groups; ++g) {
+                    mbar_wait(acc_empty + buf, cphase ^ 1);
                     tc_fence_after_sync();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BUF_COLS);
                     uint32_t accum = 0;
@@ -354,16 +426,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         if (++ph == S) ph = 0;
                     }
                     mma_commit(acc_full + buf);
+                    if (++buf == n_acc) { buf = 0; cphase ^= 1; }
                 }
                 first = false;
+            }
+        }
+    } else if (warp == 22) {
+        // =========================================================== raw activation tiles via TMA (cp.async.bulk.tensor)
+        if (lane == 0 && nraw > 0 && !FREQ && !(p.dbg & 512)) {
+            const uint32_t row_bytes = (uint32_t)(L.a_rows * raw_pitch);
+            const uint32_t cbytes = (uint32_t)raw_pitch;
+            const uint32_t n_cf = (p.in0.coef ? 2u : 0u) + ((has1 && p.in1.coef) ? 2u : 0u);
+            const uint32_t unit_bytes = row_bytes * (has1 ? 2u : 1u) + n_cf * cbytes;
+            int rc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const TcTile tl = tc_tile(tile, n_nt, n_tt);
+                const int t0 = tl.tt * TC_M;
+                if (!tile_interior(t0)) continue;
+                const float* cf0 = p.in0.coef ? p.in0.coef + (long long)tl.b * 2 * C_in : nullptr;
+                const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)tl.b * 2 * C_in : nullptr;
+                for (int sc = 0; sc < n_sc; ++sc)
+                    for (int ph = 0; ph < S; ++ph) {
+                        // row (t0 + u) * S + ph - pad_l == (tq0 + u) * S + php
+                        const int r = ph - p.pad_l;
+                        const int fd = (r >= 0) ? r / S : -((-r + S - 1) / S);
+                        const int tq0 = t0 + fd, php = r - fd * S;
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int chunk = 2 * sc + hh;
+                            if (chunk >= n_chunks) break;
+                            const int slot = rc % nraw;
+                            mbar_wait(raw_empty + slot, (uint32_t)((rc / nraw) & 1) ^ 1);
+                            uint8_t* dst = smR + slot * L.raw_slot;
+                            mbar_arrive_expect_tx(raw_full + slot, unit_bytes);
+                            tma_load_4d(dst, &tm0, chunk * TC_KC, php, tq0, tl.b, raw_full + slot);
+                            if (has1) tma_load_4d(dst + L.raw_in1, &tm1, chunk * TC_KC, php, tq0, tl.b, raw_full + slot);
+                            if (cf0) {
+                                bulk_g2s(dst + L.raw_cf, cf0 + chunk * TC_KC, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf + 128, cf0 + C_in + chunk * TC_KC, cbytes, raw_full + slot);
+                            }
+                            if (cf1) {
+                                bulk_g2s(dst + L.raw_cf + 256, cf1 + chunk * TC_KC, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf + 384, cf1 + C_in + chunk * TC_KC, cbytes, raw_full + slot);
+                            }
+                            ++rc;
+                        }
+                    }
             }
         }
     } else {
         // =========================================================== accumulator warps: fold groups, epilogue
         const int quad = warp & 3;                                   // a warp may only touch TMEM lanes 32*(warp%4)..+31
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(2 * BUF_COLS);
-        uint32_t gcount = 0;
+        const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(n_acc * BUF_COLS);
+        int buf = 0;
+        uint32_t cphase = 0;
         const float out_scale = p.tc_out_scale;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
@@ -377,10 +493,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 frow = ((long long)fb * p.fq.F_out * p.fq.FR + (long long)ff * p.fq.FR) * ((long long)p.T_out * p.fq.TR) + (long long)t * p.fq.TR;
             }
             float s = 0.f, ss = 0.f;
-            for (int g = 0; g < n_groups; ++g, ++gcount) {
-                const int buf = (int)(gcount & 1);
+            for (int g = 0; g < n_groups; ++g) {
                 const bool last = (g == n_groups - 1);
-                if (p.dbg & 64) mbar_wait(acc_full + buf, (gcount >> 1) & 1); else mbar_wait_backoff(acc_full + buf, (gcount >> 1) & 1, 128);
+                if (p.dbg & 64) mbar_wait(acc_full + buf, cphase); else mbar_wait_backoff(acc_full + buf, cphase, 128);
                 tc_fence_after_sync();
                 if (!(p.dbg & 128))
 #pragma unroll
@@ -474,6 +589,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 if (!last) tmem_st_wait();
                 tc_fence_before_sync();
                 mbar_arrive(acc_empty + buf);
+                if (++buf == n_acc) { buf = 0; cphase ^= 1; }
             }
             if (p.partials && !(p.dbg & 16)) {
                 double ds = (double)s, dss = (double)ss;
@@ -526,24 +642,85 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_force_na = 0, g_force_nb = 0, g_deep_ring = 1, g_dbg = 0;
+static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0;
+
+struct TcPlan { int resident, na, nb, nraw; TcSmemLayout L; bool ok; };
+
+// shared-memory plan: weights resident (small layers: the whole image of the single n-tile) or streamed through a ring as
+// deep as fits; A ring `na_first` stages (4, else 2) -- with a raw TMA ring the A ring only decouples producers from the MMA
+// issue, so 2 stages suffice and the rest of the shared memory buys prefetch depth (nraw units in flight).
+static TcPlan tc_plan(const ConvParams& p, int na_first, bool want_raw, int g_deep_ring) {
+    const int limit = 225 * 1024;
+    const int n_slabs = ((p.C_in + 2 * TC_KC - 1) / (2 * TC_KC)) * p.K;   // (64-channel stage chunk, tap) weight slabs per n-tile
+    const int has1 = p.in1.x ? 1 : 0;
+    const int raw_pitch = (p.C_in < TC_KC ? p.C_in : TC_KC) * 4;
+    TcPlan pl{};
+    pl.ok = false;
+    int na = na_first, nb = 4;
+    TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
+    const int min_raw = want_raw ? 2 : 0;
+    auto fits = [&](const TcSmemLayout& l) { return l.total + min_raw * tc_layout(p.K, p.S, p.n_tile, 2, 2, 1, raw_pitch, has1).raw_slot <= limit; };
+    if (n_slabs <= 64 && p.C_out == p.n_tile && fits(L)) { pl.resident = 1; nb = n_slabs; }   // one n-tile only
+    else {
+        L = tc_layout(p.K, p.S, p.n_tile, na, nb);
+        if (!fits(L)) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (!fits(L)) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (!fits(L)) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (!fits(L)) { nb = 2; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
+        if (!fits(L)) return pl;
+        // small n-tiles: a weight slab is only n_tile*256 bytes, so the ring is deepened until shared memory is full
+        if (g_deep_ring && !want_raw)
+            while (nb < 24 && nb < n_slabs && tc_layout(p.K, p.S, p.n_tile, na, nb + 1).total <= limit)
+                L = tc_layout(p.K, p.S, p.n_tile, na, ++nb);
+    }
+    int nraw = 0;
+    if (want_raw) {
+        nraw = 2;
+        while (nraw < TC_RAW_MAX && tc_layout(p.K, p.S, p.n_tile, na, nb, nraw + 1, raw_pitch, has1).total <= limit) ++nraw;
+    }
+    pl.L = tc_layout(p.K, p.S, p.n_tile, na, nb, nraw, raw_pitch, has1);
+    pl.na = na; pl.nb = nb; pl.nraw = nraw;
+    pl.ok = pl.L.total <= limit;
+    return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static int g_tma_state = 0;      // 0: not probed, 1: available, -1: unavailable / disabled (FCB_TC_TMA=0)
+
+// 4-D view of a channels-last activation [B][T][C] that makes every stride phase a dimension: (channel, phase, row / S, clip).
+// A unit of a tile = box {32 channels, 1 phase, a_rows rows, 1 clip}; rows beyond T / S (and before 0) are zero-filled.
+static bool make_act_map(CUtensorMap* tm, const InView& v, int C, int S, int T_in, int B, int a_rows) {
+    const float* base = v.x + (long long)v.row_off * C;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)S, (cuuint64_t)(T_in / S), (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)S * C * 4, (cuuint64_t)v.clip_stride * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)(C < TC_KC ? C : TC_KC), 1, (cuuint32_t)a_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((uintptr_t)base & 15) != 0 || (strides[0] & 15) || (strides[2] & 15) || dims[2] == 0) return false;
+    return g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <int N_TILE, bool FREQ>
-static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident) {
+static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, const TcPlan& pl, int n_tiles, const CUtensorMap& tm0,
+                               const CUtensorMap& tm1) {
     auto kern = conv1d_tc_kernel<N_TILE, FREQ>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, smem, st>>>(p, na, nb, n_tiles, resident, g_group_mmas);
+    kern<<<grid, TC_THREADS, pl.L.total, st>>>(p, pl.na, pl.nb, n_tiles, pl.resident, g_group_mmas, pl.nraw, tm0, tm1);
     return cudaGetLastError();
 }
 
 template <int N_TILE>
-static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, int na, int nb, int smem, int n_tiles, int resident, bool freq) {
-    return freq ? launch_tc_n<N_TILE, true>(p, st, na, nb, smem, n_tiles, resident)
-                : launch_tc_n<N_TILE, false>(p, st, na, nb, smem, n_tiles, resident);
+static cudaError_t launch_tc_modes(const ConvParams& p, cudaStream_t st, const TcPlan& pl, int n_tiles, bool freq,
+                                   const CUtensorMap& tm0, const CUtensorMap& tm1) {
+    return freq ? launch_tc_n<N_TILE, true>(p, st, pl, n_tiles, tm0, tm1) : launch_tc_n<N_TILE, false>(p, st, pl, n_tiles, tm0, tm1);
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* nparts) {
@@ -556,52 +733,48 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         if (e != cudaSuccess) return e;
         // tuning knobs (experiments only; defaults are the shipped configuration)
         if (const char* v = getenv("FCB_TC_GROUP_MMAS")) g_group_mmas = atoi(v) > 0 ? atoi(v) : TC_GROUP_MMAS;
-        if (const char* v = getenv("FCB_TC_NA")) g_force_na = atoi(v);
-        if (const char* v = getenv("FCB_TC_NB")) g_force_nb = atoi(v);
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
         if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
+        // TMA staging of the activation tiles: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+        g_tma_state = -1;
+        const char* tv = getenv("FCB_TC_TMA");
+        if (!tv || atoi(tv) != 0) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+                qres == cudaDriverEntryPointSuccess) {
+                g_encode_tiled = (EncodeTiledFn)fn;
+                g_tma_state = 1;
+            }
+        }
     }
     p.dbg = g_dbg;
     if (!(p.tc_in_scale > 0.f)) p.tc_in_scale = 16.f;           // post-GroupNorm activations are O(1): 16 x keeps |x| < 4094 finite
     if (!(p.tc_w_scale > 0.f)) p.tc_w_scale = 1.f;
     p.tc_out_scale = 1.0f / (p.tc_in_scale * p.tc_w_scale);     // powers of two: exact
     p.tc_elu_k = 1.4426950408889634f / p.tc_in_scale;
-    // small layers: the whole weight image of an n-tile (all chunks x taps) stays resident in shared memory and is
-    // loaded once per CTA; otherwise it streams through a ring.  Ring depths: as deep as shared memory allows
-    // (A even: the two producer groups alternate slots).
-    const int n_slabs = ((p.C_in + 2 * TC_KC - 1) / (2 * TC_KC)) * p.K;   // (64-channel stage chunk, tap) weight slabs per n-tile
-    const int limit = 225 * 1024;
-    int resident = 0, na = 4, nb = 4;
-    TcSmemLayout L = tc_layout(p.K, p.S, p.n_tile, na, n_slabs);
-    {
-        if (n_slabs <= 64 && p.C_out == p.n_tile && L.total <= limit) { resident = 1; nb = n_slabs; }   // one n-tile only
-        else {
-            L = tc_layout(p.K, p.S, p.n_tile, na, nb);
-            if (L.total > limit) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-            if (L.total > limit) { na = 2; nb = 4; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-            if (L.total > limit) { nb = 3; L = tc_layout(p.K, p.S, p.n_tile, na, nb); }
-            if (L.total > limit) return cudaErrorInvalidConfiguration;
-            // small n-tiles: a weight slab is only n_tile*256 bytes, so the ring is deepened until shared memory is full
-            // (measured neutral on the config-4 output conv, whose limit turned out to be the producers; kept because a
-            // deeper ring can only hide more bulk-copy latency)
-            if (g_deep_ring)
-                while (nb < 24 && nb < n_slabs && tc_layout(p.K, p.S, p.n_tile, na, nb + 1).total <= limit)
-                    L = tc_layout(p.K, p.S, p.n_tile, na, ++nb);
-            if (g_force_na > 0 && g_force_nb > 0) {
-                const TcSmemLayout L2 = tc_layout(p.K, p.S, p.n_tile, g_force_na, g_force_nb);
-                if (L2.total <= limit && g_force_na % 2 == 0) { na = g_force_na; nb = g_force_nb; L = L2; }
-            }
-        }
-    }
     const int n_tt = (p.T_out + TC_M - 1) / TC_M, n_nt = p.C_out / p.n_tile;
     *nparts = n_tt * n_nt;
     const int n_tiles = n_tt * n_nt * B;
     const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
+    // raw TMA ring: 1-D layers with interior tiles (n_tt >= 3), channel counts the box covers, 16-byte aligned views
+    CUtensorMap tm0{}, tm1{};
+    bool want_raw = g_tma_state == 1 && !freq && n_tt >= 3 && (p.C_in % TC_KC == 0 || p.C_in == 16) && p.T_in / p.S >= 1;
+    TcPlan pl{};
+    if (want_raw) {
+        pl = tc_plan(p, 2, true, g_deep_ring);
+        want_raw = pl.ok && pl.nraw >= 2 && make_act_map(&tm0, p.in0, p.C_in, p.S, p.T_in, B, pl.L.a_rows) &&
+                   (!p.in1.x || make_act_map(&tm1, p.in1, p.C_in, p.S, p.T_in, B, pl.L.a_rows));
+    }
+    if (!want_raw) {
+        pl = tc_plan(p, 4, false, g_deep_ring);
+        if (!pl.ok) return cudaErrorInvalidConfiguration;
+    }
     switch (p.n_tile) {
-        case 16: return launch_tc_modes<16>(p, st, na, nb, L.total, n_tiles, resident, freq);
-        case 32: return launch_tc_modes<32>(p, st, na, nb, L.total, n_tiles, resident, freq);
-        case 64: return launch_tc_modes<64>(p, st, na, nb, L.total, n_tiles, resident, freq);
-        case 128: return launch_tc_modes<128>(p, st, na, nb, L.total, n_tiles, resident, freq);
+        case 16: return launch_tc_modes<16>(p, st, pl, n_tiles, freq, tm0, tm1);
+        case 32: return launch_tc_modes<32>(p, st, pl, n_tiles, freq, tm0, tm1);
+        case 64: return launch_tc_modes<64>(p, st, pl, n_tiles, freq, tm0, tm1);
+        case 128: return launch_tc_modes<128>(p, st, pl, n_tiles, freq, tm0, tm1);
         default: return cudaErrorInvalidConfiguration;
     }
 }

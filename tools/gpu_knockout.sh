@@ -3,7 +3,7 @@
 # wrong on purpose) and compare per-launch durations.   tools/gpu_knockout.sh <tag> [workload]
 TAG=${1:-ko}; WL=${2:-config2}
 mkdir -p gpurun_out
-MASKS="0 8 63 127 191 319 575 1023"
+MASKS="0 7 8 32 63 1023"
 for M in $MASKS; do
   FCB_TC_DBG=$M timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ko${M}_${TAG}.csv \
     python bench.py --workload $WL --steps 1 --warmup 3 --skip-e2e --no-cpu-baseline > gpurun_out/ncu_ko${M}_${TAG}.log 2>&1
