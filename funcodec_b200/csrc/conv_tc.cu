@@ -98,6 +98,14 @@ __host__ __device__ inline int tc_units_per_group(int K, int S, int group_mmas) 
     return g < 1 ? 1 : g;
 }
 
+// Launch-invariant quantities computed on the host and read from the kernel-parameter constant bank (instead of being
+// derived -- and kept live in registers -- by every thread).
+struct TcArgs {
+    TcSmemLayout L;
+    int na, nb, n_tiles, w_resident, nraw;
+    int n_chunks, n_sc, split, n_units, upg, n_groups, n_tt, n_nt, units_per_tile, tq_rows, n_acc, raw_pitch;
+};
+
 struct TcTile { int b, nt, tt; };
 
 __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
@@ -110,9 +118,8 @@ __device__ __forceinline__ TcTile tc_tile(int id, int n_nt, int n_tt) {
 }
 
 template <int N_TILE, bool FREQ>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvParams p, const int na_stages, const int nb_stages,
-                                                                 const int n_tiles, const int w_resident, const int group_mmas,
-                                                                 const int nraw, const __grid_constant__ CUtensorMap tm0,
+__global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TcArgs ka,
+                                                                 const __grid_constant__ CUtensorMap tm0,
                                                                  const __grid_constant__ CUtensorMap tm1) {
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;          // TMEM columns per accumulator region
     constexpr uint32_t TMEM_COLS = 512;                          // the whole TMEM: one CTA per SM
@@ -121,16 +128,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C_in = p.C_in, K = p.K, S = p.S;
     const bool has1 = p.in1.x != nullptr;
-    const int raw_pitch = (C_in < TC_KC ? C_in : TC_KC) * 4;         // bytes per row of a raw (TMA-staged) unit
-    const TcSmemLayout L = tc_layout(K, S, N_TILE, na_stages, nb_stages, nraw, raw_pitch, has1 ? 1 : 0);
-    const int n_chunks = (C_in + TC_KC - 1) / TC_KC;      // C_in = 16: one half-empty chunk (zero channels, zero weights)
-    const int n_sc = (n_chunks + 1) >> 1;                 // 64-channel stage chunks
-    const bool split = n_chunks > 1;                      // both producer groups fill one stage (32 channels each)
-    const int n_units = n_sc * S;                         // ring stages per tile
-    const int upg = tc_units_per_group(K, S, group_mmas);
-    const int n_groups = (n_units + upg - 1) / upg;
-    const int n_tt = (p.T_out + TC_M - 1) / TC_M;
-    const int n_nt = p.C_out / N_TILE;
+    const TcSmemLayout& L = ka.L;
+#define na_stages ka.na
+#define nb_stages ka.nb
+#define n_tiles ka.n_tiles
+#define w_resident ka.w_resident
+#define nraw ka.nraw
+#define raw_pitch ka.raw_pitch              /* bytes per row of a raw (TMA-staged) unit */
+#define n_chunks ka.n_chunks                /* 32-channel chunks; C_in = 16: one half-empty chunk (zero channels, zero weights) */
+#define n_sc ka.n_sc                        /* 64-channel stage chunks */
+#define n_units ka.n_units                  /* ring stages per tile */
+#define upg ka.upg
+#define n_groups ka.n_groups
+#define n_tt ka.n_tt
+#define n_nt ka.n_nt
+    const bool split = ka.split != 0;                     // both producer groups fill one stage (32 channels each)
 
     uint8_t* smA = smem_raw;
     uint8_t* smB = smem_raw + L.off_b;
@@ -149,8 +161,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     // reflection, no zero padding -- so its units arrive as dense [a_rows][32 channel] boxes through the raw ring; the first / last
     // tiles of a clip keep the per-thread global loads (the index map lives there).  Units of a tile in ring order:
     // stage-major, half-minor; every role derives the slot from the same running count.
-    const int units_per_tile = n_chunks * S;
-    const int tq_rows = p.T_in / S;                                    // rows per phase the tensor map exposes
+#define units_per_tile ka.units_per_tile
+#define tq_rows ka.tq_rows                  /* rows per phase the tensor map exposes */
     auto tile_interior = [&](int t0) -> bool {
         if (nraw == 0) return false;
         const int lo = t0 * S - p.pad_l;                                // first / last input row a valid output of the tile needs
@@ -160,8 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
     // accumulator ring depth.  The MMA -> commit -> epilogue -> release hand-off costs ~2000 cycles per tile pair (measured: the
     // pure barrier skeleton of the small-tile layers), so layers whose tile is one accumulation group keep up to 8 tiles in
     // flight; layers that fold groups (deep K) ping-pong between up to 3 accumulators next to the running totals.
-    const int acc_fit = (int)TMEM_COLS / BUF_COLS;
-    const int n_acc = n_groups == 1 ? (acc_fit < ACC_MAX ? acc_fit : ACC_MAX) : (acc_fit - 1 < 3 ? acc_fit - 1 : 3);
+#define n_acc ka.n_acc
     double* red = reinterpret_cast<double*>(tmem_ptr + 2);       // [4][2] statistics scratch
 
     if (tid == 0) {
@@ -211,16 +222,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
             const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
-            const bool interior = tile_interior(t0);
+            const bool interior = !FREQ && tile_interior(t0);
             for (; unit < n_units && tile == cur_tile; ) {
                 const int sc = unit / S, ph = unit - sc * S;
                 const int chunk = 2 * sc + half;               // 32-channel chunk of this group (may not exist: odd n_chunks)
                 const uint32_t par = aphase ^ 1;
                 uint8_t* hi = smA + as * L.a_stage;
                 uint8_t* lo = hi + L.a_rows * 128;
+                const uint32_t c16 = (uint32_t)(half * 4 + (jchunk >> 1)), sub8 = (uint32_t)((jchunk & 1) << 3);
                 if (p.dbg & 512) {
                     if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);
-                } else if (chunk < n_chunks) {
+                } else if (chunk >= n_chunks) {
+                    if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
+                } else if (interior) {
+                    // ---- TMA-staged unit: the dense [a_rows][32 ch] boxes (+ the coefficient slices) wait in the raw ring; rows go
+                    // shared -> registers -> shared one at a time (no long-latency loads to batch, few live registers)
+                    const bool c_ok = chunk * TC_KC + jchunk * 4 < C_in;
+                    const int idx = 2 * S * sc + ((2 * sc + 1 < n_chunks) ? 2 * ph + half : ph);
+                    const int rc = rawbase + idx;
+                    const int rslot = rc % nraw;
+                    mbar_wait(raw_full + rslot, (uint32_t)((rc / nraw) & 1));
+                    const uint8_t* rb = smR + rslot * L.raw_slot;
+                    float4 a0 = make_float4(in_scale, in_scale, in_scale, in_scale), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+                    if (!c_ok) { a0 = b0; a1 = b0; }
+                    else {
+                        if (cf0) {
+                            a0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + jchunk * 16); b0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 128 + jchunk * 16);
+                            a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
+                            b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
+                        }
+                        if (cf1) {
+                            a1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 256 + jchunk * 16); b1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 384 + jchunk * 16);
+                            a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
+                            b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
+                        }
+                    }
+                    if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);
+                    const uint8_t* rrow = rb + rsub * raw_pitch + jchunk * 16;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int u = rsub + 32 * i;
+                        if (u < L.a_rows) {
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (c_ok) {
+                                const float4 xv = *reinterpret_cast<const float4*>(rrow + i * 32 * raw_pitch);
+                                v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
+                                v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
+                                if (has1) {
+                                    const float4 yv = *reinterpret_cast<const float4*>(rrow + L.raw_in1 + i * 32 * raw_pitch);
+                                    v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
+                                    v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
+                                }
+                                if (p.elu) {
+                                    v.x = elu_scaled(v.x, p.tc_elu_k, in_scale); v.y = elu_scaled(v.y, p.tc_elu_k, in_scale);
+                                    v.z = elu_scaled(v.z, p.tc_elu_k, in_scale); v.w = elu_scaled(v.w, p.tc_elu_k, in_scale);
+                                }
+                            }
+                            if (p.dbg & 4) continue;
+                            uint2 h, l;
+                            split_f16x2(v.x, v.y, h.x, l.x);
+                            split_f16x2(v.z, v.w, h.y, l.y);
+                            const uint32_t o = (uint32_t)u * 128u + ((c16 ^ (uint32_t)(u & 7)) << 4) + sub8;
+                            *reinterpret_cast<uint2*>(hi + o) = h;
+                            *reinterpret_cast<uint2*>(lo + o) = l;
+                        }
+                    }
+                    mbar_arrive(raw_empty + rslot);            // the raw rows have been consumed
+                    fence_proxy_async_smem();
+                } else {
                 int c = chunk * TC_KC + jchunk * 4;
                 bool c_ok = c < C_in;
                 const float* xu0 = x0;
@@ -238,41 +307,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                 }
                 // the operand scale (a power of two: exact) is folded into the deferred-GroupNorm affine
                 float4 a0 = make_float4(in_scale, in_scale, in_scale, in_scale), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+                if (!c_ok) { a0 = b0; a1 = b0; }
+                else if (cf0) {
+                    a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c));
+                    a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
+                    b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
+                }
+                if (c_ok && cf1) {
+                    a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c));
+                    a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
+                    b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
+                }
+                // all row loads of the unit are issued before the ring slot is waited for
                 constexpr int NR = 5;                      // a_rows <= 160 = 5 passes of 32 rows
                 float4 xa[NR], xb[NR];
                 bool okr[NR];
-                int rslot = -1;
-                if (!FREQ && interior) {
-                    // ---- TMA-staged unit: dense [a_rows][32 ch] boxes (+ the coefficient slices) wait in the raw ring
-                    const int idx = 2 * S * sc + ((2 * sc + 1 < n_chunks) ? 2 * ph + half : ph);
-                    const int rc = rawbase + (split ? idx : ph);
-                    rslot = rc % nraw;
-                    mbar_wait(raw_full + rslot, (uint32_t)((rc / nraw) & 1));
-                    const uint8_t* rb = smR + rslot * L.raw_slot;
-                    if (!c_ok) { a0 = b0; a1 = b0; }
-                    else {
-                        if (cf0) { a0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + jchunk * 16); b0 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 128 + jchunk * 16); }
-                        if (cf1) { a1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 256 + jchunk * 16); b1 = *reinterpret_cast<const float4*>(rb + L.raw_cf + 384 + jchunk * 16); }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NR; ++i) {
-                        const int u = rsub + 32 * i;
-                        const bool ok = c_ok && u < L.a_rows;
-                        okr[i] = ok;
-                        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        xb[i] = xa[i];
-                        if (ok) {
-                            xa[i] = *reinterpret_cast<const float4*>(rb + u * raw_pitch + jchunk * 16);
-                            if (has1) xb[i] = *reinterpret_cast<const float4*>(rb + L.raw_in1 + u * raw_pitch + jchunk * 16);
-                        }
-                    }
-                } else {
-                if (!c_ok) { a0 = b0; a1 = b0; }
-                else {
-                    if (cf0) { a0 = __ldg(reinterpret_cast<const float4*>(cf0 + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf0 + pitch + c)); }
-                    if (cf1) { a1 = __ldg(reinterpret_cast<const float4*>(cf1 + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf1 + pitch + c)); }
-                }
-                // all row loads of the unit are issued before the ring slot is waited for
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 32 * i;
@@ -290,17 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         if (has1) xb[i] = __ldg(reinterpret_cast<const float4*>(xu1 + off));
                     }
                 }
-                }
-                if (c_ok && cf0) {
-                    a0.x *= in_scale; a0.y *= in_scale; a0.z *= in_scale; a0.w *= in_scale;
-                    b0.x *= in_scale; b0.y *= in_scale; b0.z *= in_scale; b0.w *= in_scale;
-                }
-                if (c_ok && cf1) {
-                    a1.x *= in_scale; a1.y *= in_scale; a1.z *= in_scale; a1.w *= in_scale;
-                    b1.x *= in_scale; b1.y *= in_scale; b1.z *= in_scale; b1.w *= in_scale;
-                }
                 if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);
-                const uint32_t c16 = (uint32_t)(half * 4 + (jchunk >> 1)), sub8 = (uint32_t)((jchunk & 1) << 3);
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
                     const int u = rsub + 32 * i;
@@ -330,10 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                         *reinterpret_cast<uint2*>(lo + o) = l;
                     }
                 }
-                if (rslot >= 0) mbar_arrive(raw_empty + rslot);        // the raw rows are in registers / consumed
                 fence_proxy_async_smem();
-                } else {
-                    if (p.dbg & 64) mbar_wait(a_empty + as, par); else mbar_wait_backoff(a_empty + as, par, 64);      // missing half of the last stage: never read by the MMAs
                 }
                 mbar_arrive(a_full + as);
                 as += step;
@@ -480,6 +516,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         const uint32_t tot_base = tmem_base + lane_base + (uint32_t)(n_acc * BUF_COLS);
         int buf = 0;
         uint32_t cphase = 0;
+        // 2-D plain convs (no phase scatter, no padded columns) store [pseudo-clip][t][C_out] like a 1-D layer
+        const bool plain_out = FREQ && p.fq.FR == 1 && p.fq.TR == 1 && p.fq.c_store == p.C_out;
         const float out_scale = p.tc_out_scale;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
@@ -513,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
                     }
                     if (!last) {
                         tmem_st_32x32b_x32(tot_base + (uint32_t)c0, v);
-                    } else if (!FREQ) {
+                    } else if (!FREQ || plain_out) {
                         // bias + statistics in registers, then through a swizzled staging tile so that every global store
                         // instruction of the warp writes whole rows (4 rows x 128 B = 4 L1 wavefronts instead of 32)
                         uint8_t* stg = smem_raw + L.off_stg + quad * 4096;
@@ -616,6 +654,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const ConvPara
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+#undef na_stages
+#undef nb_stages
+#undef n_tiles
+#undef w_resident
+#undef nraw
+#undef raw_pitch
+#undef n_chunks
+#undef n_sc
+#undef n_units
+#undef upg
+#undef n_groups
+#undef n_tt
+#undef n_nt
+#undef units_per_tile
+#undef tq_rows
+#undef n_acc
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -713,7 +767,25 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, const TcPla
         if (e != cudaSuccess) return e;
     }
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    kern<<<grid, TC_THREADS, pl.L.total, st>>>(p, pl.na, pl.nb, n_tiles, pl.resident, g_group_mmas, pl.nraw, tm0, tm1);
+    TcArgs ka{};
+    ka.L = pl.L; ka.na = pl.na; ka.nb = pl.nb; ka.n_tiles = n_tiles; ka.w_resident = pl.resident; ka.nraw = pl.nraw;
+    ka.n_chunks = (p.C_in + TC_KC - 1) / TC_KC;
+    ka.n_sc = (ka.n_chunks + 1) >> 1;
+    ka.split = ka.n_chunks > 1;
+    ka.n_units = ka.n_sc * p.S;
+    ka.upg = tc_units_per_group(p.K, p.S, g_group_mmas);
+    ka.n_groups = (ka.n_units + ka.upg - 1) / ka.upg;
+    ka.n_tt = (p.T_out + TC_M - 1) / TC_M;
+    ka.n_nt = p.C_out / N_TILE;
+    ka.units_per_tile = ka.n_chunks * p.S;
+    ka.tq_rows = p.T_in / p.S;
+    ka.raw_pitch = (p.C_in < TC_KC ? p.C_in : TC_KC) * 4;
+    // accumulator ring depth: layers whose tile is one accumulation group keep up to 8 tiles in flight between MMA issue and
+    // epilogue; layers that fold groups (deep K) ping-pong between up to 3 accumulators next to the running totals
+    constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;
+    const int acc_fit = 512 / BUF_COLS;
+    ka.n_acc = ka.n_groups == 1 ? (acc_fit < 8 ? acc_fit : 8) : (acc_fit - 1 < 3 ? acc_fit - 1 : 3);
+    kern<<<grid, TC_THREADS, pl.L.total, st>>>(p, ka, tm0, tm1);
     return cudaGetLastError();
 }
 

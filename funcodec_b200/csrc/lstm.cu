@@ -27,7 +27,9 @@ namespace fcb {
 
 constexpr int LSTM_GB_MAX = 8;    // clips per work item (accumulator tile): 8, or 4 for small batches (more items in flight)
 constexpr int LSTM_NBUF_MAX = 8;  // h ring depth: 2 .. 8 slots, as many as shared memory holds (more independent clip groups in flight)
-constexpr int LSTM_THREADS = 416; // 8 compute warps, 2 x 2 cell warps (alternate items), 1 loader warp
+constexpr int LSTM_THREADS = 480; // 8 compute warps, up to 3 x 2 cell warps (items round-robin), 1 loader warp: 15 warps keep the
+                                  // 128-register budget of the 16-warp allocation bucket (17 warps drop to 96: measured slower)
+constexpr int LSTM_PAIRS_MAX = 3;
 constexpr int LSTM_MAX_GROUPS = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -63,7 +65,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
 template <int UNITS, int GB>
-__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf) {
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf, const int npair, const int pload) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
     constexpr int NSLICE = 8 * KS_PER_WARP;    // K slices per CTA (interleaved in groups of 4 k)
@@ -72,14 +74,14 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                                   // [H][COLS]
     float* Hs = Ws + (size_t)H * COLS;                  // [nbuf][GB][H]
-    float* red = Hs + nbuf * GB * H;               // [2][8 warps][GB][COLS]
-    float* cS = red + 2 * 8 * GB * COLS;           // [ng][GB][UNITS] cell state
+    float* red = Hs + nbuf * GB * H;               // [npair][8 warps][GB][COLS]
+    float* cS = red + npair * 8 * GB * COLS;       // [ng][GB][UNITS] cell state
     const int ng = (B + GB - 1) / GB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * GB * UNITS + 3) & ~3));
     uint64_t* hs_full = bars;                           // [nbuf] tx
     uint64_t* hs_empty = hs_full + nbuf;                // [nbuf] 8 compute-warp arrivals
-    uint64_t* red_full = hs_empty + nbuf;               // [2]    8 compute-warp arrivals
-    uint64_t* red_empty = red_full + 2;                 // [2]    64 cell-thread arrivals
+    uint64_t* red_full = hs_empty + nbuf;               // [npair] 8 compute-warp arrivals
+    uint64_t* red_empty = red_full + LSTM_PAIRS_MAX;    // [npair] 64 cell-thread arrivals
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j0 = blockIdx.x * UNITS;
     const int n_items = T * ng;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     for (int e = tid; e < ng * GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
     if (tid == 0) {
         for (int i = 0; i < nbuf; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
+        for (int i = 0; i < LSTM_PAIRS_MAX; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
         tc::mbar_fence_init();
     }
     __syncthreads();
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         const int slice = warp * KS_PER_WARP + ks;
         for (int i = ng; i < n_items; ++i) {            // items with t == 0 need no recurrent term
             const int n = i - ng;
-            const int hb = n % nbuf, rb = n & 1;
+            const int hb = n % nbuf, rb = n % npair;
             tc::mbar_wait(hs_full + hb, (uint32_t)((n / nbuf) & 1));
             if (tid == 0) LSTM_TRACE(i, 2);
             const float* Hc = Hs + hb * GB * H;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     for (int o = UNITS; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     acc[gg][bb] = v;
                 }
-            tc::mbar_wait(red_empty + rb, (uint32_t)((n >> 1) & 1) ^ 1);
+            tc::mbar_wait(red_empty + rb, (uint32_t)((n / npair) & 1) ^ 1);
             if (ks == 0) {
                 float* rd = red + (size_t)rb * 8 * GB * COLS;
 #pragma unroll
@@ -167,9 +169,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             if (lane == 0) tc::mbar_arrive(red_full + rb);
             if (tid == 0) LSTM_TRACE(i, 4);
         }
-    } else if (warp < 12) {
-        // ================================================================ cell warps: two pairs take alternate items
+    } else if (warp < 8 + 2 * LSTM_PAIRS_MAX) {
+        // ================================================================ cell warps: npair pairs take the items round-robin
         const int pair = (warp - 8) >> 1;
+        if (pair >= npair) return;
         const int ftid = (tid - 256) & 63;
         const int fbb = ftid / UNITS, fu = ftid % UNITS;
         const bool active = ftid < NFIN;
@@ -192,19 +195,22 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             }
             return v;
         };
-        float4 gxv = load_gx(pair);
-        float skv = load_skip(pair);
-        for (int i = pair; i < n_items; i += 2) {
+        // items of this pair: those whose exchange buffer (i - ng) % npair == pair; the t == 0 items (i < ng) use no buffer and are
+        // spread the same way
+        const int first = ((pair - ng) % npair + npair) % npair;      // smallest i >= 0 with (i - ng) % npair == pair
+        float4 gxv = load_gx(first);
+        float skv = load_skip(first);
+        for (int i = first; i < n_items; i += npair) {
             const int t = i / ng, g = i - t * ng;
             const int b0 = g * GB;
             const int nb = min(GB, B - b0);
             const bool mine = active && fbb < nb;
-            const float4 gx_next = load_gx(i + 2);               // in flight while this item is reduced
-            const float sk_next = load_skip(i + 2);
+            const float4 gx_next = load_gx(i + npair);           // in flight while this item is reduced
+            const float sk_next = load_skip(i + npair);
             float g4[4] = {gxv.x, gxv.y, gxv.z, gxv.w};
             if (t > 0) {
-                const int n = i - ng, rb = n & 1;
-                tc::mbar_wait_backoff(red_full + rb, (uint32_t)((n >> 1) & 1), 64);
+                const int n = i - ng, rb = pair;                 // == n % npair by construction
+                tc::mbar_wait_backoff(red_full + rb, (uint32_t)((n / npair) & 1), 64);
                 if (ftid == 0) LSTM_TRACE(i, 5);
                 if (mine) {
                     const float* rd = red + (size_t)rb * 8 * GB * COLS;
@@ -232,8 +238,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             }
             // publish h_t of this group FIRST (it heads every other CTA's critical path): the pair's stores -> named barrier ->
             // one gpu-scope release add; the skip output below is off the recurrence
-            if (pair == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
-            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + pair) : "memory");
             if (ftid == 0 && t + 1 < T)
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier + g), "r"(1u) : "memory");
             if (ftid == 0) LSTM_TRACE(i, 6);
@@ -252,7 +257,25 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         }
     } else {
         // ================================================================ loader warp
-        if (lane == 0) {
+        if (nbuf == ng && pload) {
+            // one ring slot per clip group: lane g serves group g, so the polls and copies of a timestep's groups overlap
+            if (lane < ng) {
+                const int g = lane, b0 = g * GB;
+                const int nb = min(GB, B - b0);
+                float* dst = Hs + g * GB * H;
+                for (int t = 1; t < T; ++t) {
+                    tc::mbar_wait_backoff(hs_empty + g, (uint32_t)((t - 1) & 1) ^ 1, 64);
+                    if (lane == 0) LSTM_TRACE(t * ng, 0);
+                    unsigned seen = ld_acquire_u32(p.barrier + g);
+                    while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
+                    if (lane == 0) LSTM_TRACE(t * ng, 1);
+                    asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
+                    tc::mbar_arrive_expect_tx(hs_full + g, (uint32_t)(nb * H * 4));
+                    for (int bb = 0; bb < nb; ++bb)
+                        tc::bulk_g2s(dst + bb * H, p.h_seq + ((long long)(b0 + bb) * T + (t - 1)) * H, (uint32_t)(H * 4), hs_full + g);
+                }
+            }
+        } else if (lane == 0) {
             for (int i = ng; i < n_items; ++i) {
                 const int t = i / ng, g = i - t * ng;
                 const int n = i - ng, hb = n % nbuf;
@@ -273,11 +296,11 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
 }
 
-size_t lstm_seq_smem_bytes(int H, int B, int units, int gb, int nbuf = 2) {
+size_t lstm_seq_smem_bytes(int H, int B, int units, int gb, int nbuf = 2, int npair = 2) {
     const int ng = (B + gb - 1) / gb;
     const size_t cs = ((size_t)ng * gb * units + 3) & ~(size_t)3;
-    return ((size_t)H * 4 * units + (size_t)nbuf * gb * H + 2 * 8 * 4 * units * gb + cs) * sizeof(float) +
-           (2 * nbuf + 4) * 8 + 64;
+    return ((size_t)H * 4 * units + (size_t)nbuf * gb * H + (size_t)npair * 8 * 4 * units * gb + cs) * sizeof(float) +
+           (2 * nbuf + 2 * LSTM_PAIRS_MAX) * 8 + 64;
 }
 
 // h ring depth: one slot per independent clip group (their barrier / broadcast latencies overlap), 2 .. LSTM_NBUF_MAX,
@@ -310,7 +333,12 @@ int lstm_pick_units(int H) {
 template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
-    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf);
+    // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
+    int npair = 2, pload = 1;
+    if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3) <= 220 * 1024) npair = 3;
+    if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
+    if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;
+    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair);
     auto kern = lstm_seq_kernel<UNITS, GB>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
@@ -322,7 +350,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     dim3 grid(p.H / UNITS), block(LSTM_THREADS);
     LstmSeqParams pc = p;
-    void* args[] = {&pc, &nbuf};
+    void* args[] = {&pc, &nbuf, &npair, &pload};
     return cudaLaunchCooperativeKernel((void*)kern, grid, block, args, smem, st);
 }
 
