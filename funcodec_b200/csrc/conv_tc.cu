@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
             const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
-            const bool interior = !FREQ && tile_interior(t0);
+            const bool interior = tile_interior(t0);
             for (; unit < n_units && tile == cur_tile; ) {
                 const int sc = unit / S, ph = unit - sc * S;
                 const int chunk = 2 * sc + half;               // 32-channel chunk of this group (may not exist: odd n_chunks)
@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
                 } else if (interior) {
                     // ---- TMA-staged unit: the dense [a_rows][32 ch] boxes (+ the coefficient slices) wait in the raw ring; rows go
                     // shared -> registers -> shared one at a time (no long-latency loads to batch, few live registers)
-                    const bool c_ok = chunk * TC_KC + jchunk * 4 < C_in;
+                    bool c_ok = chunk * TC_KC + jchunk * 4 < C_in;
+                    if (FREQ && p.pad_zero) {              // a zero-padded frequency tap contributes nothing (its box arrives zero-filled)
+                        const int f_src = f_out * p.fq.SF + (chunk * TC_KC) / pitch - p.fq.pad_f;
+                        c_ok = c_ok && f_src >= 0 && f_src < p.fq.F_in;
+                    }
                     const int idx = 2 * S * sc + ((2 * sc + 1 < n_chunks) ? 2 * ph + half : ph);
                     const int rc = rawbase + idx;
                     const int rslot = rc % nraw;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
         }
     } else if (warp == 22) {
         // =========================================================== raw activation tiles via TMA (cp.async.bulk.tensor)
-        if (lane == 0 && nraw > 0 && !FREQ && !(p.dbg & 512)) {
+        if (lane == 0 && nraw > 0 && !(p.dbg & 512)) {
             const uint32_t row_bytes = (uint32_t)(L.a_rows * raw_pitch);
             const uint32_t cbytes = (uint32_t)raw_pitch;
             const uint32_t n_cf = (p.in0.coef ? 2u : 0u) + ((has1 && p.in1.coef) ? 2u : 0u);
@@ -479,8 +483,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
                 const TcTile tl = tc_tile(tile, n_nt, n_tt);
                 const int t0 = tl.tt * TC_M;
                 if (!tile_interior(t0)) continue;
-                const float* cf0 = p.in0.coef ? p.in0.coef + (long long)tl.b * 2 * C_in : nullptr;
-                const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)tl.b * 2 * C_in : nullptr;
+                int b = tl.b, f_out = 0;
+                if (FREQ) { b = tl.b / p.fq.F_out; f_out = tl.b - b * p.fq.F_out; }
+                const int pitch = FREQ ? p.fq.cin : C_in;
+                const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * pitch : nullptr;
+                const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
                 for (int sc = 0; sc < n_sc; ++sc)
                     for (int ph = 0; ph < S; ++ph) {
                         // row (t0 + u) * S + ph - pad_l == (tq0 + u) * S + php
@@ -494,15 +501,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
                             mbar_wait(raw_empty + slot, (uint32_t)((rc / nraw) & 1) ^ 1);
                             uint8_t* dst = smR + slot * L.raw_slot;
                             mbar_arrive_expect_tx(raw_full + slot, unit_bytes);
-                            tma_load_4d(dst, &tm0, chunk * TC_KC, php, tq0, tl.b, raw_full + slot);
-                            if (has1) tma_load_4d(dst + L.raw_in1, &tm1, chunk * TC_KC, php, tq0, tl.b, raw_full + slot);
+                            int c0 = chunk * TC_KC;            // first stored channel of the unit
+                            if (FREQ) {
+                                // gathered chunk -> (frequency tap, 32-channel slice of it); a reflected tap is just another row,
+                                // a zero-padded one is out of bounds for the tensor map (zero fill)
+                                const int kf = c0 / pitch;
+                                c0 -= kf * pitch;
+                                int f_src = f_out * p.fq.SF + kf - p.fq.pad_f;
+                                if (!p.pad_zero) f_src = reflect_index(f_src, p.fq.F_in);
+                                tma_load_5d(dst, &tm0, c0, php, tq0, f_src, b, raw_full + slot);
+                                if (has1) tma_load_5d(dst + L.raw_in1, &tm1, c0, php, tq0, f_src, b, raw_full + slot);
+                            } else {
+                                tma_load_4d(dst, &tm0, c0, php, tq0, b, raw_full + slot);
+                                if (has1) tma_load_4d(dst + L.raw_in1, &tm1, c0, php, tq0, b, raw_full + slot);
+                            }
                             if (cf0) {
-                                bulk_g2s(dst + L.raw_cf, cf0 + chunk * TC_KC, cbytes, raw_full + slot);
-                                bulk_g2s(dst + L.raw_cf + 128, cf0 + C_in + chunk * TC_KC, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf, cf0 + c0, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf + 128, cf0 + pitch + c0, cbytes, raw_full + slot);
                             }
                             if (cf1) {
-                                bulk_g2s(dst + L.raw_cf + 256, cf1 + chunk * TC_KC, cbytes, raw_full + slot);
-                                bulk_g2s(dst + L.raw_cf + 384, cf1 + C_in + chunk * TC_KC, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf + 256, cf1 + c0, cbytes, raw_full + slot);
+                                bulk_g2s(dst + L.raw_cf + 384, cf1 + pitch + c0, cbytes, raw_full + slot);
                             }
                             ++rc;
                         }
@@ -696,7 +715,7 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0;
+static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0, g_nacc_cap = 0;
 
 struct TcPlan { int resident, na, nb, nraw; TcSmemLayout L; bool ok; };
 
@@ -707,7 +726,8 @@ static TcPlan tc_plan(const ConvParams& p, int na_first, bool want_raw, int g_de
     const int limit = 225 * 1024;
     const int n_slabs = ((p.C_in + 2 * TC_KC - 1) / (2 * TC_KC)) * p.K;   // (64-channel stage chunk, tap) weight slabs per n-tile
     const int has1 = p.in1.x ? 1 : 0;
-    const int raw_pitch = (p.C_in < TC_KC ? p.C_in : TC_KC) * 4;
+    const int cin_row = p.fq.KF > 0 ? p.fq.cin : p.C_in;                   // channels of a stored input row
+    const int raw_pitch = (cin_row < TC_KC ? cin_row : TC_KC) * 4;
     TcPlan pl{};
     pl.ok = false;
     int na = na_first, nb = 4;
@@ -758,6 +778,22 @@ static bool make_act_map(CUtensorMap* tm, const InView& v, int C, int S, int T_i
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D (FreqCodec) activation [B][F_raw][T_raw][cin]: (channel, phase, column / ST, frequency row, clip); the logical window
+// starts at (f_off, t_off) and spans F_in x T_in -- taps outside it are out of bounds (zero fill) or reflected by the caller.
+static bool make_act_map_2d(CUtensorMap* tm, const InView& v, int cin, int ST, int T_in, int F_in, int T_raw, int f_off, int B,
+                            int a_rows) {
+    const float* base = v.x + ((long long)f_off * T_raw + v.row_off) * cin;
+    const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)ST, (cuuint64_t)(T_in / ST), (cuuint64_t)F_in, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)cin * 4, (cuuint64_t)ST * cin * 4, (cuuint64_t)T_raw * cin * 4,
+                                   (cuuint64_t)v.clip_stride * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)(cin < TC_KC ? cin : TC_KC), 1, (cuuint32_t)a_rows, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (((uintptr_t)base & 15) != 0 || (strides[0] & 15) || (strides[2] & 15) || (strides[3] & 15) || dims[2] == 0) return false;
+    return g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N_TILE, bool FREQ>
 static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, const TcPlan& pl, int n_tiles, const CUtensorMap& tm0,
                                const CUtensorMap& tm1) {
@@ -779,12 +815,13 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, const TcPla
     ka.n_nt = p.C_out / N_TILE;
     ka.units_per_tile = ka.n_chunks * p.S;
     ka.tq_rows = p.T_in / p.S;
-    ka.raw_pitch = (p.C_in < TC_KC ? p.C_in : TC_KC) * 4;
+    ka.raw_pitch = ((FREQ ? p.fq.cin : p.C_in) < TC_KC ? (FREQ ? p.fq.cin : p.C_in) : TC_KC) * 4;
     // accumulator ring depth: layers whose tile is one accumulation group keep up to 8 tiles in flight between MMA issue and
     // epilogue; layers that fold groups (deep K) ping-pong between up to 3 accumulators next to the running totals
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;
     const int acc_fit = 512 / BUF_COLS;
     ka.n_acc = ka.n_groups == 1 ? (acc_fit < 8 ? acc_fit : 8) : (acc_fit - 1 < 3 ? acc_fit - 1 : 3);
+    if (g_nacc_cap >= 2 && ka.n_acc > g_nacc_cap) ka.n_acc = g_nacc_cap;       // experiments (FCB_TC_NACC)
     kern<<<grid, TC_THREADS, pl.L.total, st>>>(p, ka, tm0, tm1);
     return cudaGetLastError();
 }
@@ -807,6 +844,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         if (const char* v = getenv("FCB_TC_GROUP_MMAS")) g_group_mmas = atoi(v) > 0 ? atoi(v) : TC_GROUP_MMAS;
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
         if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
+        if (const char* v = getenv("FCB_TC_NACC")) g_nacc_cap = atoi(v);
         // TMA staging of the activation tiles: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
         g_tma_state = -1;
         const char* tv = getenv("FCB_TC_TMA");
@@ -831,12 +869,22 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
     const bool freq = p.fq.KF > 0;          // B counts pseudo-clips (clips x output frequency rows) in the 2-D mode
     // raw TMA ring: 1-D layers with interior tiles (n_tt >= 3), channel counts the box covers, 16-byte aligned views
     CUtensorMap tm0{}, tm1{};
-    bool want_raw = g_tma_state == 1 && !freq && n_tt >= 3 && (p.C_in % TC_KC == 0 || p.C_in == 16) && p.T_in / p.S >= 1;
+    // (2-D: a 32-channel unit must be a slice of ONE frequency tap -> cin % 32 == 0, or the single tap of a 16-channel 1x1 conv)
+    bool want_raw = g_tma_state == 1 && n_tt >= 3 && p.T_in / p.S >= 1 &&
+                    (freq ? (p.fq.cin % TC_KC == 0 || (p.fq.cin == 16 && p.fq.KF == 1)) : (p.C_in % TC_KC == 0 || p.C_in == 16));
+    if (freq && getenv("FCB_TC_TMA2D") && atoi(getenv("FCB_TC_TMA2D")) == 0) want_raw = false;
     TcPlan pl{};
     if (want_raw) {
         pl = tc_plan(p, 2, true, g_deep_ring);
-        want_raw = pl.ok && pl.nraw >= 2 && make_act_map(&tm0, p.in0, p.C_in, p.S, p.T_in, B, pl.L.a_rows) &&
-                   (!p.in1.x || make_act_map(&tm1, p.in1, p.C_in, p.S, p.T_in, B, pl.L.a_rows));
+        want_raw = pl.ok && pl.nraw >= 2;
+        if (want_raw && !freq)
+            want_raw = make_act_map(&tm0, p.in0, p.C_in, p.S, p.T_in, B, pl.L.a_rows) &&
+                       (!p.in1.x || make_act_map(&tm1, p.in1, p.C_in, p.S, p.T_in, B, pl.L.a_rows));
+        if (want_raw && freq) {
+            const int nclips = B / p.fq.F_out;
+            want_raw = make_act_map_2d(&tm0, p.in0, p.fq.cin, p.S, p.T_in, p.fq.F_in, p.fq.T_raw0, p.fq.f_off0, nclips, pl.L.a_rows) &&
+                       (!p.in1.x || make_act_map_2d(&tm1, p.in1, p.fq.cin, p.S, p.T_in, p.fq.F_in, p.fq.T_raw1, p.fq.f_off1, nclips, pl.L.a_rows));
+        }
     }
     if (!want_raw) {
         pl = tc_plan(p, 4, false, g_deep_ring);

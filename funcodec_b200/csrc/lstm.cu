@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
         };
         // items of this pair: those whose exchange buffer (i - ng) % npair == pair; the t == 0 items (i < ng) use no buffer and are
         // spread the same way
-        const int first = ((pair - ng) % npair + npair) % npair;      // smallest i >= 0 with (i - ng) % npair == pair
+        const int first = (pair + ng) % npair;                        // smallest i >= 0 with (i - ng) % npair == pair
         float4 gxv = load_gx(first);
         float skv = load_skip(first);
         for (int i = first; i < n_items; i += npair) {
@@ -334,7 +334,7 @@ template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
     // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
-    int npair = 2, pload = 1;
+    int npair = 2, pload = (p.B + GB - 1) / GB >= 4 ? 1 : 0;      // per-group loader lanes: slower with 2 groups (r2f: 3.7 vs 3.45 ms)
     if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3) <= 220 * 1024) npair = 3;
     if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
     if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;

@@ -1,6 +1,8 @@
 """PROFILING ONLY: per-item %globaltimer stamps of CTA 0 of the last LSTM layer launch (FCB_LSTM_TRACE=1).
 usage: FCB_LSTM_TRACE=1 python tools/lstm_trace.py <config> <B> <L>"""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from funcodec_b200 import get_config, init_state_dict
 from funcodec_b200.encodec import B200Encodec
