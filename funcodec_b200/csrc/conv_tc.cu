@@ -872,7 +872,10 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
     // (2-D: a 32-channel unit must be a slice of ONE frequency tap -> cin % 32 == 0, or the single tap of a 16-channel 1x1 conv)
     bool want_raw = g_tma_state == 1 && n_tt >= 3 && p.T_in / p.S >= 1 &&
                     (freq ? (p.fq.cin % TC_KC == 0 || (p.fq.cin == 16 && p.fq.KF == 1)) : (p.C_in % TC_KC == 0 || p.C_in == 16));
-    if (freq && getenv("FCB_TC_TMA2D") && atoi(getenv("FCB_TC_TMA2D")) == 0) want_raw = false;
+    // 2-D layers: built and parity-tested (5-D tensor maps), but measured SLOWER than the per-thread gather at config 4 (r2g: conv
+    // stack 37.3 vs 33.6 ms) -- the K_F-fold re-read of every input row makes the unit stream L2-bound either way and the TMA path
+    // adds a hand-off; opt-in (FCB_TC_TMA2D=1)
+    if (freq && !(getenv("FCB_TC_TMA2D") && atoi(getenv("FCB_TC_TMA2D")) != 0)) want_raw = false;
     TcPlan pl{};
     if (want_raw) {
         pl = tc_plan(p, 2, true, g_deep_ring);

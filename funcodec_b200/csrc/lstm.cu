@@ -65,10 +65,13 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
 template <int UNITS, int GB>
-__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf, const int npair, const int pload) {
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf, const int npair, const int pload, const int nset) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
-    constexpr int NSLICE = 8 * KS_PER_WARP;    // K slices per CTA (interleaved in groups of 4 k)
+    // compute-warp sets: nset = 1: all 8 warps split the K dimension of one item; nset = 2 (narrow layers, where an item is bound
+    // by latencies, not FMAs): two sets of 4 warps work on two consecutive items at the same time
+    const int WS = 8 / nset;                   // warps per set
+    const int NSLICE = WS * KS_PER_WARP;       // K slices per item (interleaved in groups of 4 k)
     constexpr int NFIN = GB * UNITS;      // active cell threads
     extern __shared__ __align__(128) float smem[];
     const int H = p.H, T = p.T, B = p.B;
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
     for (int e = tid; e < ng * GB * UNITS; e += LSTM_THREADS) cS[e] = 0.f;
     if (tid == 0) {
-        for (int i = 0; i < nbuf; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, 8); }
-        for (int i = 0; i < LSTM_PAIRS_MAX; ++i) { tc::mbar_init(red_full + i, 8); tc::mbar_init(red_empty + i, 64); }
+        for (int i = 0; i < nbuf; ++i) { tc::mbar_init(hs_full + i, 1); tc::mbar_init(hs_empty + i, WS); }
+        for (int i = 0; i < LSTM_PAIRS_MAX; ++i) { tc::mbar_init(red_full + i, WS); tc::mbar_init(red_empty + i, 64); }
         tc::mbar_fence_init();
     }
     __syncthreads();
@@ -107,8 +110,9 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     if (warp < 8) {
         // ================================================================ compute warps
         const int u = lane % UNITS, ks = lane / UNITS;
-        const int slice = warp * KS_PER_WARP + ks;
-        for (int i = ng; i < n_items; ++i) {            // items with t == 0 need no recurrent term
+        const int set = warp / WS, wset = warp - set * WS;
+        const int slice = wset * KS_PER_WARP + ks;
+        for (int i = ng + set; i < n_items; i += nset) {        // items with t == 0 need no recurrent term
             const int n = i - ng;
             const int hb = n % nbuf, rb = n % npair;
             tc::mbar_wait(hs_full + hb, (uint32_t)((n / nbuf) & 1));
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 float* rd = red + (size_t)rb * 8 * GB * COLS;
 #pragma unroll
                 for (int bb = 0; bb < GB; ++bb)
-                    *reinterpret_cast<float4*>(rd + (warp * GB + bb) * COLS + u * 4) =
+                    *reinterpret_cast<float4*>(rd + (wset * GB + bb) * COLS + u * 4) =
                         make_float4(acc[0][bb], acc[1][bb], acc[2][bb], acc[3][bb]);
             }
             __syncwarp();
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     const float* rd = red + (size_t)rb * 8 * GB * COLS;
                     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) {
+                    for (int w8 = 0; w8 < WS; ++w8) {
                         const float4 r4 = *reinterpret_cast<const float4*>(rd + (w8 * GB + fbb) * COLS + fu * 4);
                         s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
                     }
@@ -334,7 +338,13 @@ template <int UNITS, int GB>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
     // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
-    int npair = 2, pload = (p.B + GB - 1) / GB >= 4 ? 1 : 0;      // per-group loader lanes: slower with 2 groups (r2f: 3.7 vs 3.45 ms)
+    // per-group loader lanes only pay with many groups (r2f / r2g: config 2 (2 groups) 3.7 vs 3.45 ms, config 4 (4 groups) 8.15 vs
+    // 6.5 ms, config 3 (8 groups) 36.8 vs 38.0 ms per SLSTM)
+    const int ngroups = (p.B + GB - 1) / GB;
+    int npair = 2, pload = ngroups >= 8 ? 1 : 0;
+    // two compute-warp sets when an item's gate GEMM is small (H <= 512) and there are other groups to work on
+    int nset = (p.H <= 512 && ngroups >= 2) ? 2 : 1;
+    if (const char* v = getenv("FCB_LSTM_NSET")) { const int f = atoi(v); if (f == 1 || f == 2) nset = f; }                // experiments
     if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3) <= 220 * 1024) npair = 3;
     if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
     if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;
@@ -350,7 +360,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     dim3 grid(p.H / UNITS), block(LSTM_THREADS);
     LstmSeqParams pc = p;
-    void* args[] = {&pc, &nbuf, &npair, &pload};
+    void* args[] = {&pc, &nbuf, &npair, &pload, &nset};
     return cudaLaunchCooperativeKernel((void*)kern, grid, block, args, smem, st);
 }
 
