@@ -45,6 +45,7 @@ struct LstmW {
     int H = 0, layers = 0;
     std::vector<ConvW> ih;                // input projections as 1x1 convs: [1][H][4H] + bias (b_ih + b_hh)
     std::vector<float*> whh;              // packed [H][4H]
+    std::vector<float> whh_scale;         // power-of-two fp16 operand scale per layer (max|w| * scale in [2^13, 2^14))
 };
 
 struct ResBlockW { ConvW c1, c2, sc; };
@@ -361,7 +362,11 @@ int pack_lstm(fcb_handle* h, const std::string& prefix, int H, int layers, LstmW
         FCB_TRY(upload(h, pb, &ih.bias));
         float* dwh;
         FCB_TRY(upload(h, ph, &dwh));
-        o->ih.push_back(ih); o->whh.push_back(dwh);
+        float mx = 0.f;
+        for (float v : ph) { const float a = fabsf(v); if (a > mx && a < INFINITY) mx = a; }
+        float sc = 1.f;
+        if (mx > 0.f) { int e = 0; frexpf(mx, &e); int sh = 14 - e; if (sh > 40) sh = 40; if (sh < -40) sh = -40; sc = ldexpf(1.f, sh); }
+        o->ih.push_back(ih); o->whh.push_back(dwh); o->whh_scale.push_back(sc);
     }
     return FCB_OK;
 }
@@ -540,6 +545,8 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
         sp.skip = view_of(x);
         sp.barrier = h->lstm_barrier;
         sp.trace = h->lstm_trace;
+        sp.whh_scale = W.whh_scale[l];
+        sp.whh_inv_scale = 1.0f / (W.whh_scale[l] * 4096.0f);
         sp.B = B; sp.T = T; sp.H = H;
         FCB_CK(launch_lstm_seq(sp, r.st));
         h->launches += 1;

@@ -17,6 +17,7 @@
 //     shuffles + one shared-memory pass, and UNITS*8 threads do the cell update.
 // Latency-bound by construction (T' dependent steps); FLOPs = 2*B*T*4H*H per layer.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -64,7 +65,20 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 //     store h_t (+ skip output) and publish the group's counter with a single release-add.
 // The barrier/broadcast latency of one group is hidden behind the math of the others; with a single group
 // (B <= 8) the chain is latency-bound by construction.
-template <int UNITS, int GB>
+// mma.sync m16n8k16 (fp16 operands, fp32 accumulate): D += A * B, A = 16 gate columns x 16 k (row-major fragments), B = 16 k x 8 clips
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+constexpr float LSTM_H_SCALE = 4096.0f;   // |h| < 1: fp16 operand scale of the hidden state (power of two)
+
+// MMA = true: the gate GEMM h_{t-1} W_hh^T of an item runs on the tensor cores (mma.sync m16n8k16, N = the 8 clips of the group)
+// with the 3-term FP16 split of conv_tc.cu (W pre-scaled per layer so that max|w| is in [2^13, 2^14), h scaled by 2^12;
+// lo*hi + hi*lo + hi*hi in fp32, exact inverse scale afterwards): ~2^-22 relative like the fp32 FMA chain it replaces, at a
+// third of the shared-memory instruction count -- the item then costs one pass over the 128 KB W_hh slice (LDS-bound).
+// The W slice lives in shared memory in FRAGMENT ORDER: [k-step (16 k)][m-tile (16 columns)][hi | lo][lane][8 halfs].
+template <int UNITS, int GB, bool MMA>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeqParams p, const int nbuf, const int npair, const int pload, const int nset) {
     constexpr int COLS = 4 * UNITS;            // gate columns owned by this CTA
     constexpr int KS_PER_WARP = 32 / UNITS;    // K slices inside a warp
@@ -93,6 +107,22 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     // W_hh slice in the FFMA2-friendly layout: for every pair of consecutive k and every unit u two 16-byte records
     //   rec(kp, half, u) = { W[k][u][2*half], W[k+1][u][2*half], W[k][u][2*half+1], W[k+1][u][2*half+1] }
     // so that one LDS.128 yields two (w_k, w_{k+1}) register pairs and lanes u = 0..UNITS-1 read consecutive records.
+    if (MMA) {
+        constexpr int MT = COLS / 16;
+        __half* Wf = reinterpret_cast<__half*>(Ws);
+        for (int e = tid; e < H * COLS; e += LSTM_THREADS) {
+            const int k = e / COLS, c = e - k * COLS;
+            const float v = __ldg(p.whh + (long long)k * 4 * H + (long long)j0 * 4 + c) * p.whh_scale;
+            const __half vh = __float2half_rn(v);
+            const __half vl = __float2half_rn(v - __half2float(vh));
+            const int ksg = k >> 4, kk = k & 15, mt = c >> 4, r = c & 15;
+            const int ln = (r & 7) * 4 + ((kk & 7) >> 1);
+            const int hidx = (kk >= 8 ? 4 : 0) + (r >= 8 ? 2 : 0) + (kk & 1);
+            const size_t base = ((size_t)(ksg * MT + mt) * 2 * 32 + ln) * 8 + hidx;
+            Wf[base] = vh;
+            Wf[base + 32 * 8] = vl;
+        }
+    } else
     for (int e = tid; e < H * COLS; e += LSTM_THREADS) {
         const int k = e / COLS, c = e - k * COLS;
         const int uu = c >> 2, g = c & 3;
@@ -118,6 +148,52 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             tc::mbar_wait(hs_full + hb, (uint32_t)((n / nbuf) & 1));
             if (tid == 0) LSTM_TRACE(i, 2);
             const float* Hc = Hs + hb * GB * H;
+            if (MMA) {
+                constexpr int MT = COLS / 16;
+                const int g8 = lane >> 2, t4 = lane & 3;
+                const int ksw = (H >> 4) / WS;                          // k-steps of this warp
+                const uint4* Wf = reinterpret_cast<const uint4*>(Ws);
+                float c[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.f; c[mt][1] = 0.f; c[mt][2] = 0.f; c[mt][3] = 0.f; }
+                const float* hrow = Hc + g8 * H + t4 * 2;              // clip g8 of the group (B fragment column)
+                for (int j = 0; j < ksw; ++j) {
+                    const int ksg = wset * ksw + j;
+                    const float2 x0 = *reinterpret_cast<const float2*>(hrow + ksg * 16);
+                    const float2 x1 = *reinterpret_cast<const float2*>(hrow + ksg * 16 + 8);
+                    uint32_t bh0, bl0, bh1, bl1;
+                    tc::split_f16x2(x0.x * LSTM_H_SCALE, x0.y * LSTM_H_SCALE, bh0, bl0);
+                    tc::split_f16x2(x1.x * LSTM_H_SCALE, x1.y * LSTM_H_SCALE, bh1, bl1);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint4 ah = Wf[((size_t)(ksg * MT + mt) * 2 + 0) * 32 + lane];
+                        const uint4 al = Wf[((size_t)(ksg * MT + mt) * 2 + 1) * 32 + lane];
+                        mma_16816(c[mt], al, bh0, bh1);
+                        mma_16816(c[mt], ah, bl0, bl1);
+                        mma_16816(c[mt], ah, bh0, bh1);
+                    }
+                }
+                __syncwarp();
+                if (tid == 0) LSTM_TRACE(i, 3);
+                if (lane == 0) tc::mbar_arrive(hs_empty + hb);       // this warp is done with the h slot
+                tc::mbar_wait(red_empty + rb, (uint32_t)((n / npair) & 1) ^ 1);
+                {
+                    // C fragment: rows (gate columns) g8, g8 + 8 of the m-tile; columns (clips) 2*t4, 2*t4 + 1
+                    const float inv = p.whh_inv_scale;
+                    float* rd = red + (size_t)rb * 8 * GB * COLS + (size_t)(wset * GB + t4 * 2) * COLS + g8;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        rd[mt * 16] = c[mt][0] * inv;
+                        rd[COLS + mt * 16] = c[mt][1] * inv;
+                        rd[mt * 16 + 8] = c[mt][2] * inv;
+                        rd[COLS + mt * 16 + 8] = c[mt][3] * inv;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(red_full + rb);
+                if (tid == 0) LSTM_TRACE(i, 4);
+                continue;
+            }
             // packed fp32 FMAs (FFMA2): even-k and odd-k partial sums live in the two halves of a register pair
             float2 acc2[4][GB];
 #pragma unroll
@@ -334,7 +410,7 @@ int lstm_pick_units(int H) {
     return 0;
 }
 
-template <int UNITS, int GB>
+template <int UNITS, int GB, bool MMA>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
     // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
@@ -349,7 +425,9 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
     if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;
     const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair);
-    auto kern = lstm_seq_kernel<UNITS, GB>;
+    // the tensor-core gate GEMM needs whole k-steps per warp
+    if (MMA && (p.H % 16 != 0 || ((p.H / 16) % (8 / nset)) != 0)) return launch_seq<UNITS, GB, false>(p, st);
+    auto kern = lstm_seq_kernel<UNITS, GB, MMA>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
         if (e != cudaSuccess) return e;
@@ -368,10 +446,12 @@ cudaError_t launch_lstm_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (p.H % 4 != 0) return cudaErrorInvalidValue;
     const int units = lstm_pick_units(p.H);
     const int gb = lstm_pick_gb(p.B);
-    if (units == 8 && gb == 8) return launch_seq<8, 8>(p, st);
-    if (units == 8 && gb == 4) return launch_seq<8, 4>(p, st);
-    if (units == 4 && gb == 8) return launch_seq<4, 8>(p, st);
-    if (units == 4 && gb == 4) return launch_seq<4, 4>(p, st);
+    bool mma = p.whh_scale > 0.f;                     // tensor-core gate GEMM (default); FCB_LSTM_MMA=0: the fp32 FFMA2 path
+    if (const char* v = getenv("FCB_LSTM_MMA")) mma = mma && atoi(v) != 0;
+    if (units == 8 && gb == 8) return mma ? launch_seq<8, 8, true>(p, st) : launch_seq<8, 8, false>(p, st);
+    if (units == 8 && gb == 4) return launch_seq<8, 4, false>(p, st);
+    if (units == 4 && gb == 8) return mma ? launch_seq<4, 8, true>(p, st) : launch_seq<4, 8, false>(p, st);
+    if (units == 4 && gb == 4) return launch_seq<4, 4, false>(p, st);
     return cudaErrorInvalidConfiguration;
 }
 
