@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                                   // [H][COLS]
     float* Hs = Ws + (size_t)H * COLS;                  // [nbuf][GB][H]
-    float* red = Hs + nbuf * GB * H;               // [npair][8 warps][GB][COLS]
+    float* red = Hs + (MMA ? 0 : nbuf * GB * H);   // [npair][8 warps][GB][COLS]   (MMA: no h staging ring, fragments come from L2)
     float* cS = red + npair * 8 * GB * COLS;       // [ng][GB][UNITS] cell state
     const int ng = (B + GB - 1) / GB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * GB * UNITS + 3) & ~3));
@@ -150,32 +150,53 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             const float* Hc = Hs + hb * GB * H;
             if (MMA) {
                 constexpr int MT = COLS / 16;
+                constexpr int KSW_MAX = 8;                              // k-steps per warp (host guarantees ksw <= 8)
                 const int g8 = lane >> 2, t4 = lane & 3;
                 const int ksw = (H >> 4) / WS;                          // k-steps of this warp
                 const uint4* Wf = reinterpret_cast<const uint4*>(Ws);
-                float c[MT][4];
+                // hs_full here only signals "every CTA has published h_{t-1} of this group" (the loader thread's acquire); the
+                // lanes then pull exactly their B-fragment values (clip g8, k pairs) straight from L2 -- no staging copy, no ring
+                const int t = i / ng, g = i - t * ng;
+                const int b0 = g * GB;
+                const bool clip_ok = b0 + g8 < B;
+                const float* hrow = p.h_seq + ((long long)(b0 + g8) * T + (t - 1)) * H + wset * ksw * 16 + t4 * 2;
+                float2 xs[2 * KSW_MAX];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.f; c[mt][1] = 0.f; c[mt][2] = 0.f; c[mt][3] = 0.f; }
-                const float* hrow = Hc + g8 * H + t4 * 2;              // clip g8 of the group (B fragment column)
-                for (int j = 0; j < ksw; ++j) {
-                    const int ksg = wset * ksw + j;
-                    const float2 x0 = *reinterpret_cast<const float2*>(hrow + ksg * 16);
-                    const float2 x1 = *reinterpret_cast<const float2*>(hrow + ksg * 16 + 8);
-                    uint32_t bh0, bl0, bh1, bl1;
-                    tc::split_f16x2(x0.x * LSTM_H_SCALE, x0.y * LSTM_H_SCALE, bh0, bl0);
-                    tc::split_f16x2(x1.x * LSTM_H_SCALE, x1.y * LSTM_H_SCALE, bh1, bl1);
+                for (int j = 0; j < KSW_MAX; ++j) {
+                    xs[2 * j] = make_float2(0.f, 0.f);
+                    xs[2 * j + 1] = make_float2(0.f, 0.f);
+                    if (j < ksw && clip_ok) {
+                        xs[2 * j] = __ldcg(reinterpret_cast<const float2*>(hrow + j * 16));
+                        xs[2 * j + 1] = __ldcg(reinterpret_cast<const float2*>(hrow + j * 16 + 8));
+                    }
+                }
+                // three independent accumulator chains per m-tile (hi*hi, lo*hi, hi*lo), summed at the end: the dependent-MMA chain
+                // is ksw long instead of 3 * ksw
+                float c[MT][3][4];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint4 ah = Wf[((size_t)(ksg * MT + mt) * 2 + 0) * 32 + lane];
-                        const uint4 al = Wf[((size_t)(ksg * MT + mt) * 2 + 1) * 32 + lane];
-                        mma_16816(c[mt], al, bh0, bh1);
-                        mma_16816(c[mt], ah, bl0, bl1);
-                        mma_16816(c[mt], ah, bh0, bh1);
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { c[mt][q][0] = 0.f; c[mt][q][1] = 0.f; c[mt][q][2] = 0.f; c[mt][q][3] = 0.f; }
+#pragma unroll
+                for (int j = 0; j < KSW_MAX; ++j) {
+                    if (j < ksw) {
+                        const int ksg = wset * ksw + j;
+                        uint32_t bh0, bl0, bh1, bl1;
+                        tc::split_f16x2(xs[2 * j].x * LSTM_H_SCALE, xs[2 * j].y * LSTM_H_SCALE, bh0, bl0);
+                        tc::split_f16x2(xs[2 * j + 1].x * LSTM_H_SCALE, xs[2 * j + 1].y * LSTM_H_SCALE, bh1, bl1);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint4 ah = Wf[((size_t)(ksg * MT + mt) * 2 + 0) * 32 + lane];
+                            const uint4 al = Wf[((size_t)(ksg * MT + mt) * 2 + 1) * 32 + lane];
+                            mma_16816(c[mt][0], ah, bh0, bh1);
+                            mma_16816(c[mt][1], al, bh0, bh1);
+                            mma_16816(c[mt][2], ah, bl0, bl1);
+                        }
                     }
                 }
                 __syncwarp();
                 if (tid == 0) LSTM_TRACE(i, 3);
-                if (lane == 0) tc::mbar_arrive(hs_empty + hb);       // this warp is done with the h slot
+                if (lane == 0) tc::mbar_arrive(hs_empty + hb);       // this warp has consumed the signal
                 tc::mbar_wait(red_empty + rb, (uint32_t)((n / npair) & 1) ^ 1);
                 {
                     // C fragment: rows (gate columns) g8, g8 + 8 of the m-tile; columns (clips) 2*t4, 2*t4 + 1
@@ -183,10 +204,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     float* rd = red + (size_t)rb * 8 * GB * COLS + (size_t)(wset * GB + t4 * 2) * COLS + g8;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        rd[mt * 16] = c[mt][0] * inv;
-                        rd[COLS + mt * 16] = c[mt][1] * inv;
-                        rd[mt * 16 + 8] = c[mt][2] * inv;
-                        rd[COLS + mt * 16 + 8] = c[mt][3] * inv;
+                        rd[mt * 16] = ((c[mt][1][0] + c[mt][2][0]) + c[mt][0][0]) * inv;
+                        rd[COLS + mt * 16] = ((c[mt][1][1] + c[mt][2][1]) + c[mt][0][1]) * inv;
+                        rd[mt * 16 + 8] = ((c[mt][1][2] + c[mt][2][2]) + c[mt][0][2]) * inv;
+                        rd[COLS + mt * 16 + 8] = ((c[mt][1][3] + c[mt][2][3]) + c[mt][0][3]) * inv;
                     }
                 }
                 __syncwarp();
@@ -349,6 +370,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     unsigned seen = ld_acquire_u32(p.barrier + g);
                     while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
                     if (lane == 0) LSTM_TRACE(t * ng, 1);
+                    if (MMA) { tc::mbar_arrive(hs_full + g); continue; }   // the compute lanes load their fragments themselves
                     asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                     tc::mbar_arrive_expect_tx(hs_full + g, (uint32_t)(nb * H * 4));
                     for (int bb = 0; bb < nb; ++bb)
@@ -366,6 +388,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 unsigned seen = ld_acquire_u32(p.barrier + g);
                 while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
                 LSTM_TRACE(i, 1);
+                if (MMA) { tc::mbar_arrive(hs_full + hb); continue; }   // the compute lanes load their fragments themselves
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
                 float* dst = Hs + hb * GB * H;
@@ -376,19 +399,19 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     }
 }
 
-size_t lstm_seq_smem_bytes(int H, int B, int units, int gb, int nbuf = 2, int npair = 2) {
+size_t lstm_seq_smem_bytes(int H, int B, int units, int gb, int nbuf = 2, int npair = 2, bool ring = true) {
     const int ng = (B + gb - 1) / gb;
     const size_t cs = ((size_t)ng * gb * units + 3) & ~(size_t)3;
-    return ((size_t)H * 4 * units + (size_t)nbuf * gb * H + (size_t)npair * 8 * 4 * units * gb + cs) * sizeof(float) +
+    return ((size_t)H * 4 * units + (ring ? (size_t)nbuf * gb * H : 0) + (size_t)npair * 8 * 4 * units * gb + cs) * sizeof(float) +
            (2 * nbuf + 2 * LSTM_PAIRS_MAX) * 8 + 64;
 }
 
 // h ring depth: one slot per independent clip group (their barrier / broadcast latencies overlap), 2 .. LSTM_NBUF_MAX,
 // limited by shared memory (H = 1024: the 128 KB W_hh slice leaves room for 2 slots of 32 KB)
-static int lstm_pick_nbuf(int H, int B, int units, int gb) {
+static int lstm_pick_nbuf(int H, int B, int units, int gb, bool ring) {
     const int ng = (B + gb - 1) / gb;
     int nbuf = ng < 2 ? 2 : (ng > LSTM_NBUF_MAX ? LSTM_NBUF_MAX : ng);
-    while (nbuf > 2 && lstm_seq_smem_bytes(H, B, units, gb, nbuf) > 220 * 1024) --nbuf;
+    while (nbuf > 2 && lstm_seq_smem_bytes(H, B, units, gb, nbuf, 2, ring) > 220 * 1024) --nbuf;
     if (const char* v = getenv("FCB_LSTM_NBUF")) { const int f = atoi(v); if (f >= 2 && f <= nbuf) nbuf = f; }   // experiments
     return nbuf;
 }
@@ -412,7 +435,7 @@ int lstm_pick_units(int H) {
 
 template <int UNITS, int GB, bool MMA>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
-    int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB);
+    int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB, !MMA);
     // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
     // per-group loader lanes only pay with many groups (r2f / r2g: config 2 (2 groups) 3.7 vs 3.45 ms, config 4 (4 groups) 8.15 vs
     // 6.5 ms, config 3 (8 groups) 36.8 vs 38.0 ms per SLSTM)
@@ -421,12 +444,12 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     // two compute-warp sets when an item's gate GEMM is small (H <= 512) and there are other groups to work on
     int nset = (p.H <= 512 && ngroups >= 2) ? 2 : 1;
     if (const char* v = getenv("FCB_LSTM_NSET")) { const int f = atoi(v); if (f == 1 || f == 2) nset = f; }                // experiments
-    if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3) <= 220 * 1024) npair = 3;
+    if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3, !MMA) <= 220 * 1024) npair = 3;
     if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
     if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;
-    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair);
+    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair, !MMA);
     // the tensor-core gate GEMM needs whole k-steps per warp
-    if (MMA && (p.H % 16 != 0 || ((p.H / 16) % (8 / nset)) != 0)) return launch_seq<UNITS, GB, false>(p, st);
+    if (MMA && (p.H % 16 != 0 || ((p.H / 16) % (8 / nset)) != 0 || (p.H / 16) / (8 / nset) > 8)) return launch_seq<UNITS, GB, false>(p, st);
     auto kern = lstm_seq_kernel<UNITS, GB, MMA>;
     {
         cudaError_t e = ensure_dynamic_smem((const void*)kern, 225 * 1024);
