@@ -715,7 +715,7 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0, g_nacc_cap = 0;
+static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0, g_nacc_cap = 0, g_na_tma = 2;
 
 struct TcPlan { int resident, na, nb, nraw; TcSmemLayout L; bool ok; };
 
@@ -845,6 +845,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
         if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
         if (const char* v = getenv("FCB_TC_NACC")) g_nacc_cap = atoi(v);
+        if (const char* v = getenv("FCB_TC_NA_TMA")) { const int f = atoi(v); if (f == 2 || f == 4) g_na_tma = f; }
         // TMA staging of the activation tiles: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
         g_tma_state = -1;
         const char* tv = getenv("FCB_TC_TMA");
@@ -878,7 +879,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
     if (freq && !(getenv("FCB_TC_TMA2D") && atoi(getenv("FCB_TC_TMA2D")) != 0)) want_raw = false;
     TcPlan pl{};
     if (want_raw) {
-        pl = tc_plan(p, 2, true, g_deep_ring);
+        pl = tc_plan(p, g_na_tma, true, g_deep_ring);
         want_raw = pl.ok && pl.nraw >= 2;
         if (want_raw && !freq)
             want_raw = make_act_map(&tm0, p.in0, p.C_in, p.S, p.T_in, B, pl.L.a_rows) &&

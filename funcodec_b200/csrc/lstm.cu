@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
     const int H = p.H, T = p.T, B = p.B;
     float* Ws = smem;                                   // [H][COLS]
     float* Hs = Ws + (size_t)H * COLS;                  // [nbuf][GB][H]
-    float* red = Hs + (MMA ? 0 : nbuf * GB * H);   // [npair][8 warps][GB][COLS]   (MMA: no h staging ring, fragments come from L2)
+    float* red = Hs + nbuf * GB * H;               // [npair][8 warps][GB][COLS]
     float* cS = red + npair * 8 * GB * COLS;       // [ng][GB][UNITS] cell state
     const int ng = (B + GB - 1) / GB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(cS + ((ng * GB * UNITS + 3) & ~3));
@@ -154,20 +154,16 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 const int g8 = lane >> 2, t4 = lane & 3;
                 const int ksw = (H >> 4) / WS;                          // k-steps of this warp
                 const uint4* Wf = reinterpret_cast<const uint4*>(Ws);
-                // hs_full here only signals "every CTA has published h_{t-1} of this group" (the loader thread's acquire); the
-                // lanes then pull exactly their B-fragment values (clip g8, k pairs) straight from L2 -- no staging copy, no ring
-                const int t = i / ng, g = i - t * ng;
-                const int b0 = g * GB;
-                const bool clip_ok = b0 + g8 < B;
-                const float* hrow = p.h_seq + ((long long)(b0 + g8) * T + (t - 1)) * H + wset * ksw * 16 + t4 * 2;
+                // B fragments of this lane (clip g8, k pairs) from the staged h_{t-1} rows
+                const float* hrow = Hc + g8 * H + wset * ksw * 16 + t4 * 2;
                 float2 xs[2 * KSW_MAX];
 #pragma unroll
                 for (int j = 0; j < KSW_MAX; ++j) {
                     xs[2 * j] = make_float2(0.f, 0.f);
                     xs[2 * j + 1] = make_float2(0.f, 0.f);
-                    if (j < ksw && clip_ok) {
-                        xs[2 * j] = __ldcg(reinterpret_cast<const float2*>(hrow + j * 16));
-                        xs[2 * j + 1] = __ldcg(reinterpret_cast<const float2*>(hrow + j * 16 + 8));
+                    if (j < ksw) {
+                        xs[2 * j] = *reinterpret_cast<const float2*>(hrow + j * 16);
+                        xs[2 * j + 1] = *reinterpret_cast<const float2*>(hrow + j * 16 + 8);
                     }
                 }
                 // three independent accumulator chains per m-tile (hi*hi, lo*hi, hi*lo), summed at the end: the dependent-MMA chain
@@ -196,7 +192,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 }
                 __syncwarp();
                 if (tid == 0) LSTM_TRACE(i, 3);
-                if (lane == 0) tc::mbar_arrive(hs_empty + hb);       // this warp has consumed the signal
+                if (lane == 0) tc::mbar_arrive(hs_empty + hb);       // this warp is done with the h slot
                 tc::mbar_wait(red_empty + rb, (uint32_t)((n / npair) & 1) ^ 1);
                 {
                     // C fragment: rows (gate columns) g8, g8 + 8 of the m-tile; columns (clips) 2*t4, 2*t4 + 1
@@ -370,7 +366,6 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                     unsigned seen = ld_acquire_u32(p.barrier + g);
                     while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
                     if (lane == 0) LSTM_TRACE(t * ng, 1);
-                    if (MMA) { tc::mbar_arrive(hs_full + g); continue; }   // the compute lanes load their fragments themselves
                     asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                     tc::mbar_arrive_expect_tx(hs_full + g, (uint32_t)(nb * H * 4));
                     for (int bb = 0; bb < nb; ++bb)
@@ -388,7 +383,6 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
                 unsigned seen = ld_acquire_u32(p.barrier + g);
                 while (seen < (unsigned)t * nctas) seen = ld_acquire_u32(p.barrier + g);
                 LSTM_TRACE(i, 1);
-                if (MMA) { tc::mbar_arrive(hs_full + hb); continue; }   // the compute lanes load their fragments themselves
                 asm volatile("fence.proxy.async;" ::: "memory");     // acquired generic writes -> visible to the bulk copy
                 tc::mbar_arrive_expect_tx(hs_full + hb, (uint32_t)(nb * H * 4));
                 float* dst = Hs + hb * GB * H;
@@ -435,7 +429,7 @@ int lstm_pick_units(int H) {
 
 template <int UNITS, int GB, bool MMA>
 static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
-    int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB, !MMA);
+    int nbuf = lstm_pick_nbuf(p.H, p.B, UNITS, GB, true);
     // cell pairs: 3 when there are at least 3 independent clip groups to keep busy and the extra exchange buffer fits
     // per-group loader lanes only pay with many groups (r2f / r2g: config 2 (2 groups) 3.7 vs 3.45 ms, config 4 (4 groups) 8.15 vs
     // 6.5 ms, config 3 (8 groups) 36.8 vs 38.0 ms per SLSTM)
@@ -444,10 +438,10 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     // two compute-warp sets when an item's gate GEMM is small (H <= 512) and there are other groups to work on
     int nset = (p.H <= 512 && ngroups >= 2) ? 2 : 1;
     if (const char* v = getenv("FCB_LSTM_NSET")) { const int f = atoi(v); if (f == 1 || f == 2) nset = f; }                // experiments
-    if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3, !MMA) <= 220 * 1024) npair = 3;
+    if ((p.B + GB - 1) / GB >= 3 && lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, 3) <= 220 * 1024) npair = 3;
     if (const char* v = getenv("FCB_LSTM_PAIRS")) { const int f = atoi(v); if (f == 2 || (f == 3 && npair == 3)) npair = f; }   // experiments
     if (const char* v = getenv("FCB_LSTM_PLOAD")) pload = atoi(v) != 0;
-    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair, !MMA);
+    const size_t smem = lstm_seq_smem_bytes(p.H, p.B, UNITS, GB, nbuf, npair);
     // the tensor-core gate GEMM needs whole k-steps per warp
     if (MMA && (p.H % 16 != 0 || ((p.H / 16) % (8 / nset)) != 0 || (p.H / 16) / (8 / nset) > 8)) return launch_seq<UNITS, GB, false>(p, st);
     auto kern = lstm_seq_kernel<UNITS, GB, MMA>;
