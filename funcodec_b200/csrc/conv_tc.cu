@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
 #define tq_rows ka.tq_rows                  /* rows per phase the tensor map exposes */
     auto tile_interior = [&](int t0) -> bool {
         if (nraw == 0) return false;
-        const int lo = t0 * S - p.pad_l;                                // first / last input row a valid output of the tile needs
-        const int hi = (t0 + TC_M - 1) * S - p.pad_l + (K - 1);
-        return lo >= 0 && hi < tq_rows * S && t0 + TC_M <= p.T_out;
+        // first / last input row that a VALID output row of the tile needs (a partial last tile only counts its real rows: the
+        // rows a 1x1 layer does not have arrive zero-filled and feed discarded output rows only)
+        const int t_last = (t0 + TC_M < p.T_out ? t0 + TC_M : p.T_out) - 1;
+        const int lo = t0 * S - p.pad_l;
+        const int hi = t_last * S - p.pad_l + (K - 1);
+        return lo >= 0 && hi < tq_rows * S;
     };
     // accumulator ring depth.  The MMA -> commit -> epilogue -> release hand-off costs ~2000 cycles per tile pair (measured: the
     // pure barrier skeleton of the small-tile layers), so layers whose tile is one accumulation group keep up to 8 tiles in
@@ -871,7 +874,8 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
     // raw TMA ring: 1-D layers with interior tiles (n_tt >= 3), channel counts the box covers, 16-byte aligned views
     CUtensorMap tm0{}, tm1{};
     // (2-D: a 32-channel unit must be a slice of ONE frequency tap -> cin % 32 == 0, or the single tap of a 16-channel 1x1 conv)
-    bool want_raw = g_tma_state == 1 && n_tt >= 3 && p.T_in / p.S >= 1 &&
+    // (interior tiles exist when the clip has at least 3 tiles, or for 1x1 layers -- no halo -- always)
+    bool want_raw = g_tma_state == 1 && (n_tt >= 3 || (p.K == 1 && p.S == 1 && p.pad_l == 0)) && p.T_in / p.S >= 1 &&
                     (freq ? (p.fq.cin % TC_KC == 0 || (p.fq.cin == 16 && p.fq.KF == 1)) : (p.C_in % TC_KC == 0 || p.C_in == 16));
     // 2-D layers: built and parity-tested (5-D tensor maps), but measured SLOWER than the per-thread gather at config 4 (r2g: conv
     // stack 37.3 vs 33.6 ms) -- the K_F-fold re-read of every input row makes the unit stream L2-bound either way and the TMA path
