@@ -258,76 +258,97 @@ __global__ void sumsq_partials_kernel(const float* __restrict__ x, int L, int ch
     }
 }
 
-// Conv with a single output channel (the decoder's last SConv1d, seanet_decoder.py:160-164): pure HBM streaming
-// (reads C_in floats per sample, writes one).  One thread produces 4 consecutive samples from a transformed input
-// window staged in shared memory; weights are broadcast reads.  Input views must carry precomputed coefficients.
-constexpr int C1_TT = 4, C1_THREADS = 128, C1_TILE = C1_TT * C1_THREADS;
+// Conv with a single output channel (the decoder's last SConv1d, seanet_decoder.py:160-164): pure HBM streaming (reads C_in
+// floats per sample, writes one).  out[t] = bias + sum_k d_k[t + k - pad], d_k[r] = sum_c f(x[r][c]) w[k][c]: every input row is
+// loaded (coalesced: 8 lanes x 16 B per row, 4 rows per warp instruction), transformed and dotted with the K taps exactly ONCE
+// -- each lane holds the K x 4 weights of its 4 channels in registers, the 8 lanes of a row reduce with 3 shuffle levels -- and
+// the K partial products per row go through shared memory to the threads that own the outputs.  C_in == 32, K <= 8.
+constexpr int C1_THREADS = 256, C1_TILE = 1024, C1_KMAX = 8;
 
 __global__ void __launch_bounds__(C1_THREADS) conv1d_cout1_kernel(const ConvParams p) {
-    extern __shared__ __align__(16) float smem[];
+    __shared__ float D[C1_KMAX][C1_TILE + C1_KMAX];      // d_k of the tile's input rows (row index relative to t0 - pad_l)
+    __shared__ double red[64];
     const int C_in = p.C_in, K = p.K;
-    const int pitch = C_in + 1;
-    const int R = C1_TILE + K - 1;
-    float* Ws = smem;                       // [K][C_in]
-    float* Xs = Ws + ((K * C_in + 3) & ~3); // [R][pitch]
-    const int tid = threadIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
     const int t0 = blockIdx.x * C1_TILE;
     const bool has1 = p.in1.x != nullptr;
-    for (int e = tid; e < K * C_in; e += C1_THREADS) Ws[e] = __ldg(p.w + e);       // packed [k][ci][1]
+    const int jchunk = lane & 7, rsub = lane >> 3;
+    const int c = jchunk * 4;
     const float* x0 = p.in0.x + (long long)b * p.in0.clip_stride + (long long)p.in0.row_off * C_in;
     const float* x1 = has1 ? p.in1.x + (long long)b * p.in1.clip_stride + (long long)p.in1.row_off * C_in : nullptr;
-    const float* cf0 = p.in0.coef ? p.in0.coef + (long long)b * 2 * C_in : nullptr;
-    const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * C_in : nullptr;
+    float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), b0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b1 = b0;
+    if (p.in0.coef) {
+        const float* cf = p.in0.coef + (long long)b * 2 * C_in;
+        a0 = __ldg(reinterpret_cast<const float4*>(cf + c)); b0 = __ldg(reinterpret_cast<const float4*>(cf + C_in + c));
+    }
+    if (has1 && p.in1.coef) {
+        const float* cf = p.in1.coef + (long long)b * 2 * C_in;
+        a1 = __ldg(reinterpret_cast<const float4*>(cf + c)); b1 = __ldg(reinterpret_cast<const float4*>(cf + C_in + c));
+    }
+    float4 w[C1_KMAX];                                   // packed [k][ci][1]
+#pragma unroll
+    for (int k = 0; k < C1_KMAX; ++k) w[k] = k < K ? __ldg(reinterpret_cast<const float4*>(p.w + k * C_in + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int gt_max = (p.T_out - 1) - p.pad_l + (K - 1);
-    const int nvec = C_in / 4;
-    for (int e = tid; e < R * nvec; e += C1_THREADS) {
-        const int row = e / nvec, c = (e - row * nvec) * 4;
-        const int gt = t0 - p.pad_l + row;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int src = reflect_index(gt, p.T_ext);
-        if (gt <= gt_max && src >= 0 && src < p.T_in) {
-            const long long off = (long long)src * C_in + c;
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(x0 + off));
-            float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cf0) { a = __ldg(reinterpret_cast<const float4*>(cf0 + c)); bb = __ldg(reinterpret_cast<const float4*>(cf0 + C_in + c)); }
-            v.x = fmaf(xv.x, a.x, bb.x); v.y = fmaf(xv.y, a.y, bb.y); v.z = fmaf(xv.z, a.z, bb.z); v.w = fmaf(xv.w, a.w, bb.w);
-            if (has1) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                a = make_float4(1.f, 1.f, 1.f, 1.f); bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cf1) { a = __ldg(reinterpret_cast<const float4*>(cf1 + c)); bb = __ldg(reinterpret_cast<const float4*>(cf1 + C_in + c)); }
-                v.x = v.x + fmaf(yv.x, a.x, bb.x); v.y = v.y + fmaf(yv.y, a.y, bb.y);
-                v.z = v.z + fmaf(yv.z, a.z, bb.z); v.w = v.w + fmaf(yv.w, a.w, bb.w);
+    const int R = min(C1_TILE, p.T_out - t0) + K - 1;   // input rows of this tile
+    constexpr int UNR = 4;                               // rows in flight per lane
+    for (int rbase = warp * 4; rbase < R; rbase += 8 * 4 * UNR) {      // warp-uniform trip count (full-mask shuffles inside)
+        const int r0 = rbase + rsub;
+        float4 xv[UNR], yv[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int i = 0; i < UNR; ++i) {
+            const int row = r0 + i * 32;
+            const int gt = t0 - p.pad_l + row;
+            const int src = reflect_index(gt, p.T_ext);
+            ok[i] = row < R && gt <= gt_max && src >= 0 && src < p.T_in;
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            yv[i] = xv[i];
+            if (ok[i]) {
+                const long long off = (long long)src * C_in + c;
+                xv[i] = __ldcs(reinterpret_cast<const float4*>(x0 + off));
+                if (has1) yv[i] = __ldcs(reinterpret_cast<const float4*>(x1 + off));
             }
-            if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
         }
-        float* d = Xs + row * pitch + c;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+#pragma unroll
+        for (int i = 0; i < UNR; ++i) {
+            const int row = r0 + i * 32;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[i]) {
+                v.x = fmaf(xv[i].x, a0.x, b0.x); v.y = fmaf(xv[i].y, a0.y, b0.y); v.z = fmaf(xv[i].z, a0.z, b0.z); v.w = fmaf(xv[i].w, a0.w, b0.w);
+                if (has1) {
+                    v.x = v.x + fmaf(yv[i].x, a1.x, b1.x); v.y = v.y + fmaf(yv[i].y, a1.y, b1.y);
+                    v.z = v.z + fmaf(yv[i].z, a1.z, b1.z); v.w = v.w + fmaf(yv[i].w, a1.w, b1.w);
+                }
+                if (p.elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+            }
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < C1_KMAX; ++k) {
+                float d = fmaf(v.w, w[k].w, fmaf(v.z, w[k].z, fmaf(v.y, w[k].y, v.x * w[k].x)));
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if (jchunk == k) mine = d;
+            }
+            if (row < R && jchunk < K) D[jchunk][row] = mine;
+        }
     }
     __syncthreads();
-    // thread -> samples tid + 128*i (interleaved: conflict-free rows, coalesced stores)
-    float acc[C1_TT];
-#pragma unroll
-    for (int i = 0; i < C1_TT; ++i) acc[i] = 0.f;
-    for (int k = 0; k < K; ++k)
-        for (int c = 0; c < C_in; ++c) {
-            const float w = Ws[k * C_in + c];
-#pragma unroll
-            for (int i = 0; i < C1_TT; ++i) acc[i] = fmaf(Xs[(tid + C1_THREADS * i + k) * pitch + c], w, acc[i]);
-        }
     const float bias = __ldg(p.bias);
     float s = 0.f, ss = 0.f;
     float* outb = p.out + (long long)b * p.out_clip_stride;
 #pragma unroll
-    for (int i = 0; i < C1_TT; ++i) {
-        const int t = t0 + tid + C1_THREADS * i;
+    for (int i = 0; i < C1_TILE / C1_THREADS; ++i) {
+        const int tl = tid + C1_THREADS * i, t = t0 + tl;
         if (t < p.T_out) {
-            const float o = acc[i] + bias;
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc += D[k][tl + k];
+            const float o = acc + bias;
             outb[t] = o;
             s += o; ss = fmaf(o, o, ss);
         }
     }
     if (p.partials) {
-        __shared__ double red[64];
         double ds = (double)s, dss = (double)ss;
         block_reduce_2d(ds, dss, red);
         if (tid == 0) {
@@ -338,20 +359,15 @@ __global__ void __launch_bounds__(C1_THREADS) conv1d_cout1_kernel(const ConvPara
 }
 
 bool conv_cout1_supported(const ConvParams& p) {
-    return p.C_out == 1 && p.S == 1 && p.D == 1 && !p.pad_zero && !p.div_scale && p.C_in % 4 == 0 && p.C_in <= 64 &&
+    return p.C_out == 1 && p.S == 1 && p.D == 1 && !p.pad_zero && !p.div_scale && p.C_in == 32 && p.K <= C1_KMAX &&
            !(p.in0.stats && !p.in0.coef) && !(p.in1.x && p.in1.stats && !p.in1.coef);
 }
 int conv_cout1_num_parts(int T_out) { return (T_out + C1_TILE - 1) / C1_TILE; }
 
 cudaError_t launch_conv_cout1(const ConvParams& p, int B, cudaStream_t st, int* nparts) {
-    const size_t smem = (((size_t)p.K * p.C_in + 3) & ~(size_t)3) * 4 + (size_t)(C1_TILE + p.K - 1) * (p.C_in + 1) * 4;
-    {
-        cudaError_t e = ensure_dynamic_smem((const void*)conv1d_cout1_kernel, 200 * 1024);
-        if (e != cudaSuccess) return e;
-    }
     dim3 grid(conv_cout1_num_parts(p.T_out), B);
     *nparts = grid.x;
-    conv1d_cout1_kernel<<<grid, C1_THREADS, smem, st>>>(p);
+    conv1d_cout1_kernel<<<grid, C1_THREADS, 0, st>>>(p);
     return cudaGetLastError();
 }
 

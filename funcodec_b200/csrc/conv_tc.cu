@@ -541,6 +541,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
         // 2-D plain convs (no phase scatter, no padded columns) store [pseudo-clip][t][C_out] like a 1-D layer
         const bool plain_out = FREQ && p.fq.FR == 1 && p.fq.TR == 1 && p.fq.c_store == p.C_out;
         const float out_scale = p.tc_out_scale;
+        // fused GroupNorm finalisation: partials of the current clip written by this CTA since the last report
+        int fin_clip = -1, fin_local = 0;
+        auto fin_flush = [&]() {
+            // all 128 accumulator threads call this together.  Report this CTA's partial count for fin_clip; whoever completes the
+            // clip reduces ALL its partials in a fixed order (independent of which CTA does it) and writes stats + affine.
+            if (fin_clip < 0 || fin_local == 0) return;
+            int* flag = reinterpret_cast<int*>(red + 8);
+            if (quad == 0 && lane == 0) {
+                __threadfence();                                         // this CTA's partials before the count
+                const int old = atomicAdd(p.fin_counter + fin_clip, fin_local);
+                *flag = (old + fin_local == p.fin_parts) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool last_cta = *flag != 0;
+            if (last_cta) {
+                __threadfence();                                         // the other CTAs' partials after the count
+                const int t128 = quad * 32 + lane;
+                const double* pp = p.partials + (long long)fin_clip * p.fin_parts * 2;
+                double fs = 0.0, fss = 0.0;
+                for (int i = t128; i < p.fin_parts; i += 128) { fs += __ldcg(pp + 2 * i); fss += __ldcg(pp + 2 * i + 1); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    fs += __shfl_xor_sync(0xffffffffu, fs, o);
+                    fss += __shfl_xor_sync(0xffffffffu, fss, o);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone has read the flag
+                if (lane == 0) { red[quad * 2] = fs; red[quad * 2 + 1] = fss; }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const double ts = (red[0] + red[2]) + (red[4] + red[6]), tss = (red[1] + red[3]) + (red[5] + red[7]);
+                const double mean_d = ts / p.fin_count;
+                double var = tss / p.fin_count - mean_d * mean_d;
+                if (var < 0.0) var = 0.0;
+                const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)p.fin_eps));
+                if (t128 == 0) {
+                    p.fin_stats[2 * fin_clip] = mean;
+                    p.fin_stats[2 * fin_clip + 1] = rstd;
+                    p.fin_counter[fin_clip] = 0;                         // ready for the next launch
+                }
+                if (p.fin_coef)
+                    for (int c = t128; c < p.fin_C; c += 128) {
+                        const float a = rstd * p.fin_gamma[c];
+                        p.fin_coef[(long long)fin_clip * 2 * p.fin_C + c] = a;
+                        p.fin_coef[(long long)fin_clip * 2 * p.fin_C + p.fin_C + c] = p.fin_beta[c] - a * mean;
+                    }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");              // `red` / flag free again
+            fin_local = 0;
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const TcTile tl = tc_tile(tile, n_nt, n_tt);
             const int t = tl.tt * TC_M + quad * 32 + lane;
@@ -667,8 +715,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
                     dst[0] = (red[0] + red[2]) + (red[4] + red[6]);
                     dst[1] = (red[1] + red[3]) + (red[5] + red[7]);
                 }
+                if (p.fin_counter) {
+                    const int clip = FREQ ? tl.b / p.fq.F_out : tl.b;
+                    if (clip != fin_clip) { fin_flush(); fin_clip = clip; }
+                    ++fin_local;
+                }
             }
         }
+        if (p.fin_counter && p.partials && !(p.dbg & 16)) fin_flush();
     }
     tc_fence_before_sync();
     __syncthreads();
