@@ -83,7 +83,9 @@ struct fcb_handle {
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
     int* fin_counter = nullptr;  // per-clip partial counters of the fused GroupNorm finalisation (conv_tc.cu), zero between launches
-    int fuse_stats = 1;          // "fuse_stats" option / FCB_FUSE_STATS=0: separate stats_finalize launches
+    int fuse_stats = 0;          // "fuse_stats" option / FCB_FUSE_STATS=1: GroupNorm finalisation inside the conv kernel.  OFF by default:
+                                 // measured slower at config 2 (r2m: conv stack 11.7 vs 10.8 ms -- the last CTA's serial reduction sits in
+                                 // every launch's tail) and neutral at B = 1; parity-tested, kept as an option
     unsigned long long* lstm_trace = nullptr;   // PROFILING ONLY (env FCB_LSTM_TRACE): managed buffer, dumped by fcb_destroy
     bool use_tc = true;      // tensor-core conv path (FCB_DISABLE_TC=1 or fcb_set_option disables it)
     int use_tc2d = 7;        // FreqCodec 2-D layers on the tensor-core path, bit mask of Conv2W::tc_class ("use_tc2d" option)
@@ -1691,7 +1693,7 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
         h->stft_tc = value != 0;
         return FCB_OK;
     }
-    if (strcmp(key, "fuse_stats") == 0) {          // GroupNorm finalisation inside the conv kernel (default) vs a separate launch
+    if (strcmp(key, "fuse_stats") == 0) {          // GroupNorm finalisation inside the conv kernel vs a separate launch (default)
         h->fuse_stats = value != 0;
         return FCB_OK;
     }
