@@ -1,4 +1,6 @@
-"""Condense `ncu --page raw --csv` into one line per kernel launch with the metrics the roofline needs."""
+"""Condense `ncu --page raw --csv` into one line per kernel launch with the metrics the roofline needs.
+usage: summarize_ncu_raw.py raw.csv [--traffic-json profiles/conv_traffic.json workload source-file-name]
+(the optional arguments also record dram read + write bytes summed over the listed launches for bench.py's roofline.traffic)"""
 import csv
 import sys
 
@@ -40,3 +42,22 @@ for row in rd[2:]:
             if v_ not in ("0", "0.000000", "", "n/a"):
                 out.append(f"{h_}={v_}")
     print(" ".join(out))
+
+if len(sys.argv) >= 6 and sys.argv[2] == "--traffic-json":
+    import json
+    import os
+    path, workload, source = sys.argv[3], sys.argv[4], sys.argv[5]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, n = 0.0, 0
+    for row in rd[2:]:
+        if len(row) < len(hdr):
+            continue
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if key in idx:
+                total += float(row[idx[key]].replace(",", "")) * scale.get(units[idx[key]], 1.0)
+        n += 1
+    d = {}
+    if os.path.exists(path):
+        d = json.load(open(path))
+    d[workload] = dict(bytes=total, launches=n, source=source)
+    json.dump(d, open(path, "w"), indent=1)
