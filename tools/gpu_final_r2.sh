@@ -3,6 +3,7 @@
 # conv launches (-> profiles/conv_traffic.json) + RVQ/LSTM.   tools/gpu_final_r2.sh <tag>
 TAG=${1:-r2z}
 mkdir -p gpurun_out
+timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 (time timeout 900 python -m pytest tests -m gpu -q -rf) > gpurun_out/pytest_full_${TAG}.txt 2>&1
 tail -6 gpurun_out/pytest_full_${TAG}.txt
 cp gpurun_out/parity_records.json gpurun_out/parity_records_${TAG}.json 2>/dev/null
