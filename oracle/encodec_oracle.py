@@ -122,7 +122,7 @@ def lstm_manual(x_tbc, p, prefix: str, num_layers: int):
 def lstm_aten(x_tbc, p, prefix: str, num_layers: int):
     """The reference's own call: nn.LSTM(dimension, dimension, num_layers) (lstm.py:20,24)."""
     H = x_tbc.shape[-1]
-    m = torch.nn.LSTM(H, H, num_layers).to(x_tbc.dtype)
+    m = torch.nn.LSTM(H, H, num_layers).to(device=x_tbc.device, dtype=x_tbc.dtype)
     with torch.no_grad():
         for name, par in m.named_parameters():
             par.copy_(p[f"{prefix}.lstm.{name}"])
