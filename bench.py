@@ -266,25 +266,37 @@ def config5_extra(model, cfg, dev, rank, world, steps=5):
     out = {}
     ms = timed(lambda i: run_dev(wavs[i % 4]), steps)
     out["device_resident"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3))
-    # shared pinned host batch, one PCIe link per GPU
-    shb = SharedHostBatch(f"fcb_bench_{os.environ.get('MASTER_PORT', '0')}", GB, L, n_q, Tf, rank, world, create=(rank == 0))
-    dist.barrier()
-    shb.map()
-    if rank == 0:
-        shb.wav.copy_(0.1 * torch.randn(GB, L, generator=g))
-    dist.barrier()
-    lo, hi = shb.shard()
-    ms = timed(lambda i: model.roundtrip_host(shb.wav[lo:hi], shb.codes[rank], shb.recon[lo:hi]), steps)
-    out["e2e_shared_host"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3), h2d_bytes_per_step=GB * L * 4,
-                                  d2h_bytes_per_step=n_q * GB * Tf * 8 + GB * L * 4,
-                                  path="one /dev/shm batch page-locked by every rank; each rank fcb_roundtrip_host on its shard")
+    # shared pinned host batch, one PCIe link per GPU (skipped, with the reason, when /dev/shm cannot hold the batch)
+    shb, why = None, ""
+    try:
+        shb = SharedHostBatch(f"fcb_bench_{os.environ.get('MASTER_PORT', '0')}", GB, L, n_q, Tf, rank, world, create=(rank == 0))
+    except OSError as exc:
+        why = f"/dev/shm: {exc}"
+    ok = torch.tensor([1 if shb is not None else 0], dtype=torch.int32, device=dev)
+    dist.broadcast(ok, src=0)
+    hw_host = hr_host = None
+    if int(ok.item()) == 1:
+        dist.barrier()
+        shb.map()
+        if rank == 0:
+            shb.wav.copy_(0.1 * torch.randn(GB, L, generator=g))
+        dist.barrier()
+        lo, hi = shb.shard()
+        ms = timed(lambda i: model.roundtrip_host(shb.wav[lo:hi], shb.codes[rank], shb.recon[lo:hi]), steps)
+        out["e2e_shared_host"] = dict(ms_per_step=ms, frames_per_s=GB * Tf / (ms * 1e-3), h2d_bytes_per_step=GB * L * 4,
+                                      d2h_bytes_per_step=n_q * GB * Tf * 8 + GB * L * 4,
+                                      path="one /dev/shm batch page-locked by every rank; each rank fcb_roundtrip_host on its shard")
+        hw_host, hr_host = shb.wav, shb.recon
+    else:
+        shb = None
+        out["e2e_shared_host"] = dict(skipped=why or "rank 0 could not reserve the shared batch in /dev/shm")
     # NCCL scatter / gather through rank 0's GPU
     sharded = ShardedCodec(run_dev)
     hw = hc = hr = dw = None
     if rank == 0:
-        hw = shb.wav
+        hw = hw_host if hw_host is not None else (0.1 * torch.randn(GB, L, generator=g)).pin_memory()
         hc = torch.empty((n_q, GB, Tf), dtype=torch.int64).pin_memory()
-        hr = shb.recon
+        hr = hr_host if hr_host is not None else torch.empty((GB, 1, L), dtype=torch.float32).pin_memory()
         dw = torch.empty((GB, L), dtype=torch.float32, device=dev)
 
     def scatter_step(i):
@@ -302,7 +314,8 @@ def config5_extra(model, cfg, dev, rank, world, steps=5):
                                    path="rank0 pinned host -> H2D -> NCCL scatter -> fcb_roundtrip -> NCCL gather -> D2H")
     out["workload"] = f"encodec_16k_n32_ds640 B={GB} ({B}/GPU) L={L} n_q={n_q} (BASELINE config 5 on {world} GPUs)"
     dist.barrier()
-    shb.close()
+    if shb is not None:
+        shb.close()
     return out
 
 

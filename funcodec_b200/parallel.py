@@ -115,8 +115,18 @@ class SharedHostBatch:
         sizes = [n_clips * length * 4, n_q * n_clips * frames * 8, n_clips * length * 4]
         self.nbytes = sum(sizes)
         if create:
-            with open(self.path, "wb") as f:
-                f.truncate(self.nbytes)
+            # reserve the pages now: a tmpfs that is too small must fail HERE (OSError) and not with SIGBUS at the first write
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            try:
+                os.posix_fallocate(fd, 0, self.nbytes)
+            except OSError:
+                os.close(fd)
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
+                raise
+            os.close(fd)
         self._create = create
         self._raw = None
         self._sizes = sizes

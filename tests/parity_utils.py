@@ -62,6 +62,10 @@ def classify_codes(codes_test, codes_ref, margins_ref, margin_tol):
 
 def assert_codes_parity(codes_test, codes_ref, margins_ref, margin_tol, min_exact_rate=0.97, what="", **extra):
     r = classify_codes(codes_test, codes_ref, margins_ref, margin_tol)
+    # The bar follows what was MEASURED on B200 (profiles/parity_r2.json: at most ONE near-tie flip in any comparison, 3999 / 4000
+    # frames on config 2, 100 % elsewhere): whatever a caller passes, no more than max(2 frames, 0.5 %) may flip.
+    allowed = max(2, int(0.005 * r["total_frames"]))
+    min_exact_rate = max(min_exact_rate, 1.0 - allowed / max(1, r["total_frames"]) - 1e-9)
     n_q = int(np.asarray(codes_ref).shape[0])
     first = r["first_stage"]
     # stage-level exact count: every (stage, frame) before a frame's first divergence matches by construction
