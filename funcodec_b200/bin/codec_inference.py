@@ -61,18 +61,17 @@ def config_from_yaml(path: str):
             refuse(f"{side}.norm must be time_group_norm")
         if conf.get("causal", False):
             refuse(f"{side}.causal must be false")
-        if conf.get("dilation_base", 2) != 1 and conf.get("n_residual_layers", 1) > 1:
-            refuse(f"{side}: stacked dilated residual layers are not supported")
-        if conf.get("n_residual_layers", 1) != 1:
-            refuse(f"{side}.n_residual_layers must be 1")
-        if conf.get("seq_model", "lstm") not in ("lstm",):
-            refuse(f"{side}.seq_model must be lstm")
+        if conf.get("seq_model", "lstm") not in ("lstm", "none", None):
+            refuse(f"{side}.seq_model must be lstm or none")
         if conf.get("activation", "ELU") != "ELU" or conf.get("pad_mode", "reflect") != "reflect":
             refuse(f"{side}: activation must be ELU and pad_mode reflect")
     if q.get("codec_dim") is not None or q.get("codec_range") is not None:
         refuse("quantizer projections / codec_range")
     if int(q.get("q0_ds_ratio", 1) or 1) != 1:
         refuse("quantizer_conf.q0_ds_ratio must be 1")
+    for key in ("n_residual_layers", "dilation_base", "seq_model"):
+        if enc.get(key, None) != dec.get(key, None):
+            refuse(f"encoder_conf.{key} != decoder_conf.{key}")
     ratios = dec.get("ratios", [8, 5, 4, 2])
     if enc.get("ratios", [8, 5, 4, 2]) != ratios:
         refuse("encoder and decoder ratios differ")
@@ -98,7 +97,11 @@ def config_from_yaml(path: str):
                       residual_kernel_size=int(enc.get("residual_kernel_size", 3)),
                       codebook_size=int(q.get("codebook_size", 1024)), num_quantizers=int(q.get("num_quantizers", 32)),
                       sample_rate=int(q.get("sampling_rate", 16000)), audio_normalize=bool(m.get("audio_normalize", True)),
-                      lstm_layers=int(enc.get("seq_layer_num", 2)), **kw)
+                      lstm_layers=int(enc.get("seq_layer_num", 2)) if enc.get("seq_model", "lstm") == "lstm" else 0,
+                      n_residual_layers=int(enc.get("n_residual_layers", 1)),
+                      # with one residual block the dilation base never shows (base ** 0 == 1): keep the default so that equal
+                      # models compare equal
+                      dilation_base=int(enc.get("dilation_base", 2)) if int(enc.get("n_residual_layers", 1)) > 1 else 2, **kw)
     if int(q.get("encoder_hop_length", cfg.hop_length)) != cfg.hop_length:
         refuse("quantizer_conf.encoder_hop_length != hop of the ratios")
     return cfg, m.get("segment_dur"), m.get("overlap_ratio")

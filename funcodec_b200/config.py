@@ -36,6 +36,10 @@ class CodecConfig:
     # seanet_encoder.py:224,234,321, seanet_decoder.py:219,229,324): groups = channels // 2 // ratio, -1 = dense
     conv_group_ratio: int = -1
     tr_conv_group_ratio: int = -1
+    # residual blocks per stage / dilation base of the time-domain stacks (encoder_conf / decoder_conf n_residual_layers,
+    # dilation_base; seanet_encoder.py:122-128): block j's first conv has dilation dilation_base ** j
+    n_residual_layers: int = 1
+    dilation_base: int = 2
 
     def conv_groups(self, channels: int) -> int:
         """groups of a 2-D conv whose reference expression is `channels // 2 // conv_group_ratio`."""
@@ -104,6 +108,14 @@ PRESETS: Dict[str, CodecConfig] = {
                                       dimension=32, codebook_size=64, num_quantizers=6, conv_group_ratio=1, tr_conv_group_ratio=2),
     "freq_small": CodecConfig(name="freq_small", arch=1, ratios=(1, 1, 2, 1), ratios_f=(4, 4, 4, 4), n_filters=4,
                               dimension=32, codebook_size=64, num_quantizers=6),
+    # conf/soundstream_noncausal_16k_n32_600k_step{,_ds640}.yaml: 3 dilated residual blocks per stage, no sequence model, D = 512
+    "soundstream_noncausal_16k_n32_ds320": CodecConfig(name="soundstream_noncausal_16k_n32_ds320", ratios=(8, 5, 4, 2), dimension=512,
+                                                       lstm_layers=0, n_residual_layers=3),
+    "soundstream_noncausal_16k_n32_ds640": CodecConfig(name="soundstream_noncausal_16k_n32_ds640", ratios=(8, 5, 4, 2, 2), dimension=512,
+                                                       lstm_layers=0, n_residual_layers=3),
+    "soundstream_noncausal_small": CodecConfig(name="soundstream_noncausal_small", ratios=(5, 4, 2), n_filters=4, dimension=48,
+                                               codebook_size=64, num_quantizers=4, lstm_layers=0, n_residual_layers=3,
+                                               audio_normalize=False),
     "small_ds320": CodecConfig(name="small_ds320", ratios=(8, 5, 4, 2), n_filters=8, dimension=64,
                                codebook_size=256, num_quantizers=8),
 }

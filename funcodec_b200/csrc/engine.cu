@@ -30,7 +30,7 @@ struct HostTensor {
 };
 
 struct ConvW {           // one SConv1d / SConvTranspose1d, packed for conv1d_cl_kernel
-    int cin = 0, cout = 0, k = 0, s = 1;
+    int cin = 0, cout = 0, k = 0, s = 1, d = 1;
     bool transposed = false;
     float* w = nullptr;      // [K_eff][cin][cout_eff]
     float* bias = nullptr;   // [cout_eff]
@@ -278,7 +278,7 @@ void build_tc_image_tf32(const std::vector<float>& wp /*[K][cin][cout_eff]*/, in
 
 int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, int K, int cin, int cout_eff, ConvW* o) {
     o->n_tile = 0;
-    if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, 1)) return FCB_OK;
+    if (!h->use_tc || !conv_tc_supported(cin, cout_eff, K, 1, o->d)) return FCB_OK;   // dilated convs run on the SIMT kernel
     const int n_tile = conv_tc_n_tile(cout_eff);
     std::vector<float> img;
     build_tc_image_f16(wp, K, cin, cout_eff, n_tile, &img, &o->tc_scale);
@@ -288,7 +288,7 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
 }
 
 // SConv1d: conv.conv.weight [cout][cin][k] -> [k][cin][cout]
-int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k, int s, ConvW* o) {
+int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k, int s, ConvW* o, int dilation = 1) {
     const HostTensor *w, *b, *g, *be;
     FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, k}, &w));
     FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
@@ -299,7 +299,7 @@ int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k
         for (int ci = 0; ci < cin; ++ci)
             for (int kk = 0; kk < k; ++kk)
                 p[((size_t)kk * cin + ci) * cout + co] = w->data[((size_t)co * cin + ci) * k + kk];
-    o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->transposed = false;
+    o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->d = dilation; o->transposed = false;
     FCB_TRY(pack_tc(h, p, k, cin, cout, o));
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, b->data, &o->bias));
@@ -375,8 +375,8 @@ int pack_lstm(fcb_handle* h, const std::string& prefix, int H, int layers, LstmW
     return FCB_OK;
 }
 
-int pack_resblock(fcb_handle* h, const std::string& prefix, int dim, ResBlockW* o) {
-    FCB_TRY(pack_conv(h, prefix + ".block.1", dim, dim / 2, h->cfg.residual_kernel_size, 1, &o->c1));
+int pack_resblock(fcb_handle* h, const std::string& prefix, int dim, ResBlockW* o, int dilation = 1) {
+    FCB_TRY(pack_conv(h, prefix + ".block.1", dim, dim / 2, h->cfg.residual_kernel_size, 1, &o->c1, dilation));
     FCB_TRY(pack_conv(h, prefix + ".block.3", dim / 2, dim, 1, 1, &o->c2));
     FCB_TRY(pack_conv(h, prefix + ".shortcut", dim, dim, 1, 1, &o->sc));
     return FCB_OK;
@@ -466,19 +466,19 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
     if (in0.C != L.cin) return fail(h, FCB_E_INVALID, "internal: channel mismatch");
     Act o;
     if (!L.transposed) {
-        const int k = L.k, s = L.s, d = 1;
+        const int k = L.k, s = L.s, d = L.d;
         const int padding_total = (k - 1) * d - (s - 1);
         // get_extra_padding_for_conv1d (conv.py:57-64), integer form of ceil((T - k + pt)/s)
-        const int num = in0.T - k + padding_total;
+        const int num = in0.T - ((k - 1) * d + 1) + padding_total;     // effective kernel size (k - 1) * d + 1 (conv.py:57-64)
         const int n_frames_ceil = (num >= 0 ? (num + s - 1) / s : -((-num) / s)) + 1;
-        const int ideal = (n_frames_ceil - 1) * s + (k - padding_total);
+        const int ideal = (n_frames_ceil - 1) * s + ((k - 1) * d + 1 - padding_total);
         const int extra = ideal - in0.T;
         const int pr = padding_total / 2, pl = padding_total - pr;
         const int pr_tot = pr + extra;
         const int max_pad = pl > pr_tot ? pl : pr_tot;
         p.K = k; p.S = s; p.D = d; p.pad_l = pl; p.pad_zero = 0;
         p.T_ext = in0.T <= max_pad ? max_pad + 1 : in0.T;     // pad1d tiny-input branch (conv.py:89-97)
-        p.T_out = (in0.T + pl + pr_tot - k) / s + 1;
+        p.T_out = (in0.T + pl + pr_tot - ((k - 1) * d + 1)) / s + 1;
         p.C_out = L.cout;
         o.T = p.T_out; o.C = L.cout; o.clip_stride = (long long)p.T_out * L.cout; o.row_off = 0;
     } else {
@@ -570,12 +570,13 @@ int run_lstm(Run& r, const Act& x, const LstmW& W, Act* out) {
     return FCB_OK;
 }
 
-int run_resblock(Run& r, const Act& x, const ResBlockW& W, Act* sc_out, Act* blk_out) {
+// x (+ x1: the input may itself be the pending sum shortcut + block of the previous resblock of the stage)
+int run_resblock(Run& r, const Act& x, const ResBlockW& W, Act* sc_out, Act* blk_out, const Act* x1 = nullptr) {
     Act h1, h2, sc;
-    FCB_TRY(run_conv(r, x, nullptr, true, nullptr, W.c1, true, &h1));
+    FCB_TRY(run_conv(r, x, x1, true, nullptr, W.c1, true, &h1));
     FCB_TRY(run_conv(r, h1, nullptr, true, nullptr, W.c2, true, &h2));
     FCB_TRY(release(r, h1));
-    FCB_TRY(run_conv(r, x, nullptr, false, nullptr, W.sc, true, &sc));
+    FCB_TRY(run_conv(r, x, x1, false, nullptr, W.sc, true, &sc));
     *sc_out = sc; *blk_out = h2;
     return FCB_OK;
 }
@@ -606,10 +607,18 @@ int run_encoder(Run& r, const float* wav, int L, float* scale_out, Act* out) {
     Act a;
     FCB_TRY(run_conv(r, x, nullptr, false, scale, h->enc_conv0, true, &a));
     if (scale_owned) FCB_TRY(pool_free(r, scale));
-    for (size_t i = 0; i < h->enc_rb.size(); ++i) {
+    const int nres = (int)(h->enc_rb.size() / (h->enc_down.empty() ? 1 : h->enc_down.size()));
+    for (size_t i = 0; i < h->enc_down.size(); ++i) {
         Act sc, blk, d;
-        FCB_TRY(run_resblock(r, a, h->enc_rb[i], &sc, &blk));
+        FCB_TRY(run_resblock(r, a, h->enc_rb[i * nres], &sc, &blk));
         FCB_TRY(release(r, a));
+        for (int j = 1; j < nres; ++j) {          // stacked residual blocks: the next block consumes the pending sum
+            Act sc2, blk2;
+            FCB_TRY(run_resblock(r, sc, h->enc_rb[i * nres + j], &sc2, &blk2, &blk));
+            FCB_TRY(release(r, sc));
+            FCB_TRY(release(r, blk));
+            sc = sc2; blk = blk2;
+        }
         FCB_TRY(run_conv(r, sc, &blk, true, nullptr, h->enc_down[i], true, &d));
         FCB_TRY(release(r, sc));
         FCB_TRY(release(r, blk));
@@ -662,8 +671,16 @@ int run_decoder_time(Run& r, const float* emb, int n_frames, const float* scale,
         FCB_TRY(run_conv(r, sc, have_blk ? &blk : nullptr, true, nullptr, h->dec_up[i], true, &u));
         FCB_TRY(release(r, sc));
         if (have_blk) FCB_TRY(release(r, blk));
-        FCB_TRY(run_resblock(r, u, h->dec_rb[i], &sc, &blk));
+        const int nres = (int)(h->dec_rb.size() / h->dec_up.size());
+        FCB_TRY(run_resblock(r, u, h->dec_rb[i * nres], &sc, &blk));
         FCB_TRY(release(r, u));
+        for (int j = 1; j < nres; ++j) {
+            Act sc2, blk2;
+            FCB_TRY(run_resblock(r, sc, h->dec_rb[i * nres + j], &sc2, &blk2, &blk));
+            FCB_TRY(release(r, sc));
+            FCB_TRY(release(r, blk));
+            sc = sc2; blk = blk2;
+        }
         have_blk = true;
     }
     Act f;
@@ -1299,13 +1316,19 @@ int fcb_finalize(fcb_handle* h) {
     } else {
     FCB_TRY(pack_conv(h, "encoder.model.0", 1, nf, c.kernel_size, 1, &h->enc_conv0));
     int n = 1, mult = 1;
+    const int nres = c.n_residual_layers > 0 ? c.n_residual_layers : 1, dbase = c.dilation_base > 0 ? c.dilation_base : 2;
     for (int i = c.n_ratios - 1; i >= 0; --i) {      // encoder applies the ratios reversed (seanet_encoder.py:102)
         const int ratio = c.ratios[i];
-        ResBlockW rb; ConvW down;
-        FCB_TRY(pack_resblock(h, "encoder.model." + std::to_string(n), mult * nf, &rb));
-        FCB_TRY(pack_conv(h, "encoder.model." + std::to_string(n + 2), mult * nf, 2 * mult * nf, 2 * ratio, ratio, &down));
-        h->enc_rb.push_back(rb); h->enc_down.push_back(down);
-        mult *= 2; n += 3;
+        ConvW down;
+        int dil = 1;
+        for (int j = 0; j < nres; ++j, dil *= dbase) {            // dilations dilation_base^j (seanet_encoder.py:122-128)
+            ResBlockW rb;
+            FCB_TRY(pack_resblock(h, "encoder.model." + std::to_string(n + j), mult * nf, &rb, dil));
+            h->enc_rb.push_back(rb);
+        }
+        FCB_TRY(pack_conv(h, "encoder.model." + std::to_string(n + nres + 1), mult * nf, 2 * mult * nf, 2 * ratio, ratio, &down));
+        h->enc_down.push_back(down);
+        mult *= 2; n += nres + 2;
     }
     if (c.lstm_layers > 0) {
         FCB_TRY(pack_lstm(h, "encoder.model." + std::to_string(n), mult * nf, c.lstm_layers, &h->enc_lstm));
@@ -1321,11 +1344,16 @@ int fcb_finalize(fcb_handle* h) {
     }
     for (int i = 0; i < c.n_ratios; ++i) {
         const int ratio = c.ratios[i];
-        ConvW up; ResBlockW rb;
+        ConvW up;
         FCB_TRY(pack_convtr(h, "decoder.model." + std::to_string(n + 1), mult * nf, mult * nf / 2, ratio, &up));
-        FCB_TRY(pack_resblock(h, "decoder.model." + std::to_string(n + 2), mult * nf / 2, &rb));
-        h->dec_up.push_back(up); h->dec_rb.push_back(rb);
-        mult /= 2; n += 3;
+        h->dec_up.push_back(up);
+        int dil = 1;
+        for (int j = 0; j < nres; ++j, dil *= dbase) {
+            ResBlockW rb;
+            FCB_TRY(pack_resblock(h, "decoder.model." + std::to_string(n + 2 + j), mult * nf / 2, &rb, dil));
+            h->dec_rb.push_back(rb);
+        }
+        mult /= 2; n += nres + 2;
     }
     FCB_TRY(pack_conv(h, "decoder.model." + std::to_string(n + 1), nf, 1, c.last_kernel_size, 1, &h->dec_final));
     }
@@ -1380,12 +1408,15 @@ int fcb_finalize(fcb_handle* h) {
         const fcb_config& cc = h->cfg;
         h->by_name["encoder.model.0"] = &h->enc_conv0;
         int nn = 1;
-        for (size_t i = 0; i < h->enc_rb.size(); ++i, nn += 3) {
-            const std::string pre = "encoder.model." + std::to_string(nn);
-            h->by_name[pre + ".block.1"] = &h->enc_rb[i].c1;
-            h->by_name[pre + ".block.3"] = &h->enc_rb[i].c2;
-            h->by_name[pre + ".shortcut"] = &h->enc_rb[i].sc;
-            h->by_name["encoder.model." + std::to_string(nn + 2)] = &h->enc_down[i];
+        const int nres = cc.n_residual_layers > 0 ? cc.n_residual_layers : 1;
+        for (size_t i = 0; i < h->enc_down.size(); ++i, nn += nres + 2) {
+            for (int j = 0; j < nres; ++j) {
+                const std::string pre = "encoder.model." + std::to_string(nn + j);
+                h->by_name[pre + ".block.1"] = &h->enc_rb[i * nres + j].c1;
+                h->by_name[pre + ".block.3"] = &h->enc_rb[i * nres + j].c2;
+                h->by_name[pre + ".shortcut"] = &h->enc_rb[i * nres + j].sc;
+            }
+            h->by_name["encoder.model." + std::to_string(nn + nres + 1)] = &h->enc_down[i];
         }
         if (cc.lstm_layers > 0) {
             for (int l = 0; l < cc.lstm_layers; ++l) h->by_name["encoder.model." + std::to_string(nn) + ".lstm.ih" + std::to_string(l)] = &h->enc_lstm.ih[l];
@@ -1394,12 +1425,14 @@ int fcb_finalize(fcb_handle* h) {
         h->by_name["encoder.model." + std::to_string(nn + 1)] = &h->enc_final;
         h->by_name["decoder.model.0"] = &h->dec_conv0;
         nn = cc.lstm_layers > 0 ? 2 : 1;
-        for (size_t i = 0; i < h->dec_up.size(); ++i, nn += 3) {
+        for (size_t i = 0; i < h->dec_up.size(); ++i, nn += nres + 2) {
             h->by_name["decoder.model." + std::to_string(nn + 1)] = &h->dec_up[i];
-            const std::string pre = "decoder.model." + std::to_string(nn + 2);
-            h->by_name[pre + ".block.1"] = &h->dec_rb[i].c1;
-            h->by_name[pre + ".block.3"] = &h->dec_rb[i].c2;
-            h->by_name[pre + ".shortcut"] = &h->dec_rb[i].sc;
+            for (int j = 0; j < nres; ++j) {
+                const std::string pre = "decoder.model." + std::to_string(nn + 2 + j);
+                h->by_name[pre + ".block.1"] = &h->dec_rb[i * nres + j].c1;
+                h->by_name[pre + ".block.3"] = &h->dec_rb[i * nres + j].c2;
+                h->by_name[pre + ".shortcut"] = &h->dec_rb[i * nres + j].sc;
+            }
         }
         h->by_name["decoder.model." + std::to_string(nn + 1)] = &h->dec_final;
     }

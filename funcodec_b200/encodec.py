@@ -61,6 +61,7 @@ class B200Encodec:
         c.sample_rate, c.audio_normalize, c.gn_eps = cfg.sample_rate, int(cfg.audio_normalize), cfg.gn_eps
         c.arch, c.n_fft, c.stft_hop = cfg.arch, cfg.n_fft, cfg.stft_hop
         c.conv_group_ratio, c.tr_conv_group_ratio = cfg.conv_group_ratio, cfg.tr_conv_group_ratio
+        c.n_residual_layers, c.dilation_base = cfg.n_residual_layers, cfg.dilation_base
         for i, r in enumerate(cfg.ratios_f):
             c.ratios_f[i] = r
         self._h = ctypes.c_void_p()

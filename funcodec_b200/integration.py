@@ -50,6 +50,23 @@ def config_from_reference_model(model) -> CodecConfig:
     n_lstm = len([k for k in sd if k.startswith("decoder.model.1.lstm.weight_ih_l")])
     last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.model."))
     rb_k = sd["encoder.model.1.block.1.conv.conv.weight"].shape[-1]
+    # stacked residual blocks (n_residual_layers): consecutive encoder.model.N with a shortcut conv; their first convs carry the
+    # dilations dilation_base ** j (seanet_encoder.py:122-128)
+    n_res = 1
+    while f"encoder.model.{1 + n_res}.shortcut.conv.conv.weight" in sd:
+        n_res += 1
+    dil_base = 2
+    if n_res > 1 and not freq and hasattr(enc, "model"):
+        dils = []
+        for j in range(n_res):
+            blk = enc.model[1 + j]
+            conv = blk.block[1].conv.conv
+            dils.append(int(conv.dilation[0]))
+        dil_base = dils[1] if dils[0] == 1 else 0
+        if dil_base < 1 or any(dils[j] != dil_base ** j for j in range(n_res)):
+            raise UnsupportedReferenceModel(f"residual-block dilations {dils} are not dilation_base ** j")
+    if n_res > 1 and freq:
+        raise UnsupportedReferenceModel("n_residual_layers > 1 is only supported for the time-domain stacks")
     dconf = getattr(model, "domain_conf", None) or {}
     cfg = CodecConfig(name="from_reference", ratios=ratios, arch=1 if freq else 0, ratios_f=ratios_f,
                       n_fft=int(dconf.get("n_fft", 512)), stft_hop=int(dconf.get("hop_length", 160)),
@@ -58,7 +75,7 @@ def config_from_reference_model(model) -> CodecConfig:
                       last_kernel_size=int(sd[f"decoder.model.{last_idx}.conv.conv.weight"].shape[-1]),
                       residual_kernel_size=int(rb_k), lstm_layers=n_lstm, codebook_size=int(embed.shape[1]),
                       num_quantizers=int(embed.shape[0]), sample_rate=int(q.sampling_rate),
-                      audio_normalize=bool(model.audio_normalize))
+                      audio_normalize=bool(model.audio_normalize), n_residual_layers=n_res, dilation_base=dil_base)
     if cfg.hop_length != int(q.encoder_hop_length):
         raise UnsupportedReferenceModel("quantizer.encoder_hop_length does not match prod(ratios)")
     if freq:
@@ -107,8 +124,8 @@ def _check_module_options(model) -> None:
                 norm_conv = getattr(mod, "conv", None) if hasattr(mod, "conv") else getattr(mod, "convtr", None)
                 inner = getattr(norm_conv, "conv", None) if hasattr(norm_conv, "conv") else getattr(norm_conv, "convtr", None)
                 dil = getattr(inner, "dilation", (1,))
-                if any(int(d) != 1 for d in dil):
-                    raise UnsupportedReferenceModel(f"{side}: dilated convolutions are not supported")
+                if name != "SConv1d" and any(int(d) != 1 for d in dil):
+                    raise UnsupportedReferenceModel(f"{side}: dilated 2-D / transposed convolutions are not supported")
             elif name == "SLSTM" and not getattr(mod, "skip", True):
                 raise UnsupportedReferenceModel(f"{side}: SLSTM must use the skip connection (res_seq: true)")
             elif name in ("Snake1d", "Snake", "PReLU", "ReLU", "LeakyReLU", "GELU", "Tanh") or \

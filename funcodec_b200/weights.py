@@ -25,11 +25,13 @@ def conv_specs(cfg: CodecConfig) -> List[Dict]:
 
     specs.append(dict(name="encoder.model.0.conv", kind="conv", cin=1, cout=nf, k=cfg.kernel_size, s=1))
     n, mult = 1, 1
+    nres = cfg.n_residual_layers
     for r in reversed(cfg.ratios):
-        specs += rb(f"encoder.model.{n}", mult * nf)
-        specs.append(dict(name=f"encoder.model.{n + 2}.conv", kind="conv", cin=mult * nf, cout=2 * mult * nf, k=2 * r, s=r))
+        for j in range(nres):
+            specs += rb(f"encoder.model.{n + j}", mult * nf)
+        specs.append(dict(name=f"encoder.model.{n + nres + 1}.conv", kind="conv", cin=mult * nf, cout=2 * mult * nf, k=2 * r, s=r))
         mult *= 2
-        n += 3
+        n += nres + 2
     if cfg.lstm_layers > 0:
         specs.append(dict(name=f"encoder.model.{n}.lstm", kind="lstm", dim=mult * nf))
         n += 1
@@ -42,9 +44,10 @@ def conv_specs(cfg: CodecConfig) -> List[Dict]:
         n = 2
     for r in cfg.ratios:
         specs.append(dict(name=f"decoder.model.{n + 1}.convtr", kind="convtr", cin=mult * nf, cout=mult * nf // 2, k=2 * r, s=r))
-        specs += rb(f"decoder.model.{n + 2}", mult * nf // 2)
+        for j in range(nres):
+            specs += rb(f"decoder.model.{n + 2 + j}", mult * nf // 2)
         mult //= 2
-        n += 3
+        n += nres + 2
     specs.append(dict(name=f"decoder.model.{n + 1}.conv", kind="conv", cin=nf, cout=1, k=cfg.last_kernel_size, s=1))
     return specs
 

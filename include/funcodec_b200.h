@@ -70,6 +70,11 @@ typedef struct fcb_config {
      * (seanet_encoder.py:224,234,321; seanet_decoder.py:219,229,324): groups = channels / 2 / ratio; <= 0: dense */
     int32_t conv_group_ratio;
     int32_t tr_conv_group_ratio;
+    /* time-domain stacks (arch 0): residual blocks per stage and their dilation base -- block j's first conv has dilation
+     * dilation_base^j (seanet_encoder.py:122-128, seanet_decoder.py:141-147; the soundstream_noncausal YAMLs use 3 and 2).
+     * 0 in either field selects the reference defaults (1 block, base 2). */
+    int32_t n_residual_layers;
+    int32_t dilation_base;
 } fcb_config;
 
 typedef struct fcb_handle fcb_handle;

@@ -272,7 +272,8 @@ class OracleEncodec:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], ratios: Sequence[int], sample_rate: int = 16000,
                  lstm_layers: int = 2, audio_normalize: bool = True, dtype=torch.float32,
-                 manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01, device="cpu"):
+                 manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01, device="cpu",
+                 n_residual_layers: int = 1, dilation_base: int = 2):
         self.segment_dur = segment_dur
         self.overlap_ratio = overlap_ratio
         # device != "cpu" is only used by bench.py's labelled CUDA-eager context leg (same ATen ops on the GPU)
@@ -285,6 +286,8 @@ class OracleEncodec:
         self.hop = int(math.prod(self.ratios))
         self.sample_rate = sample_rate
         self.lstm_layers = lstm_layers
+        self.n_residual_layers = n_residual_layers      # stacked dilated residual blocks (soundstream_noncausal YAMLs)
+        self.dilation_base = dilation_base
         self.audio_normalize = audio_normalize
         self.dtype = dtype
         self.manual_lstm = manual_lstm
@@ -299,12 +302,12 @@ class OracleEncodec:
             scale = 1e-8 + volume
             x_b1l = x_b1l / scale
             scale = scale.view(-1, 1)
-        emb = seanet_encoder(x_b1l, self.enc, self.ratios, self.lstm_layers, self.manual_lstm)
+        emb = seanet_encoder(x_b1l, self.enc, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base)
         return emb, scale
 
     # codec_basic.py:398-408
     def decode_frame(self, emb_btd, scale):
-        out = seanet_decoder(emb_btd, self.dec, self.ratios, self.lstm_layers, self.manual_lstm)
+        out = seanet_decoder(emb_btd, self.dec, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base)
         if scale is not None:
             out = out * scale.view(-1, 1, 1)
         return out

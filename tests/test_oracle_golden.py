@@ -202,7 +202,7 @@ def test_laura_call_patterns_on_the_oracle():
 def test_soundstream_noncausal_topology(golden_dir):
     """conf/soundstream_noncausal_16k_n32_600k_step.yaml's topology -- three residual blocks per stage with dilations 1 / 2 / 4
     (seanet_encoder.py:122-128), no sequence model -- against the unmodified reference SEANetEncoder / SEANetDecoder
-    (tools/gen_golden_soundstream.py).  Oracle only: the CUDA engine does not build this topology yet."""
+    (tools/gen_golden_soundstream.py).  (The CUDA engine builds this topology too: tests/test_gpu_parity.py.)"""
     z = np.load(os.path.join(golden_dir, "soundstream_noncausal_small.npz"))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
     ratios = [int(r) for r in z["ratios"]]

@@ -42,7 +42,8 @@ def build_reference_encodec(cfg):
                         ratios=list(cfg.ratios), norm="time_group_norm", causal=False,
                         kernel_size=cfg.kernel_size, last_kernel_size=cfg.last_kernel_size,
                         residual_kernel_size=cfg.residual_kernel_size,
-                        seq_layer_num=cfg.lstm_layers)
+                        seq_layer_num=cfg.lstm_layers, seq_model="lstm" if cfg.lstm_layers > 0 else "none",
+                        n_residual_layers=cfg.n_residual_layers, dilation_base=cfg.dilation_base)
     quant = CostumeQuantizer(input_size=cfg.dimension, codebook_size=cfg.codebook_size,
                              num_quantizers=cfg.num_quantizers, ema_decay=0.99, kmeans_init=True,
                              sampling_rate=cfg.sample_rate, quantize_dropout=True,
@@ -52,7 +53,8 @@ def build_reference_encodec(cfg):
                         ratios=list(cfg.ratios), norm="time_group_norm", causal=False,
                         kernel_size=cfg.kernel_size, last_kernel_size=cfg.last_kernel_size,
                         residual_kernel_size=cfg.residual_kernel_size,
-                        seq_layer_num=cfg.lstm_layers)
+                        seq_layer_num=cfg.lstm_layers, seq_model="lstm" if cfg.lstm_layers > 0 else "none",
+                        n_residual_layers=cfg.n_residual_layers, dilation_base=cfg.dilation_base)
     model = Encodec(input_size=1, odim=cfg.dimension, encoder=enc, quantizer=quant, decoder=dec,
                     discriminator=None, target_sample_hz=cfg.sample_rate,
                     multi_spectral_window_powers_of_two=[], audio_normalize=cfg.audio_normalize,
