@@ -34,6 +34,11 @@ constexpr int LSTM_PAIRS_MAX = 3;
 constexpr int LSTM_MAX_GROUPS = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// EXPERIMENT (FCB_LSTM_FASTCELL=1, off by default): hardware ex2 / rcp based gates -- ~3e-7 relative instead of ~1e-7, a
+// shorter dependent chain in the cell phase that heads every timestep's critical path
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + tc::exp2f_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_approx(1.0f + tc::exp2f_approx(2.8853900817779268f * x)), 1.0f); }
 
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
@@ -325,11 +330,13 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_seq_kernel(const LstmSeq
             long long o = 0;
             if (mine) {
                 const int b = b0 + fbb, j = j0 + fu;
-                const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
+                float ig, fg, gg, og;
+                if (p.fast_cell) { ig = sigmoid_fast(g4[0]); fg = sigmoid_fast(g4[1]); gg = tanh_fast(g4[2]); og = sigmoid_fast(g4[3]); }
+                else { ig = sigmoidf_(g4[0]); fg = sigmoidf_(g4[1]); gg = tanhf(g4[2]); og = sigmoidf_(g4[3]); }
                 float* cp = cS + (g * GB + fbb) * UNITS + fu;
                 const float c = fg * (*cp) + ig * gg;
                 *cp = c;
-                h = og * tanhf(c);
+                h = og * (p.fast_cell ? tanh_fast(c) : tanhf(c));
                 o = ((long long)b * T + t) * H + j;
                 __stcg(p.h_seq + o, h);
             }
@@ -455,6 +462,7 @@ static cudaError_t launch_seq(const LstmSeqParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     dim3 grid(p.H / UNITS), block(LSTM_THREADS);
     LstmSeqParams pc = p;
+    if (const char* v = getenv("FCB_LSTM_FASTCELL")) pc.fast_cell = atoi(v) != 0;
     void* args[] = {&pc, &nbuf, &npair, &pload, &nset};
     return cudaLaunchCooperativeKernel((void*)kern, grid, block, args, smem, st);
 }
