@@ -104,8 +104,6 @@ struct TcArgs {
     TcSmemLayout L;
     int na, nb, n_tiles, w_resident, nraw;
     int n_chunks, n_sc, split, n_units, upg, n_groups, n_tt, n_nt, units_per_tile, tq_rows, n_acc, raw_pitch;
-    int tma_all;      // 1-D layers: EVERY tile takes the TMA path; the few rows the tensor map cannot deliver (reflected / zero
-                      // padding at the clip ends) are patched by the producer threads
 };
 
 struct TcTile { int b, nt, tt; };
@@ -165,17 +163,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
     // stage-major, half-minor; every role derives the slot from the same running count.
 #define units_per_tile ka.units_per_tile
 #define tq_rows ka.tq_rows                  /* rows per phase the tensor map exposes */
-    auto tile_strict_interior = [&](int t0) -> bool {
+    auto tile_interior = [&](int t0) -> bool {
+        if (nraw == 0) return false;
         // first / last input row that a VALID output row of the tile needs (a partial last tile only counts its real rows: the
         // rows a 1x1 layer does not have arrive zero-filled and feed discarded output rows only)
         const int t_last = (t0 + TC_M < p.T_out ? t0 + TC_M : p.T_out) - 1;
         const int lo = t0 * S - p.pad_l;
         const int hi = t_last * S - p.pad_l + (K - 1);
         return lo >= 0 && hi < tq_rows * S;
-    };
-    auto tile_interior = [&](int t0) -> bool {           // does this tile's input come through the raw TMA ring?
-        if (nraw == 0) return false;
-        return ka.tma_all != 0 || tile_strict_interior(t0);
     };
     // accumulator ring depth.  The MMA -> commit -> epilogue -> release hand-off costs ~2000 cycles per tile pair (measured: the
     // pure barrier skeleton of the small-tile layers), so layers whose tile is one accumulation group keep up to 8 tiles in
@@ -231,7 +226,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
             const float* cf1 = (has1 && p.in1.coef) ? p.in1.coef + (long long)b * 2 * pitch : nullptr;
             const int cur_tile = tile;
             const bool interior = tile_interior(t0);
-            const bool edge = interior && !tile_strict_interior(t0);     // TMA tile with rows the tensor map cannot deliver
             for (; unit < n_units && tile == cur_tile; ) {
                 const int sc = unit / S, ph = unit - sc * S;
                 const int chunk = 2 * sc + half;               // 32-channel chunk of this group (may not exist: odd n_chunks)
@@ -277,31 +271,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv1d_tc_kernel(const __grid_c
                         const int u = rsub + 32 * i;
                         if (u < L.a_rows) {
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            bool use = c_ok;
-                            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
-                            if (use) {
-                                xv = *reinterpret_cast<const float4*>(rrow + i * 32 * raw_pitch);
-                                if (has1) yv = *reinterpret_cast<const float4*>(rrow + L.raw_in1 + i * 32 * raw_pitch);
-                            }
-                            if (!FREQ && edge && use) {
-                                // clip ends: rows past the last input any valid output reads count as zero; rows outside the tensor
-                                // map are zero padding (transposed conv) or a reflected / uncovered row fetched directly
-                                const int gt = (t0 + u) * S + ph - p.pad_l;
-                                if (gt > gt_max) use = false;
-                                else if (gt < 0 || gt >= tq_rows * S) {
-                                    const int src = reflect_index(gt, p.T_ext);
-                                    if (p.pad_zero || src < 0 || src >= p.T_in) use = false;
-                                    else {
-                                        const long long off = (long long)src * C_in + chunk * TC_KC + jchunk * 4;
-                                        xv = __ldg(reinterpret_cast<const float4*>(x0 + off));
-                                        if (has1) yv = __ldg(reinterpret_cast<const float4*>(x1 + off));
-                                    }
-                                }
-                            }
-                            if (use) {
+                            if (c_ok) {
+                                const float4 xv = *reinterpret_cast<const float4*>(rrow + i * 32 * raw_pitch);
                                 v.x = fmaf(xv.x, a0.x, b0.x); v.y = fmaf(xv.y, a0.y, b0.y);
                                 v.z = fmaf(xv.z, a0.z, b0.z); v.w = fmaf(xv.w, a0.w, b0.w);
                                 if (has1) {
+                                    const float4 yv = *reinterpret_cast<const float4*>(rrow + L.raw_in1 + i * 32 * raw_pitch);
                                     v.x = v.x + fmaf(yv.x, a1.x, b1.x); v.y = v.y + fmaf(yv.y, a1.y, b1.y);
                                     v.z = v.z + fmaf(yv.z, a1.z, b1.z); v.w = v.w + fmaf(yv.w, a1.w, b1.w);
                                 }
@@ -797,9 +772,9 @@ int conv_tc_num_parts(int T_out, int C_out_eff) {
 
 static int g_num_sms = 0;
 
-static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0, g_nacc_cap = 0, g_na_tma = 2, g_tma_all = 1;
+static int g_group_mmas = TC_GROUP_MMAS, g_deep_ring = 1, g_dbg = 0, g_nacc_cap = 0, g_na_tma = 2;
 
-struct TcPlan { int resident, na, nb, nraw; TcSmemLayout L; bool ok; int tma_all; };
+struct TcPlan { int resident, na, nb, nraw; TcSmemLayout L; bool ok; };
 
 // shared-memory plan: weights resident (small layers: the whole image of the single n-tile) or streamed through a ring as
 // deep as fits; A ring `na_first` stages (4, else 2) -- with a raw TMA ring the A ring only decouples producers from the MMA
@@ -898,7 +873,6 @@ static cudaError_t launch_tc_n(const ConvParams& p, cudaStream_t st, const TcPla
     ka.units_per_tile = ka.n_chunks * p.S;
     ka.tq_rows = p.T_in / p.S;
     ka.raw_pitch = ((FREQ ? p.fq.cin : p.C_in) < TC_KC ? (FREQ ? p.fq.cin : p.C_in) : TC_KC) * 4;
-    ka.tma_all = pl.nraw > 0 ? pl.tma_all : 0;
     // accumulator ring depth: layers whose tile is one accumulation group keep up to 8 tiles in flight between MMA issue and
     // epilogue; layers that fold groups (deep K) ping-pong between up to 3 accumulators next to the running totals
     constexpr int BUF_COLS = N_TILE < 32 ? 32 : N_TILE;
@@ -928,7 +902,6 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         if (const char* v = getenv("FCB_TC_DEEP_RING")) g_deep_ring = atoi(v) != 0;
         if (const char* v = getenv("FCB_TC_DBG")) g_dbg = atoi(v);      // profiling knock-outs (wrong results)
         if (const char* v = getenv("FCB_TC_NACC")) g_nacc_cap = atoi(v);
-        if (const char* v = getenv("FCB_TC_TMA_ALL")) g_tma_all = atoi(v) != 0;     // 0: clip-end tiles keep the per-thread path
         if (const char* v = getenv("FCB_TC_NA_TMA")) { const int f = atoi(v); if (f == 2 || f == 4) g_na_tma = f; }
         // TMA staging of the activation tiles: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
         g_tma_state = -1;
@@ -955,10 +928,8 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
     // raw TMA ring: 1-D layers with interior tiles (n_tt >= 3), channel counts the box covers, 16-byte aligned views
     CUtensorMap tm0{}, tm1{};
     // (2-D: a 32-channel unit must be a slice of ONE frequency tap -> cin % 32 == 0, or the single tap of a 16-channel 1x1 conv)
-    // 1-D layers: every tile goes through the ring (the producers patch the few clip-end rows the tensor map cannot deliver),
-    // unless the layer is in the tiny-input padding branch (T_ext != T_in, conv.py:89-97); 2-D layers: interior tiles only
-    const bool tma_all = !freq && p.T_ext == p.T_in && g_tma_all;
-    bool want_raw = g_tma_state == 1 && (tma_all || n_tt >= 3 || (p.K == 1 && p.S == 1 && p.pad_l == 0)) && p.T_in / p.S >= 1 &&
+    // (interior tiles exist when the clip has at least 3 tiles, or for 1x1 layers -- no halo -- always)
+    bool want_raw = g_tma_state == 1 && (n_tt >= 3 || (p.K == 1 && p.S == 1 && p.pad_l == 0)) && p.T_in / p.S >= 1 &&
                     (freq ? (p.fq.cin % TC_KC == 0 || (p.fq.cin == 16 && p.fq.KF == 1)) : (p.C_in % TC_KC == 0 || p.C_in == 16));
     // 2-D layers: built and parity-tested (5-D tensor maps), but measured SLOWER than the per-thread gather at config 4 (r2g: conv
     // stack 37.3 vs 33.6 ms) -- the K_F-fold re-read of every input row makes the unit stream L2-bound either way and the TMA path
@@ -981,7 +952,6 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int B, cudaStream_t st, int* 
         pl = tc_plan(p, 4, false, g_deep_ring);
         if (!pl.ok) return cudaErrorInvalidConfiguration;
     }
-    pl.tma_all = (want_raw && tma_all) ? 1 : 0;
     switch (p.n_tile) {
         case 16: return launch_tc_modes<16>(p, st, pl, n_tiles, freq, tm0, tm1);
         case 32: return launch_tc_modes<32>(p, st, pl, n_tiles, freq, tm0, tm1);
