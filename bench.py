@@ -145,8 +145,7 @@ def make_oracle(cfg, sd, device="cpu"):
         from oracle.freqcodec_oracle import OracleFreqCodec
         return OracleFreqCodec(sd, list(zip(cfg.ratios_f, cfg.ratios)), cfg.sample_rate, cfg.lstm_layers, cfg.n_fft, cfg.stft_hop)
     from oracle.encodec_oracle import OracleEncodec
-    return OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers, device=device,
-                         n_residual_layers=cfg.n_residual_layers, dilation_base=cfg.dilation_base)
+    return OracleEncodec.from_config(sd, cfg, device=device)
 
 
 def cpu_oracle_time(cfg, sd, B, L, bit_width, reps, warm):

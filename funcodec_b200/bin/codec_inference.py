@@ -57,10 +57,13 @@ def config_from_yaml(path: str):
         raise SystemExit(f"unsupported configuration: {msg}")
 
     for side, conf in (("encoder_conf", enc), ("decoder_conf", dec)):
-        if conf.get("norm", "none") != "time_group_norm":
-            refuse(f"{side}.norm must be time_group_norm")
-        if conf.get("causal", False):
-            refuse(f"{side}.causal must be false")
+        # the classes default to norm='weight_norm', causal=False (seanet_encoder.py:93-94, seanet_decoder.py:92-93)
+        if conf.get("norm", "weight_norm") not in ("time_group_norm", "weight_norm", "none"):
+            refuse(f"{side}.norm must be time_group_norm, weight_norm or none")
+        if conf.get("causal", False) and conf.get("norm", "weight_norm") == "time_group_norm":
+            refuse(f"{side}: GroupNorm doesn't support causal evaluation (conv.py:46-47)")
+        if float(conf.get("trim_right_ratio", 1.0)) != 1.0:
+            refuse(f"{side}.trim_right_ratio must be 1")
         if conf.get("seq_model", "lstm") not in ("lstm", "none", None):
             refuse(f"{side}.seq_model must be lstm or none")
         if conf.get("activation", "ELU") != "ELU" or conf.get("pad_mode", "reflect") != "reflect":
@@ -69,6 +72,8 @@ def config_from_yaml(path: str):
         refuse("quantizer projections / codec_range")
     if int(q.get("q0_ds_ratio", 1) or 1) != 1:
         refuse("quantizer_conf.q0_ds_ratio must be 1")
+    if enc.get("norm", "weight_norm") != dec.get("norm", "weight_norm") or bool(enc.get("causal", False)) != bool(dec.get("causal", False)):
+        refuse("encoder_conf and decoder_conf must agree on norm and causal")
     for key in ("n_residual_layers", "dilation_base", "seq_model"):
         if enc.get(key, None) != dec.get(key, None):
             refuse(f"encoder_conf.{key} != decoder_conf.{key}")
@@ -89,6 +94,8 @@ def config_from_yaml(path: str):
         ratios = [int(r[1]) for r in ratios]
         if m.get("segment_dur") is not None:
             refuse("segment_dur must be null for FreqCodec")
+        if enc.get("norm", "weight_norm") != "time_group_norm" or enc.get("causal", False):
+            refuse("FreqCodec: norm must be time_group_norm and causal false")
     elif domain not in (None, "time", ["time", "time"]):
         refuse(f"codec_domain {domain}")
     cfg = CodecConfig(name="from_yaml", ratios=tuple(int(r) for r in ratios), n_filters=int(enc.get("n_filters", 32)),
@@ -101,7 +108,8 @@ def config_from_yaml(path: str):
                       n_residual_layers=int(enc.get("n_residual_layers", 1)),
                       # with one residual block the dilation base never shows (base ** 0 == 1): keep the default so that equal
                       # models compare equal
-                      dilation_base=int(enc.get("dilation_base", 2)) if int(enc.get("n_residual_layers", 1)) > 1 else 2, **kw)
+                      dilation_base=int(enc.get("dilation_base", 2)) if int(enc.get("n_residual_layers", 1)) > 1 else 2,
+                      norm=str(enc.get("norm", "weight_norm")), causal=bool(enc.get("causal", False)), **kw)
     if int(q.get("encoder_hop_length", cfg.hop_length)) != cfg.hop_length:
         refuse("quantizer_conf.encoder_hop_length != hop of the ratios")
     return cfg, m.get("segment_dur"), m.get("overlap_ratio")

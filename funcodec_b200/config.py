@@ -3,8 +3,8 @@
 Mirrors the YAML keys the reference feeds to GANSpeechCodecTask.build_model
 (/root/reference/funcodec/tasks/gan_speech_codec.py:301-358): `encoder_conf`, `quantizer_conf`,
 `decoder_conf`, `model_conf` of egs/LibriTTS/codec/conf/encodec_16k_n32_600k_step{,_ds640}.yaml.
-Only the branches the named configs use are representable (time_group_norm, non-causal,
-true_skip=False, compress=2, 2-layer LSTM, use_ddp RVQ without projections, segment_dur=null).
+Representable: norm time_group_norm / weight_norm / none, causal or not (time-domain stacks), true_skip=False, compress=2,
+LSTM or no sequence model, stacked dilated residual blocks, RVQ without projections.
 """
 from dataclasses import dataclass, field, asdict
 from typing import Dict, Optional, Tuple
@@ -40,6 +40,10 @@ class CodecConfig:
     # dilation_base; seanet_encoder.py:122-128): block j's first conv has dilation dilation_base ** j
     n_residual_layers: int = 1
     dilation_base: int = 2
+    # encoder_conf / decoder_conf `norm` and `causal` of the time-domain stacks (conv.py:21-55,251-253,293-297):
+    # 'time_group_norm' | 'weight_norm' | 'none'; causal needs a norm other than time_group_norm (conv.py:46-47)
+    norm: str = "time_group_norm"
+    causal: bool = False
 
     def conv_groups(self, channels: int) -> int:
         """groups of a 2-D conv whose reference expression is `channels // 2 // conv_group_ratio`."""
@@ -116,9 +120,21 @@ PRESETS: Dict[str, CodecConfig] = {
     "soundstream_noncausal_small": CodecConfig(name="soundstream_noncausal_small", ratios=(5, 4, 2), n_filters=4, dimension=48,
                                                codebook_size=64, num_quantizers=4, lstm_layers=0, n_residual_layers=3,
                                                audio_normalize=False),
+    # conf/soundstream_16k_n32_600k_step.yaml: weight_norm, causal, 3 dilated residual blocks per stage, no sequence model
+    "soundstream_16k_n32_ds320": CodecConfig(name="soundstream_16k_n32_ds320", ratios=(8, 5, 4, 2), dimension=512, lstm_layers=0,
+                                             n_residual_layers=3, norm="weight_norm", causal=True),
+    "soundstream_causal_small": CodecConfig(name="soundstream_causal_small", ratios=(5, 4, 2), n_filters=4, dimension=48,
+                                            codebook_size=64, num_quantizers=4, lstm_layers=0, n_residual_layers=3,
+                                            norm="weight_norm", causal=True),
+    # weight_norm with the SLSTM kept, non-causal (every norm / sequence-model combination shares the same kernels)
+    "weightnorm_lstm_small": CodecConfig(name="weightnorm_lstm_small", ratios=(5, 4, 2), n_filters=8, dimension=32,
+                                         codebook_size=64, num_quantizers=8, norm="weight_norm"),
     "small_ds320": CodecConfig(name="small_ds320", ratios=(8, 5, 4, 2), n_filters=8, dimension=64,
                                codebook_size=256, num_quantizers=8),
 }
+
+
+NORM_CODES = {"time_group_norm": 0, "weight_norm": 1, "none": 2}     # fcb_config.norm
 
 
 def get_config(name: str) -> CodecConfig:

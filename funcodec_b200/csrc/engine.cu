@@ -287,24 +287,59 @@ int pack_tc(fcb_handle* h, const std::vector<float>& wp /*[K][cin][cout_eff]*/, 
     return FCB_OK;
 }
 
+// Effective weight of a NormConv1d / NormConvTranspose1d (conv.py:25-35,148-202).  `norm: time_group_norm` stores the plain
+// `.weight`; `norm: weight_norm` stores torch.nn.utils.weight_norm's `.weight_g` [d0,1,1] and `.weight_v` (dim 0: output
+// channels of a Conv1d, INPUT channels of a ConvTranspose1d) and the module computes w = v * (g / ||v||_2 over the other dims)
+// (ATen _weight_norm); a checkpoint that already carries the folded `.weight` (remove_weight_norm) is taken as is.
+int effective_weight(fcb_handle* h, const std::string& base, std::vector<int64_t> shape, std::vector<float>* w_out) {
+    const HostTensor* w = find(h, base + ".weight");
+    if (h->cfg.norm == 0 || w) {
+        FCB_TRY(need(h, base + ".weight", shape, &w));
+        *w_out = w->data;
+        return FCB_OK;
+    }
+    const HostTensor *g, *v;
+    FCB_TRY(need(h, base + ".weight_g", {shape[0], 1, 1}, &g));
+    FCB_TRY(need(h, base + ".weight_v", shape, &v));
+    const size_t inner = (size_t)(shape[1] * shape[2]);
+    w_out->resize(v->data.size());
+    for (int64_t i = 0; i < shape[0]; ++i) {
+        double ss = 0.0;
+        for (size_t j = 0; j < inner; ++j) { const double x = v->data[(size_t)i * inner + j]; ss += x * x; }
+        const float f = g->data[(size_t)i] / (float)sqrt(ss);
+        for (size_t j = 0; j < inner; ++j) (*w_out)[(size_t)i * inner + j] = v->data[(size_t)i * inner + j] * f;
+    }
+    return FCB_OK;
+}
+
+// GroupNorm(1, C) affine of `norm: time_group_norm`; none for weight_norm / none (get_norm_module returns nn.Identity, conv.py:37-55)
+int pack_norm_affine(fcb_handle* h, const std::string& base, int cout, ConvW* o) {
+    o->gamma = o->beta = nullptr;
+    if (h->cfg.norm != 0) return FCB_OK;
+    const HostTensor *g, *be;
+    FCB_TRY(need(h, base + ".weight", {cout}, &g));
+    FCB_TRY(need(h, base + ".bias", {cout}, &be));
+    FCB_TRY(upload(h, g->data, &o->gamma));
+    FCB_TRY(upload(h, be->data, &o->beta));
+    return FCB_OK;
+}
+
 // SConv1d: conv.conv.weight [cout][cin][k] -> [k][cin][cout]
 int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k, int s, ConvW* o, int dilation = 1) {
-    const HostTensor *w, *b, *g, *be;
-    FCB_TRY(need(h, prefix + ".conv.conv.weight", {cout, cin, k}, &w));
+    const HostTensor* b;
+    std::vector<float> w;
+    FCB_TRY(effective_weight(h, prefix + ".conv.conv", {cout, cin, k}, &w));
     FCB_TRY(need(h, prefix + ".conv.conv.bias", {cout}, &b));
-    FCB_TRY(need(h, prefix + ".conv.norm.weight", {cout}, &g));
-    FCB_TRY(need(h, prefix + ".conv.norm.bias", {cout}, &be));
     std::vector<float> p((size_t)k * cin * cout);
     for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
             for (int kk = 0; kk < k; ++kk)
-                p[((size_t)kk * cin + ci) * cout + co] = w->data[((size_t)co * cin + ci) * k + kk];
+                p[((size_t)kk * cin + ci) * cout + co] = w[((size_t)co * cin + ci) * k + kk];
     o->cin = cin; o->cout = cout; o->k = k; o->s = s; o->d = dilation; o->transposed = false;
     FCB_TRY(pack_tc(h, p, k, cin, cout, o));
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, b->data, &o->bias));
-    FCB_TRY(upload(h, g->data, &o->gamma));
-    FCB_TRY(upload(h, be->data, &o->beta));
+    FCB_TRY(pack_norm_affine(h, prefix + ".conv.norm", cout, o));
     return FCB_OK;
 }
 
@@ -314,18 +349,17 @@ int pack_conv(fcb_handle* h, const std::string& prefix, int cin, int cout, int k
 // packed [tap][cin][p*cout + co]: tap 0 <-> x[t-1] (W[..][p+s]), tap 1 <-> x[t] (W[..][p]).
 int pack_convtr(fcb_handle* h, const std::string& prefix, int cin, int cout, int s, ConvW* o) {
     const int k = 2 * s;
-    const HostTensor *w, *b, *g, *be;
-    FCB_TRY(need(h, prefix + ".convtr.convtr.weight", {cin, cout, k}, &w));
+    const HostTensor* b;
+    std::vector<float> w;
+    FCB_TRY(effective_weight(h, prefix + ".convtr.convtr", {cin, cout, k}, &w));
     FCB_TRY(need(h, prefix + ".convtr.convtr.bias", {cout}, &b));
-    FCB_TRY(need(h, prefix + ".convtr.norm.weight", {cout}, &g));
-    FCB_TRY(need(h, prefix + ".convtr.norm.bias", {cout}, &be));
     const int ce = s * cout;
     std::vector<float> p((size_t)2 * cin * ce), bias(ce);
     for (int ci = 0; ci < cin; ++ci)
         for (int co = 0; co < cout; ++co)
             for (int ph = 0; ph < s; ++ph) {
-                p[((size_t)0 * cin + ci) * ce + ph * cout + co] = w->data[((size_t)ci * cout + co) * k + ph + s];
-                p[((size_t)1 * cin + ci) * ce + ph * cout + co] = w->data[((size_t)ci * cout + co) * k + ph];
+                p[((size_t)0 * cin + ci) * ce + ph * cout + co] = w[((size_t)ci * cout + co) * k + ph + s];
+                p[((size_t)1 * cin + ci) * ce + ph * cout + co] = w[((size_t)ci * cout + co) * k + ph];
             }
     for (int ph = 0; ph < s; ++ph)
         for (int co = 0; co < cout; ++co) bias[ph * cout + co] = b->data[co];
@@ -333,8 +367,7 @@ int pack_convtr(fcb_handle* h, const std::string& prefix, int cin, int cout, int
     FCB_TRY(pack_tc(h, p, 2, cin, ce, o));
     FCB_TRY(upload(h, p, &o->w));
     FCB_TRY(upload(h, bias, &o->bias));
-    FCB_TRY(upload(h, g->data, &o->gamma));
-    FCB_TRY(upload(h, be->data, &o->beta));
+    FCB_TRY(pack_norm_affine(h, prefix + ".convtr.norm", cout, o));
     return FCB_OK;
 }
 
@@ -457,6 +490,8 @@ InView view_of(const Act& a) {
 int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_scale, const ConvW& L,
              bool want_norm, Act* out) {
     fcb_handle* h = r.h;
+    want_norm = want_norm && L.gamma != nullptr;   // norm: weight_norm / none -> the conv output is the layer output
+    const bool causal = h->cfg.causal != 0;
     ConvParams p{};
     p.in0 = view_of(in0);
     if (in1) p.in1 = view_of(*in1); else p.in1.x = nullptr;
@@ -473,7 +508,8 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         const int n_frames_ceil = (num >= 0 ? (num + s - 1) / s : -((-num) / s)) + 1;
         const int ideal = (n_frames_ceil - 1) * s + ((k - 1) * d + 1 - padding_total);
         const int extra = ideal - in0.T;
-        const int pr = padding_total / 2, pl = padding_total - pr;
+        // causal: pad1d(x, (padding_total, extra_padding)) (conv.py:251-253), else the asymmetric split (:255-258)
+        const int pr = causal ? 0 : padding_total / 2, pl = padding_total - pr;
         const int pr_tot = pr + extra;
         const int max_pad = pl > pr_tot ? pl : pr_tot;
         p.K = k; p.S = s; p.D = d; p.pad_l = pl; p.pad_zero = 0;
@@ -487,7 +523,8 @@ int run_conv(Run& r, const Act& in0, const Act* in1, bool elu, const float* div_
         p.T_out = in0.T + 1;
         p.C_out = s * L.cout;
         const int padding_total = L.k - s;                    // conv.py:283-303
-        const int pr = padding_total / 2, pl = padding_total - pr;
+        // causal (trim_right_ratio = 1): everything is trimmed on the right (conv.py:293-297)
+        const int pr = causal ? padding_total : padding_total / 2, pl = padding_total - pr;
         o.T = in0.T * s; o.C = L.cout; o.clip_stride = (long long)p.T_out * p.C_out; o.row_off = pl;
     }
     p.w = L.w; p.bias = L.bias; p.w_tc = L.w_tc; p.n_tile = L.n_tile; p.tc_w_scale = L.tc_scale;
@@ -1264,6 +1301,9 @@ int fcb_create(const fcb_config* cfg, fcb_handle** out) {
     for (int i = 0; i < cfg->n_ratios; ++i)
         if (cfg->ratios[i] < 1) return FCB_E_INVALID;
     if (cfg->arch != 0 && cfg->arch != 1) return FCB_E_INVALID;
+    if (cfg->norm < 0 || cfg->norm > 2 || (cfg->causal != 0 && cfg->causal != 1)) return FCB_E_INVALID;
+    if (cfg->causal && cfg->norm == 0) return FCB_E_INVALID;      // "GroupNorm doesn't support causal evaluation" (conv.py:46-47)
+    if (cfg->arch == 1 && (cfg->norm != 0 || cfg->causal)) return FCB_E_INVALID;   // FreqCodec: time_group_norm, non-causal only
     if (cfg->arch == 1) {
         if (cfg->n_fft < 16 || cfg->n_fft % 2 != 0 || cfg->stft_hop < 1 || cfg->stft_hop > cfg->n_fft) return FCB_E_INVALID;
         for (int i = 0; i < cfg->n_ratios; ++i)

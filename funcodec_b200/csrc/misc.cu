@@ -31,9 +31,12 @@ __global__ void final_output_kernel(const float* __restrict__ raw, const float* 
     const int b = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= out_len) return;
-    const float mean = stats[2 * b], rstd = stats[2 * b + 1];
-    const float a = rstd * gamma[0];
-    float v = fmaf(raw[(long long)b * T_raw + t], a, beta[0] - a * mean);
+    float v = raw[(long long)b * T_raw + t];
+    if (stats) {       // deferred GroupNorm(1, 1) of the last conv (norm: time_group_norm); weight_norm / none output is plain
+        const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+        const float a = rstd * gamma[0];
+        v = fmaf(v, a, beta[0] - a * mean);
+    }
     if (scale) v = v * scale[b];
     out[(long long)b * out_len + t] = v;
 }

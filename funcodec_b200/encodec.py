@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _capi
-from .config import CodecConfig
+from .config import CodecConfig, NORM_CODES
 
 
 class _QuantizerInfo:
@@ -62,6 +62,7 @@ class B200Encodec:
         c.arch, c.n_fft, c.stft_hop = cfg.arch, cfg.n_fft, cfg.stft_hop
         c.conv_group_ratio, c.tr_conv_group_ratio = cfg.conv_group_ratio, cfg.tr_conv_group_ratio
         c.n_residual_layers, c.dilation_base = cfg.n_residual_layers, cfg.dilation_base
+        c.norm, c.causal = NORM_CODES[cfg.norm], int(cfg.causal)
         for i, r in enumerate(cfg.ratios_f):
             c.ratios_f[i] = r
         self._h = ctypes.c_void_p()

@@ -34,26 +34,43 @@ def config_from_reference_model(model) -> CodecConfig:
         if tuple(reversed(ratios)) != tuple(int(r) for r in enc.ratios):
             raise UnsupportedReferenceModel("encoder/decoder ratios differ")
     sd: Dict[str, torch.Tensor] = model.state_dict()
-    if any(k.endswith("weight_g") or k.endswith("weight_v") for k in sd):
-        raise UnsupportedReferenceModel("weight_norm parametrisation is not supported (norm must be time_group_norm)")
-    if "encoder.model.0.conv.norm.weight" not in sd:
-        raise UnsupportedReferenceModel("norm must be time_group_norm")
+    # encoder_conf / decoder_conf `norm` (conv.py:21-55): weight_norm leaves weight_g / weight_v and no norm module,
+    # time_group_norm a GroupNorm(1, C) per conv, none neither; spectral_norm / layer_norm are not built
+    if any(k.endswith("weight_orig") or k.endswith("weight_u") for k in sd):
+        raise UnsupportedReferenceModel("norm spectral_norm is not supported (time_group_norm, weight_norm or none)")
+    wn = [k.endswith("weight_g") for k in sd if k.startswith(("encoder.model.", "decoder.model.")) and
+          (k.endswith("conv.weight_g") or k.endswith("conv.weight") or k.endswith("convtr.weight_g") or k.endswith("convtr.weight"))]
+    if any(wn) and not all(wn):
+        raise UnsupportedReferenceModel("encoder and decoder must use the same norm")
+    if any(wn):
+        norm = "weight_norm"
+    elif "encoder.model.0.conv.norm.weight" in sd:
+        norm = "time_group_norm"
+    else:
+        norm = "none"
+    if (norm == "time_group_norm") != ("decoder.model.0.conv.norm.weight" in sd):
+        raise UnsupportedReferenceModel("encoder and decoder must use the same norm")
+    if freq and norm != "time_group_norm":
+        raise UnsupportedReferenceModel("FreqCodec: norm must be time_group_norm")
     if getattr(model, "segment_dur", None) is not None and freq:
         raise UnsupportedReferenceModel("segment_dur must be null for FreqCodec (whole-utterance processing)")
     if getattr(q, "input_proj", None) is not None or getattr(q, "input_act", None) is not None:
         raise UnsupportedReferenceModel("quantizer projections / codec_range are not supported")
-    _check_module_options(model)
+    causal = _check_module_options(model)
+    if causal and (freq or norm == "time_group_norm"):
+        raise UnsupportedReferenceModel("causal convolutions need the time-domain stacks with norm weight_norm / none")
     embed = stacked_codebooks(sd)
     if embed is None:
         raise UnsupportedReferenceModel("no codebook buffers found (quantizer.rq.model.embed or ...layers.N._codebook.embed)")
-    w0 = sd["encoder.model.0.conv.conv.weight"]
+    wk = "weight_v" if norm == "weight_norm" else "weight"
+    w0 = sd["encoder.model.0.conv.conv." + wk]
     n_lstm = len([k for k in sd if k.startswith("decoder.model.1.lstm.weight_ih_l")])
     last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.model."))
-    rb_k = sd["encoder.model.1.block.1.conv.conv.weight"].shape[-1]
+    rb_k = sd["encoder.model.1.block.1.conv.conv." + wk].shape[-1]
     # stacked residual blocks (n_residual_layers): consecutive encoder.model.N with a shortcut conv; their first convs carry the
     # dilations dilation_base ** j (seanet_encoder.py:122-128)
     n_res = 1
-    while f"encoder.model.{1 + n_res}.shortcut.conv.conv.weight" in sd:
+    while f"encoder.model.{1 + n_res}.shortcut.conv.conv.{wk}" in sd:
         n_res += 1
     dil_base = 2
     if n_res > 1 and not freq and hasattr(enc, "model"):
@@ -72,10 +89,11 @@ def config_from_reference_model(model) -> CodecConfig:
                       n_fft=int(dconf.get("n_fft", 512)), stft_hop=int(dconf.get("hop_length", 160)),
                       n_filters=int(w0.shape[0]), dimension=int(embed.shape[2]),
                       kernel_size=int(w0.shape[-1]),
-                      last_kernel_size=int(sd[f"decoder.model.{last_idx}.conv.conv.weight"].shape[-1]),
+                      last_kernel_size=int(sd[f"decoder.model.{last_idx}.conv.conv.{wk}"].shape[-1]),
                       residual_kernel_size=int(rb_k), lstm_layers=n_lstm, codebook_size=int(embed.shape[1]),
                       num_quantizers=int(embed.shape[0]), sample_rate=int(q.sampling_rate),
-                      audio_normalize=bool(model.audio_normalize), n_residual_layers=n_res, dilation_base=dil_base)
+                      audio_normalize=bool(model.audio_normalize), n_residual_layers=n_res, dilation_base=dil_base,
+                      norm=norm, causal=causal)
     if cfg.hop_length != int(q.encoder_hop_length):
         raise UnsupportedReferenceModel("quantizer.encoder_hop_length does not match prod(ratios)")
     if freq:
@@ -106,10 +124,12 @@ def stacked_codebooks(sd):
     return torch.stack(per, dim=0) if per else None
 
 
-def _check_module_options(model) -> None:
+def _check_module_options(model) -> bool:
     """Options that change the maths but not the parameter names / shapes: inspect the module attributes
-    (conv.py:240-241,275-276; lstm.py:19; ddp_core_vq.py:354-356; seanet_encoder.py:49-61) and refuse anything else."""
+    (conv.py:240-241,275-276; lstm.py:19; ddp_core_vq.py:354-356; seanet_encoder.py:49-61) and refuse anything the engine does
+    not build.  Returns the stacks' `causal` flag (one value for every conv of both stacks)."""
     import torch.nn as nn
+    causal_seen = set()
     for side in ("encoder", "decoder"):
         net = getattr(model, side)
         if not hasattr(net, "modules"):       # not an nn.Module (a plain description object): nothing to inspect
@@ -117,12 +137,18 @@ def _check_module_options(model) -> None:
         for mod in net.modules():
             name = type(mod).__name__
             if name in ("SConv1d", "SConv2d", "SConvTranspose1d", "SConvTranspose2d"):
-                if getattr(mod, "causal", False):
-                    raise UnsupportedReferenceModel(f"{side}: causal convolutions are not supported")
+                causal_seen.add(bool(getattr(mod, "causal", False)))
+                if float(getattr(mod, "trim_right_ratio", 1.0)) != 1.0:
+                    raise UnsupportedReferenceModel(f"{side}: trim_right_ratio must be 1")
                 if getattr(mod, "pad_mode", "reflect") != "reflect":
                     raise UnsupportedReferenceModel(f"{side}: pad_mode must be reflect")
                 norm_conv = getattr(mod, "conv", None) if hasattr(mod, "conv") else getattr(mod, "convtr", None)
                 inner = getattr(norm_conv, "conv", None) if hasattr(norm_conv, "conv") else getattr(norm_conv, "convtr", None)
+                nm = getattr(norm_conv, "norm", None)
+                if nm is not None and type(nm).__name__ not in ("GroupNorm", "Identity"):
+                    raise UnsupportedReferenceModel(f"{side}: norm module {type(nm).__name__} is not supported")
+                if isinstance(nm, nn.GroupNorm) and int(nm.num_groups) != 1:
+                    raise UnsupportedReferenceModel(f"{side}: GroupNorm must have one group (time_group_norm)")
                 dil = getattr(inner, "dilation", (1,))
                 if name != "SConv1d" and any(int(d) != 1 for d in dil):
                     raise UnsupportedReferenceModel(f"{side}: dilated 2-D / transposed convolutions are not supported")
@@ -134,6 +160,9 @@ def _check_module_options(model) -> None:
     rq = getattr(getattr(model.quantizer, "rq", None), "model", None)
     if rq is not None and int(getattr(rq, "q0_ds_ratio", 1)) != 1:
         raise UnsupportedReferenceModel("quantizer q0_ds_ratio must be 1")
+    if len(causal_seen) > 1:
+        raise UnsupportedReferenceModel("encoder and decoder must agree on `causal`")
+    return bool(causal_seen.pop()) if causal_seen else False
 
 
 def wrap_reference_encodec(model, device: str = "cuda:0"):

@@ -109,18 +109,26 @@ def state_dict_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
     if cfg.arch == 1:
         return _freq_shapes(cfg)
     shapes: Dict[str, Tuple[int, ...]] = {}
+    def normed(base, wshape, cout):
+        # NormConv1d / NormConvTranspose1d parameters (conv.py:25-55,148-202): weight_norm re-parametrises `weight` as
+        # weight_g [d0,1,1] x weight_v and has no norm module; 'none' has neither
+        if cfg.norm == "weight_norm":
+            shapes[base + ".weight_v"] = wshape
+            shapes[base + ".weight_g"] = (wshape[0], 1, 1)
+        else:
+            shapes[base + ".weight"] = wshape
+        shapes[base + ".bias"] = (cout,)
+        if cfg.norm == "time_group_norm":
+            head = base.rsplit(".", 1)[0]
+            shapes[head + ".norm.weight"] = (cout,)
+            shapes[head + ".norm.bias"] = (cout,)
+
     for sp in conv_specs(cfg):
         n = sp["name"]
         if sp["kind"] == "conv":
-            shapes[n + ".conv.weight"] = (sp["cout"], sp["cin"], sp["k"])
-            shapes[n + ".conv.bias"] = (sp["cout"],)
-            shapes[n + ".norm.weight"] = (sp["cout"],)
-            shapes[n + ".norm.bias"] = (sp["cout"],)
+            normed(n + ".conv", (sp["cout"], sp["cin"], sp["k"]), sp["cout"])
         elif sp["kind"] == "convtr":
-            shapes[n + ".convtr.weight"] = (sp["cin"], sp["cout"], sp["k"])
-            shapes[n + ".convtr.bias"] = (sp["cout"],)
-            shapes[n + ".norm.weight"] = (sp["cout"],)
-            shapes[n + ".norm.bias"] = (sp["cout"],)
+            normed(n + ".convtr", (sp["cin"], sp["cout"], sp["k"]), sp["cout"])
         else:
             H = sp["dim"]
             for l in range(cfg.lstm_layers):
@@ -135,6 +143,9 @@ def state_dict_shapes(cfg: CodecConfig) -> Dict[str, Tuple[int, ...]]:
     shapes["quantizer.rq.model.embed"] = (nq, K, D)
     shapes["quantizer.rq.model.embed_avg"] = (nq, K, D)
     return shapes
+
+
+WN_GAIN = 1.6
 
 
 def init_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
@@ -157,9 +168,14 @@ def init_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
         elif ".lstm." in name:
             H = shape[-1] if len(shape) == 2 else shape[0] // 4
             sd[name] = uni(shape, 1.0 / math.sqrt(H))
-        elif name.endswith("convtr.weight") or name.endswith("conv.weight"):
+        elif name.endswith("convtr.weight") or name.endswith("conv.weight") or name.endswith(".weight_v"):
             fan_in = shape[1] * int(math.prod(shape[2:]))     # torch: fan_in uses dim 1 (also for [Cin, Cout, k...])
             sd[name] = uni(shape, 1.0 / math.sqrt(fan_in))
+        elif name.endswith(".weight_g"):
+            # weight_norm initialises g = ||v|| (so w == v); perturbed, and with the gain that keeps activations O(1) through the
+            # un-normalised stack (v ~ U(+-1/sqrt(fan_in)) alone shrinks the variance 3x per conv)
+            v = sd[name[:-1] + "v"]
+            sd[name] = v.flatten(1).norm(dim=1).view(shape) * WN_GAIN * (1.0 + 0.1 * torch.randn(shape, generator=g))
         else:  # conv / convtr bias
             sd[name] = uni(shape, 0.1)
     nq, K, D = cfg.num_quantizers, cfg.codebook_size, cfg.dimension

@@ -75,6 +75,13 @@ typedef struct fcb_config {
      * 0 in either field selects the reference defaults (1 block, base 2). */
     int32_t n_residual_layers;
     int32_t dilation_base;
+    /* encoder_conf / decoder_conf `norm` (conv.py:21-55) for arch 0 -- 0: time_group_norm (GroupNorm(1, C) after every conv),
+     * 1: weight_norm (tensors `...weight_g` / `...weight_v`, folded at fcb_finalize; a folded `...weight` is accepted too),
+     * 2: none.  `causal` (0 / 1): left-only reflect padding of the convs and right-only trimming of the transposed convs
+     * (conv.py:251-253,293-297; trim_right_ratio 1) -- conf/soundstream_16k_n32_600k_step.yaml is {weight_norm, causal}.
+     * causal with time_group_norm is refused like the reference does (conv.py:46-47); arch 1 takes neither. */
+    int32_t norm;
+    int32_t causal;
 } fcb_config;
 
 typedef struct fcb_handle fcb_handle;

@@ -46,38 +46,56 @@ def pad1d_reflect(x: torch.Tensor, paddings: Tuple[int, int]) -> torch.Tensor:
     return padded[..., :end]
 
 
-def conv_paddings(length: int, k: int, s: int, d: int) -> Tuple[int, int]:
-    """Non-causal SConv1d padding (conv.py:245-258): returns (pad_left, pad_right incl. extra)."""
+def conv_paddings(length: int, k: int, s: int, d: int, causal: bool = False) -> Tuple[int, int]:
+    """SConv1d padding (conv.py:245-258): returns (pad_left, pad_right incl. extra); causal pads (padding_total, extra)."""
     padding_total = (k - 1) * d - (s - 1)
     extra = extra_padding_for_conv1d(length, k, s, padding_total)
+    if causal:
+        return padding_total, extra
     pr = padding_total // 2
     pl = padding_total - pr
     return pl, pr + extra
 
 
+def normed_weight(p: Dict[str, torch.Tensor], base: str) -> torch.Tensor:
+    """apply_parametrization_norm (conv.py:25-35): `norm: weight_norm` wraps the conv in torch.nn.utils.weight_norm, whose
+    forward pre-hook computes weight = _weight_norm(weight_v, weight_g, dim=0); the other norms keep the plain `weight`."""
+    if base + ".weight_g" in p:
+        return torch._weight_norm(p[base + ".weight_v"], p[base + ".weight_g"], 0)
+    return p[base + ".weight"]
+
+
+def maybe_group_norm(y, p: Dict[str, torch.Tensor], base: str):
+    """get_norm_module (conv.py:37-55): GroupNorm(1, C) for time_group_norm, nn.Identity for weight_norm / none."""
+    if base + ".weight" in p:
+        return F.group_norm(y, 1, p[base + ".weight"], p[base + ".bias"], EPS_GN)
+    return y
+
+
 # --------------------------------------------------------------------------- L1 modules
-def sconv1d(x, p: Dict[str, torch.Tensor], prefix: str, stride: int = 1, dilation: int = 1):
+def sconv1d(x, p: Dict[str, torch.Tensor], prefix: str, stride: int = 1, dilation: int = 1, causal: bool = False):
     """SConv1d.forward (conv.py:243-261) + NormConv1d.forward (conv.py:155-164):
-    reflect pad -> Conv1d(bias) -> GroupNorm(1, C_out)."""
-    w = p[prefix + ".conv.conv.weight"]
+    reflect pad -> Conv1d(bias) -> GroupNorm(1, C_out) (time_group_norm) / nothing (weight_norm, none)."""
+    w = normed_weight(p, prefix + ".conv.conv")
     b = p[prefix + ".conv.conv.bias"]
     k = w.shape[-1]
-    pl, pr = conv_paddings(x.shape[-1], k, stride, dilation)
+    pl, pr = conv_paddings(x.shape[-1], k, stride, dilation, causal)
     x = pad1d_reflect(x, (pl, pr))
     y = F.conv1d(x, w, b, stride=stride, dilation=dilation)
-    return F.group_norm(y, 1, p[prefix + ".conv.norm.weight"], p[prefix + ".conv.norm.bias"], EPS_GN)
+    return maybe_group_norm(y, p, prefix + ".conv.norm")
 
 
-def sconvtr1d(x, p: Dict[str, torch.Tensor], prefix: str, stride: int):
+def sconvtr1d(x, p: Dict[str, torch.Tensor], prefix: str, stride: int, causal: bool = False):
     """SConvTranspose1d.forward (conv.py:281-305) + NormConvTranspose1d (conv.py:198-202):
-    ConvTranspose1d -> GroupNorm(1, C_out) over the UNtrimmed output -> trim (pl, pr)."""
-    w = p[prefix + ".convtr.convtr.weight"]  # [Cin, Cout, k]
+    ConvTranspose1d -> GroupNorm(1, C_out) over the UNtrimmed output (time_group_norm only) -> trim (pl, pr); causal with
+    trim_right_ratio = 1 trims everything on the right (conv.py:293-297)."""
+    w = normed_weight(p, prefix + ".convtr.convtr")  # [Cin, Cout, k]
     b = p[prefix + ".convtr.convtr.bias"]
     k = w.shape[-1]
     y = F.conv_transpose1d(x, w, b, stride=stride)
-    y = F.group_norm(y, 1, p[prefix + ".convtr.norm.weight"], p[prefix + ".convtr.norm.bias"], EPS_GN)
+    y = maybe_group_norm(y, p, prefix + ".convtr.norm")
     padding_total = k - stride
-    pr = padding_total // 2
+    pr = padding_total if causal else padding_total // 2
     pl = padding_total - pr
     return y[..., pl: y.shape[-1] - pr]
 
@@ -87,12 +105,12 @@ def elu(x):
     return F.elu(x, alpha=1.0)
 
 
-def resblock(x, p, prefix: str, res_kernel: int = 3, dilation: int = 1):
+def resblock(x, p, prefix: str, res_kernel: int = 3, dilation: int = 1, causal: bool = False):
     """SEANetResnetBlock.forward (seanet_encoder.py:16-61): shortcut(x) + block(x), true_skip=False; the first block conv
     carries the dilation (dilations=[dilation_base ** j, 1], seanet_encoder.py:125)."""
-    h = sconv1d(elu(x), p, prefix + ".block.1", dilation=dilation)
-    h = sconv1d(elu(h), p, prefix + ".block.3")
-    return sconv1d(x, p, prefix + ".shortcut") + h
+    h = sconv1d(elu(x), p, prefix + ".block.1", dilation=dilation, causal=causal)
+    h = sconv1d(elu(h), p, prefix + ".block.3", causal=causal)
+    return sconv1d(x, p, prefix + ".shortcut", causal=causal) + h
 
 
 def lstm_manual(x_tbc, p, prefix: str, num_layers: int):
@@ -145,39 +163,39 @@ def sub_dict(p: Dict[str, torch.Tensor], head: str) -> Dict[str, torch.Tensor]:
 
 
 def seanet_encoder(x, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False,
-                   n_residual_layers: int = 1, dilation_base: int = 2):
+                   n_residual_layers: int = 1, dilation_base: int = 2, causal: bool = False):
     """SEANetEncoder.forward (seanet_encoder.py:108-162,171-185).  x: [B,1,L] -> [B,T',D].
     `ratios` as given in the YAML; the encoder applies them reversed (seanet_encoder.py:102).  n_residual_layers > 1 (the
     soundstream_* YAMLs) stacks residual blocks with dilations dilation_base ** j (:122-128); lstm_layers = 0 is
     `seq_model: none`."""
-    h = sconv1d(x, p, "model.0")
+    h = sconv1d(x, p, "model.0", causal=causal)
     n = 1
     for r in reversed(list(ratios)):
         for j in range(n_residual_layers):
-            h = resblock(h, p, f"model.{n + j}", dilation=dilation_base ** j)
-        h = sconv1d(elu(h), p, f"model.{n + n_residual_layers + 1}", stride=r)
+            h = resblock(h, p, f"model.{n + j}", dilation=dilation_base ** j, causal=causal)
+        h = sconv1d(elu(h), p, f"model.{n + n_residual_layers + 1}", stride=r, causal=causal)
         n += n_residual_layers + 2
     if lstm_layers > 0:
         h = slstm(h, p, f"model.{n}", lstm_layers, manual_lstm)
         n += 1
-    h = sconv1d(elu(h), p, f"model.{n + 1}")
+    h = sconv1d(elu(h), p, f"model.{n + 1}", causal=causal)
     return h.permute(0, 2, 1)
 
 
 def seanet_decoder(z, p, ratios: Sequence[int], lstm_layers: int = 2, manual_lstm: bool = False,
-                   n_residual_layers: int = 1, dilation_base: int = 2):
+                   n_residual_layers: int = 1, dilation_base: int = 2, causal: bool = False):
     """SEANetDecoder.forward (seanet_decoder.py:107-172,177-180).  z: [B,T',D] -> [B,1,T'*hop]."""
-    h = sconv1d(z.permute(0, 2, 1), p, "model.0")
+    h = sconv1d(z.permute(0, 2, 1), p, "model.0", causal=causal)
     n = 1
     if lstm_layers > 0:
         h = slstm(h, p, "model.1", lstm_layers, manual_lstm)
         n = 2
     for r in ratios:
-        h = sconvtr1d(elu(h), p, f"model.{n + 1}", stride=r)
+        h = sconvtr1d(elu(h), p, f"model.{n + 1}", stride=r, causal=causal)
         for j in range(n_residual_layers):
-            h = resblock(h, p, f"model.{n + 2 + j}", dilation=dilation_base ** j)
+            h = resblock(h, p, f"model.{n + 2 + j}", dilation=dilation_base ** j, causal=causal)
         n += n_residual_layers + 2
-    return sconv1d(elu(h), p, f"model.{n + 1}")
+    return sconv1d(elu(h), p, f"model.{n + 1}", causal=causal)
 
 
 # --------------------------------------------------------------------------- RVQ
@@ -273,8 +291,10 @@ class OracleEncodec:
     def __init__(self, state_dict: Dict[str, torch.Tensor], ratios: Sequence[int], sample_rate: int = 16000,
                  lstm_layers: int = 2, audio_normalize: bool = True, dtype=torch.float32,
                  manual_lstm: bool = False, segment_dur=None, overlap_ratio: float = 0.01, device="cpu",
-                 n_residual_layers: int = 1, dilation_base: int = 2):
+                 n_residual_layers: int = 1, dilation_base: int = 2, causal: bool = False):
         self.segment_dur = segment_dur
+        self.causal = causal                            # encoder_conf / decoder_conf causal (soundstream_16k YAML); the norm
+        #                                                 (time_group_norm / weight_norm / none) follows from the state_dict keys
         self.overlap_ratio = overlap_ratio
         # device != "cpu" is only used by bench.py's labelled CUDA-eager context leg (same ATen ops on the GPU)
         sd = {k: v.detach().to(device, dtype) if v.is_floating_point() else v.detach().to(device)
@@ -293,6 +313,14 @@ class OracleEncodec:
         self.manual_lstm = manual_lstm
         self.n_q_max, self.bins, self.dim = self.embed.shape
 
+    @classmethod
+    def from_config(cls, state_dict, cfg, **kw):
+        """Oracle for a hyper-parameter record with the YAML-derived fields (ratios, sample_rate, lstm_layers, audio_normalize,
+        n_residual_layers, dilation_base, causal); the norm follows from the state_dict keys."""
+        return cls(state_dict, cfg.ratios, cfg.sample_rate, cfg.lstm_layers, audio_normalize=cfg.audio_normalize,
+                   n_residual_layers=getattr(cfg, "n_residual_layers", 1), dilation_base=getattr(cfg, "dilation_base", 2),
+                   causal=bool(getattr(cfg, "causal", False)), **kw)
+
     # codec_basic.py:361-380
     def encode_frame(self, x_b1l):
         scale = None
@@ -302,12 +330,14 @@ class OracleEncodec:
             scale = 1e-8 + volume
             x_b1l = x_b1l / scale
             scale = scale.view(-1, 1)
-        emb = seanet_encoder(x_b1l, self.enc, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base)
+        emb = seanet_encoder(x_b1l, self.enc, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base,
+                             self.causal)
         return emb, scale
 
     # codec_basic.py:398-408
     def decode_frame(self, emb_btd, scale):
-        out = seanet_decoder(emb_btd, self.dec, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base)
+        out = seanet_decoder(emb_btd, self.dec, self.ratios, self.lstm_layers, self.manual_lstm, self.n_residual_layers, self.dilation_base,
+                             self.causal)
         if scale is not None:
             out = out * scale.view(-1, 1, 1)
         return out

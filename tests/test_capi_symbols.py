@@ -116,13 +116,14 @@ def test_config_from_the_real_reference_modules():
     from ref_harness import build_reference_encodec
     from funcodec_b200.integration import config_from_reference_model, stacked_codebooks, UnsupportedReferenceModel
     from funcodec_b200.weights import state_dict_shapes
-    for name in ("encodec_16k_n32_ds320", "tiny_ds40", "soundstream_noncausal_small"):
+    for name in ("encodec_16k_n32_ds320", "tiny_ds40", "soundstream_noncausal_small", "soundstream_causal_small",
+                 "weightnorm_lstm_small"):
         cfg = get_config(name)
         m = build_reference_encodec(cfg)
         got = config_from_reference_model(m)
         for f in ("arch", "ratios", "n_filters", "dimension", "kernel_size", "last_kernel_size", "residual_kernel_size",
                   "lstm_layers", "codebook_size", "num_quantizers", "sample_rate", "audio_normalize", "n_residual_layers",
-                  "dilation_base"):
+                  "dilation_base", "norm", "causal"):
             assert getattr(got, f) == getattr(cfg, f), (name, f)
         sd = m.state_dict()
         for k, shp in state_dict_shapes(cfg).items():
@@ -130,7 +131,7 @@ def test_config_from_the_real_reference_modules():
         assert tuple(stacked_codebooks(sd).shape) == (cfg.num_quantizers, cfg.codebook_size, cfg.dimension)
     # options that keep parameter names and shapes but change the maths are refused
     m = build_reference_encodec(get_config("tiny_ds40"))
-    m.encoder.model[0].causal = True
+    m.encoder.model[0].causal = True                   # one causal conv among non-causal ones / causal under GroupNorm
     with pytest.raises(UnsupportedReferenceModel):
         config_from_reference_model(m)
     m.encoder.model[0].causal = False

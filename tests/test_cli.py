@@ -86,12 +86,13 @@ def test_config_from_yaml_roundtrips_the_presets(tmp_path, name):
 
 @pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="the reference checkout only exists in the build container")
 def test_config_from_the_reference_repo_yamls():
-    """The YAMLs the reference ships: the two Encodec ones, the two mag_phase FreqCodec ones and the two non-causal SoundStream ones
-    (3 dilated residual blocks per stage, no sequence model) map to presets; the others are refused with a message (weight_norm +
-    causal soundstream, mag_angle domain)."""
+    """The YAMLs the reference ships: the two Encodec ones, the two mag_phase FreqCodec ones, the two non-causal SoundStream ones
+    (3 dilated residual blocks per stage, no sequence model) and the causal weight_norm SoundStream one map to presets; the
+    mag_angle FreqCodec one is refused with a message."""
     want = {"encodec_16k_n32_600k_step.yaml": "encodec_16k_n32_ds320", "encodec_16k_n32_600k_step_ds640.yaml": "encodec_16k_n32_ds640",
             "soundstream_noncausal_16k_n32_600k_step.yaml": "soundstream_noncausal_16k_n32_ds320",
             "soundstream_noncausal_16k_n32_600k_step_ds640.yaml": "soundstream_noncausal_16k_n32_ds640",
+            "soundstream_16k_n32_600k_step.yaml": "soundstream_16k_n32_ds320",
             "freqcodec_mag_phase_16k_n32_600k_step.yaml": "freqcodec_magphase_16k_n32_ds320",
             "freqcodec_mag_phase_16k_n32_600k_step_ds640.yaml": "freqcodec_magphase_16k_n32_ds640"}
     for fn in sorted(os.listdir(REF_CONF)):
@@ -100,7 +101,7 @@ def test_config_from_the_reference_repo_yamls():
             got, _, _ = CLI.config_from_yaml(path)
             cfg = get_config(want[fn])
             for f in ("arch", "ratios", "ratios_f", "n_filters", "dimension", "lstm_layers", "codebook_size", "num_quantizers",
-                      "sample_rate", "hop_length", "conv_group_ratio", "n_residual_layers", "dilation_base"):
+                      "sample_rate", "hop_length", "conv_group_ratio", "n_residual_layers", "dilation_base", "norm", "causal"):
                 assert getattr(got, f) == getattr(cfg, f), (fn, f)
         else:
             with pytest.raises(SystemExit):

@@ -77,7 +77,10 @@ def test_layers_rvq(golden_dir):
 
 
 MODEL_FILES = ["model_tiny_ds40.npz", "model_tiny_ds40_ragged.npz", "model_small_ds320.npz",
-               "model_encodec_16k_n32_ds640.npz", "model_encodec_16k_n32_ds320.npz"]
+               "model_encodec_16k_n32_ds640.npz", "model_encodec_16k_n32_ds320.npz",
+               # norm weight_norm: {causal, 3 dilated residual blocks, no sequence model} and {non-causal, SLSTM}
+               # (tools/gen_golden_norms.py)
+               "model_soundstream_causal_small.npz", "model_weightnorm_lstm_small.npz"]
 
 
 @pytest.mark.parametrize("fname", MODEL_FILES)
@@ -86,7 +89,7 @@ def test_model_inference(golden_dir, fname):
     cfg = get_config(str(z["cfg_name"]))
     sd = init_state_dict(cfg, int(z["seed"]))
     assert abs(_sd_checksum(sd) - float(z["sd_checksum"])) <= 1e-6 * float(z["sd_checksum"]), "synthetic init drifted"
-    o = O.OracleEncodec(sd, cfg.ratios, cfg.sample_rate, cfg.lstm_layers)
+    o = O.OracleEncodec.from_config(sd, cfg)
     wav = torch.from_numpy(z["wav"])
     keys = sorted({k.split(".")[0] for k in z.files if k.endswith(".codes")})
     for key in keys:
@@ -212,3 +215,24 @@ def test_soundstream_noncausal_topology(golden_dir):
     y = O.seanet_decoder(torch.from_numpy(z["emb"]), O.sub_dict(sd, "decoder."), ratios, lstm_layers=0, n_residual_layers=3)
     assert y.shape == z["y"].shape
     assert np.abs(y.numpy() - z["y"]).max() <= 2e-6
+
+
+def test_soundstream_causal_weight_norm_topology(golden_dir):
+    """conf/soundstream_16k_n32_600k_step.yaml's branches -- `norm: weight_norm` (weight_g / weight_v re-parametrisation, no norm
+    module, conv.py:25-55) and `causal: true` (left-only reflect padding, right-only trimming of the transposed convs,
+    conv.py:251-253,293-297) on the stacked dilated residual blocks -- against the unmodified reference SEANetEncoder /
+    SEANetDecoder (tools/gen_golden_soundstream.py)."""
+    z = np.load(os.path.join(golden_dir, "soundstream_causal_small.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    assert "encoder.model.0.conv.conv.weight_g" in sd and "encoder.model.0.conv.norm.weight" not in sd
+    ratios = [int(r) for r in z["ratios"]]
+    kw = dict(lstm_layers=0, n_residual_layers=3, causal=True)
+    emb = O.seanet_encoder(torch.from_numpy(z["x"]), O.sub_dict(sd, "encoder."), ratios, **kw)
+    assert emb.shape == z["emb"].shape
+    assert np.abs(emb.numpy() - z["emb"]).max() <= 2e-6
+    y = O.seanet_decoder(torch.from_numpy(z["emb"]), O.sub_dict(sd, "decoder."), ratios, **kw)
+    assert y.shape == z["y"].shape
+    assert np.abs(y.numpy() - z["y"]).max() <= 2e-6
+    # the non-causal paddings on the same weights give a different signal (the flag is live)
+    emb_nc = O.seanet_encoder(torch.from_numpy(z["x"]), O.sub_dict(sd, "encoder."), ratios, lstm_layers=0, n_residual_layers=3)
+    assert np.abs(emb_nc.numpy() - z["emb"]).max() > 1e-3

@@ -39,7 +39,7 @@ def build_reference_encodec(cfg):
     import torch
     Encodec, SEANetEncoder, SEANetDecoder, CostumeQuantizer = import_reference()
     enc = SEANetEncoder(input_size=1, dimension=cfg.dimension, n_filters=cfg.n_filters,
-                        ratios=list(cfg.ratios), norm="time_group_norm", causal=False,
+                        ratios=list(cfg.ratios), norm=getattr(cfg, "norm", "time_group_norm"), causal=bool(getattr(cfg, "causal", False)),
                         kernel_size=cfg.kernel_size, last_kernel_size=cfg.last_kernel_size,
                         residual_kernel_size=cfg.residual_kernel_size,
                         seq_layer_num=cfg.lstm_layers, seq_model="lstm" if cfg.lstm_layers > 0 else "none",
@@ -50,7 +50,7 @@ def build_reference_encodec(cfg):
                              rand_num_quant=[2, 4, 8, 16, 32], use_ddp=True,
                              encoder_hop_length=cfg.hop_length)
     dec = SEANetDecoder(input_size=cfg.dimension, channels=1, n_filters=cfg.n_filters,
-                        ratios=list(cfg.ratios), norm="time_group_norm", causal=False,
+                        ratios=list(cfg.ratios), norm=getattr(cfg, "norm", "time_group_norm"), causal=bool(getattr(cfg, "causal", False)),
                         kernel_size=cfg.kernel_size, last_kernel_size=cfg.last_kernel_size,
                         residual_kernel_size=cfg.residual_kernel_size,
                         seq_layer_num=cfg.lstm_layers, seq_model="lstm" if cfg.lstm_layers > 0 else "none",
