@@ -83,6 +83,9 @@ struct fcb_handle {
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
     int* fin_counter = nullptr;  // per-clip partial counters of the fused GroupNorm finalisation (conv_tc.cu), zero between launches
+    int rvq_sliced = 0;          // "rvq_sliced" option / FCB_RVQ_SLICED=1: allow the column-sliced fp32 RVQ kernel (rvq_simt.cu) for D > 260
+                                 // (the SoundStream YAMLs' D = 512).  OFF by default: written after the last GPU minutes of round 2 were
+                                 // spent (r2o found that D = 512 never fit the whole-chunk kernel) -- NOT validated on hardware yet
     int fuse_stats = 0;          // "fuse_stats" option / FCB_FUSE_STATS=1: GroupNorm finalisation inside the conv kernel.  OFF by default:
                                  // measured slower at config 2 (r2m: conv stack 11.7 vs 10.8 ms -- the last CTA's serial reduction sits in
                                  // every launch's tail) and neutral at B = 1; parity-tested, kept as an option
@@ -1266,6 +1269,7 @@ int do_encode(fcb_handle* h, const float* wav, int B, int L, int n_q, int64_t* c
     q.codes = reinterpret_cast<long long*>(codes);
     q.sub_quants = sub_quants; q.enc_out = encoder_out;
     q.embed_tc = h->embed_tc;
+    q.allow_sliced = h->rvq_sliced;
     if (h->use_tc && h->embed_tc) {
         q.quant = nullptr;
         FCB_CK(launch_rvq_tc(q, st));
@@ -1411,6 +1415,15 @@ int fcb_finalize(fcb_handle* h) {
     }
     const HostTensor* emb;
     FCB_TRY(need(h, "quantizer.rq.model.embed", {c.num_quantizers, c.codebook_size, D}, &emb));
+    if (const char* v = getenv("FCB_RVQ_SLICED")) h->rvq_sliced = atoi(v) != 0;
+    {
+        const int ds = rvq_simt_slice(D);
+        if (ds == 0) return fail(h, FCB_E_INVALID, "dimension " + std::to_string(D) + " is too wide for the RVQ kernels");
+        if (ds != D && !h->rvq_sliced)
+            return fail(h, FCB_E_INVALID, "dimension " + std::to_string(D) + ": the RVQ kernels keep the residual, the running sum and a "
+                        "128-codeword chunk in shared memory, which fits D <= 260; the column-sliced kernel for wider embeddings has "
+                        "not been validated on hardware yet -- opt in with fcb_set_option(\"rvq_sliced\", 1) or FCB_RVQ_SLICED=1");
+    }
     FCB_TRY(upload(h, emb->data, &h->embed));
     if (h->use_tc && rvq_tc_supported(D, c.codebook_size)) {
         // per stage: [1][D][K] "weights" (codeword = output channel) -> slab images, stages concatenated
@@ -1764,6 +1777,11 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
     }
     if (strcmp(key, "stft_tc") == 0) {             // STFT / iSTFT as tensor-core GEMMs (default) vs the direct-DFT kernels
         h->stft_tc = value != 0;
+        return FCB_OK;
+    }
+    if (strcmp(key, "rvq_sliced") == 0) {          // column-sliced fp32 RVQ kernel for D > 260 (not hardware-validated yet)
+        if (h->finalized) return fail(h, FCB_E_STATE, "rvq_sliced must be set before fcb_finalize");
+        h->rvq_sliced = value != 0;
         return FCB_OK;
     }
     if (strcmp(key, "fuse_stats") == 0) {          // GroupNorm finalisation inside the conv kernel vs a separate launch (default)

@@ -77,8 +77,10 @@ struct RvqParams {
     float* quant;         // [B][T][D] or nullptr
     float* sub_quants;    // [n_q][B][D][T] or nullptr
     float* enc_out;       // [B][T][D] or nullptr
+    int allow_sliced;     // rvq_simt.cu: permit the column-sliced kernel for a D too wide for the whole-chunk one ("rvq_sliced" option)
 };
 cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st);
+int rvq_simt_slice(int D);      // 0: no SIMT RVQ kernel for this D; D: whole-chunk kernel; else the sliced kernel's slice width
 constexpr int RVQ_TC_N = 128;   // codewords per tensor-core tile == n_tile of the codebook slab image
 bool rvq_tc_supported(int D, int K);
 cudaError_t launch_rvq_tc(const RvqParams& p, cudaStream_t st);

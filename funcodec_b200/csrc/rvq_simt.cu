@@ -19,14 +19,19 @@ namespace fcb {
 constexpr int RVQ_ROWS = 32;
 constexpr int RVQ_CHUNK = 128;
 
-__global__ void __launch_bounds__(256, 2) rvq_kernel(const RvqParams p) {
+// SLICED (D too wide for a whole [128][D] codebook chunk next to the residual and the running sum, e.g. the SoundStream YAMLs'
+// D = 512): the chunk is staged `ds` columns at a time and the 4x4 dot products keep accumulating across the slices -- the k order
+// of every dot product, hence every bit of the result, is the same as in the unsliced kernel.
+template <bool SLICED>
+__global__ void __launch_bounds__(256, 2) rvq_kernel(const RvqParams p, const int ds) {
     extern __shared__ __align__(16) float smem[];
     const int D = p.D, K = p.K, T = p.T;
     const int pitch = D + 4;
+    const int cpitch = SLICED ? ds + 4 : pitch;
     float* Xs = smem;                       // [32][pitch] residual
     float* Os = Xs + RVQ_ROWS * pitch;      // [32][pitch] quantized_out
-    float* Cs = Os + RVQ_ROWS * pitch;      // [128][pitch] codebook chunk
-    float* xx = Cs + RVQ_CHUNK * pitch;     // [32]
+    float* Cs = Os + RVQ_ROWS * pitch;      // [128][cpitch] codebook chunk (SLICED: `ds` of its D columns)
+    float* xx = Cs + RVQ_CHUNK * cpitch;    // [32]
     int* best = reinterpret_cast<int*>(xx + RVQ_ROWS);   // [32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -72,36 +77,68 @@ __global__ void __launch_bounds__(256, 2) rvq_kernel(const RvqParams p) {
         for (int i = 0; i < 4; ++i) { bval[i] = 3.402823466e38f; bidx[i] = 0x7fffffff; }
 
         for (int c0 = 0; c0 < K; c0 += RVQ_CHUNK) {
-            __syncthreads();   // previous chunk consumed (and xx / residual updates visible)
-            for (int e = tid * 4; e < RVQ_CHUNK * D; e += 256 * 4) {
-                const int c = e / D, d = e - c * D;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c0 + c < K) v = __ldg(reinterpret_cast<const float4*>(E + (long long)(c0 + c) * D + d));
-                *reinterpret_cast<float4*>(Cs + c * pitch + d) = v;
-            }
-            __syncthreads();
             float dot[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dot[i][j] = 0.f;
-            const float* xr = Xs + (warp * 4) * pitch;
-            const float* cr = Cs + lane * pitch;
-            for (int k = 0; k < D; k += 4) {
-                float4 xv[4], cv[4];
+            if constexpr (!SLICED) {
+                __syncthreads();   // previous chunk consumed (and xx / residual updates visible)
+                for (int e = tid * 4; e < RVQ_CHUNK * D; e += 256 * 4) {
+                    const int c = e / D, d = e - c * D;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c0 + c < K) v = __ldg(reinterpret_cast<const float4*>(E + (long long)(c0 + c) * D + d));
+                    *reinterpret_cast<float4*>(Cs + c * pitch + d) = v;
+                }
+                __syncthreads();
+                const float* xr = Xs + (warp * 4) * pitch;
+                const float* cr = Cs + lane * pitch;
+                for (int k = 0; k < D; k += 4) {
+                    float4 xv[4], cv[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr + i * pitch + k);
+                    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr + i * pitch + k);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cr + j * 32 * pitch + k);
+                    for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cr + j * 32 * pitch + k);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dot[i][j] = fmaf(xv[i].x, cv[j].x, dot[i][j]);
-                        dot[i][j] = fmaf(xv[i].y, cv[j].y, dot[i][j]);
-                        dot[i][j] = fmaf(xv[i].z, cv[j].z, dot[i][j]);
-                        dot[i][j] = fmaf(xv[i].w, cv[j].w, dot[i][j]);
+                        for (int j = 0; j < 4; ++j) {
+                            dot[i][j] = fmaf(xv[i].x, cv[j].x, dot[i][j]);
+                            dot[i][j] = fmaf(xv[i].y, cv[j].y, dot[i][j]);
+                            dot[i][j] = fmaf(xv[i].z, cv[j].z, dot[i][j]);
+                            dot[i][j] = fmaf(xv[i].w, cv[j].w, dot[i][j]);
+                        }
+                }
+            } else {
+                for (int d0 = 0; d0 < D; d0 += ds) {
+                    const int dw = min(ds, D - d0);          // columns of this slice (a multiple of 4)
+                    __syncthreads();   // previous slice / chunk consumed (and xx / residual updates visible)
+                    for (int e = tid * 4; e < RVQ_CHUNK * dw; e += 256 * 4) {
+                        const int c = e / dw, d = e - c * dw;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c0 + c < K) v = __ldg(reinterpret_cast<const float4*>(E + (long long)(c0 + c) * D + d0 + d));
+                        *reinterpret_cast<float4*>(Cs + c * cpitch + d) = v;
                     }
+                    __syncthreads();
+                    const float* xr = Xs + (warp * 4) * pitch + d0;
+                    const float* cr = Cs + lane * cpitch;
+                    for (int k = 0; k < dw; k += 4) {
+                        float4 xv[4], cv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr + i * pitch + k);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cv[j] = *reinterpret_cast<const float4*>(cr + j * 32 * cpitch + k);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                dot[i][j] = fmaf(xv[i].x, cv[j].x, dot[i][j]);
+                                dot[i][j] = fmaf(xv[i].y, cv[j].y, dot[i][j]);
+                                dot[i][j] = fmaf(xv[i].z, cv[j].z, dot[i][j]);
+                                dot[i][j] = fmaf(xv[i].w, cv[j].w, dot[i][j]);
+                            }
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -183,16 +220,34 @@ __global__ void embed_sum_kernel(const long long* __restrict__ codes, int q_majo
     out[e] = acc;
 }
 
+constexpr size_t RVQ_SMEM_MAX = 200 * 1024;
+static size_t rvq_smem_bytes(int D, int ds) {
+    return ((size_t)2 * RVQ_ROWS * (D + 4) + (size_t)RVQ_CHUNK * (ds + 4) + RVQ_ROWS) * sizeof(float) + RVQ_ROWS * sizeof(int);
+}
+// 0: D does not fit at all; D: the whole-chunk kernel; else the slice width of the sliced kernel
+int rvq_simt_slice(int D) {
+    if (D % 4 != 0 || D < 4) return 0;
+    if (rvq_smem_bytes(D, D) <= RVQ_SMEM_MAX) return D;
+    for (int ds = 256; ds >= 32; ds >>= 1)
+        if (rvq_smem_bytes(D, ds) <= RVQ_SMEM_MAX) return ds;
+    return 0;
+}
+
 cudaError_t launch_rvq(const RvqParams& p, cudaStream_t st) {
-    if (p.D % 4 != 0) return cudaErrorInvalidValue;
-    const int pitch = p.D + 4;
-    const size_t smem = ((size_t)(2 * RVQ_ROWS + RVQ_CHUNK) * pitch + RVQ_ROWS) * sizeof(float) + RVQ_ROWS * sizeof(int);
-    {
-        cudaError_t e = ensure_dynamic_smem((const void*)rvq_kernel, 200 * 1024);
-        if (e != cudaSuccess) return e;
-    }
+    const int ds = rvq_simt_slice(p.D);
+    if (ds == 0 || (ds != p.D && !p.allow_sliced)) return cudaErrorInvalidValue;
+    const size_t smem = rvq_smem_bytes(p.D, ds);
     const long long M = (long long)p.B * p.T;
-    rvq_kernel<<<(unsigned)((M + RVQ_ROWS - 1) / RVQ_ROWS), 256, smem, st>>>(p);
+    const unsigned grid = (unsigned)((M + RVQ_ROWS - 1) / RVQ_ROWS);
+    if (ds == p.D) {
+        cudaError_t e = ensure_dynamic_smem((const void*)rvq_kernel<false>, (int)RVQ_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        rvq_kernel<false><<<grid, 256, smem, st>>>(p, ds);
+    } else {
+        cudaError_t e = ensure_dynamic_smem((const void*)rvq_kernel<true>, (int)RVQ_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        rvq_kernel<true><<<grid, 256, smem, st>>>(p, ds);
+    }
     return cudaGetLastError();
 }
 
