@@ -32,13 +32,14 @@ WAV_TOL = 1e-4
 
 def main():
     bad = 0
+    cases = {}
     for name in ("soundstream_noncausal_16k_n32_ds320", "soundstream_16k_n32_ds320"):
         cfg = get_config(name)
         sd = init_state_dict(cfg, 0)
-        oracle = O.OracleEncodec.from_config(sd, cfg)
         wav = 0.1 * torch.randn(2, 48000, generator=torch.Generator().manual_seed(6006))
-        ora = oracle.inference(wav, want_margin=True)
-        for use_tc in (1, 0):
+        cases[name] = (cfg, sd, wav, O.OracleEncodec.from_config(sd, cfg).inference(wav, want_margin=True))
+    for use_tc in (1, 0):
+        for name, (cfg, sd, wav, ora) in cases.items():
             model = B200Encodec(cfg, sd, "cuda:0", options={"use_tc": use_tc, "rvq_sliced": 1})
             r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
             enc_err = float((r["encoder_out"].cpu() - ora["encoder_out"]).abs().max())
@@ -54,7 +55,9 @@ def main():
             ok = res["bad_frames"] == 0 and res["near_tie_frames"] <= max(2, frames // 100) and werr <= WAV_TOL and derr <= WAV_TOL
             bad += not ok
             print(f"{'OK ' if ok else 'FAIL'} {name} use_tc={use_tc}: encoder_out max-abs {enc_err:.2e}, frames {frames}, "
-                  f"near-tie flips {res['near_tie_frames']}, bad {res['bad_frames']}, recon max-abs {werr:.2e}, decode-only {derr:.2e}")
+                  f"near-tie flips {res['near_tie_frames']}, bad {res['bad_frames']}, worst accepted margin {res['worst_margin']:.2e}, "
+                  f"recon max-abs {werr:.2e}, decode-only {derr:.2e}", flush=True)
+            del model
     return 1 if bad else 0
 
 
