@@ -83,9 +83,10 @@ struct fcb_handle {
     int* err_flag = nullptr;
     unsigned* lstm_barrier = nullptr;
     int* fin_counter = nullptr;  // per-clip partial counters of the fused GroupNorm finalisation (conv_tc.cu), zero between launches
-    int rvq_sliced = 0;          // "rvq_sliced" option / FCB_RVQ_SLICED=1: allow the column-sliced fp32 RVQ kernel (rvq_simt.cu) for D > 260
-                                 // (the SoundStream YAMLs' D = 512).  OFF by default: written after the last GPU minutes of round 2 were
-                                 // spent (r2o found that D = 512 never fit the whole-chunk kernel) -- NOT validated on hardware yet
+    int rvq_sliced = 1;          // "rvq_sliced" option / FCB_RVQ_SLICED: the column-sliced fp32 RVQ kernel (rvq_simt.cu) for D > 260 (the
+                                 // SoundStream YAMLs' D = 512; r2o found that such a D never fit the whole-chunk kernel).  Validated on
+                                 // hardware in r2q (profiles/soundstream_fullwidth_r2q.txt: codes exact on 4 x 300 frames x 32 stages);
+                                 // 0 makes fcb_finalize refuse such a D instead
     int fuse_stats = 0;          // "fuse_stats" option / FCB_FUSE_STATS=1: GroupNorm finalisation inside the conv kernel.  OFF by default:
                                  // measured slower at config 2 (r2m: conv stack 11.7 vs 10.8 ms -- the last CTA's serial reduction sits in
                                  // every launch's tail) and neutral at B = 1; parity-tested, kept as an option
@@ -1421,8 +1422,8 @@ int fcb_finalize(fcb_handle* h) {
         if (ds == 0) return fail(h, FCB_E_INVALID, "dimension " + std::to_string(D) + " is too wide for the RVQ kernels");
         if (ds != D && !h->rvq_sliced)
             return fail(h, FCB_E_INVALID, "dimension " + std::to_string(D) + ": the RVQ kernels keep the residual, the running sum and a "
-                        "128-codeword chunk in shared memory, which fits D <= 260; the column-sliced kernel for wider embeddings has "
-                        "not been validated on hardware yet -- opt in with fcb_set_option(\"rvq_sliced\", 1) or FCB_RVQ_SLICED=1");
+                        "128-codeword chunk in shared memory, which fits D <= 260; the column-sliced kernel for wider embeddings is "
+                        "switched off (fcb_set_option(\"rvq_sliced\", 0) / FCB_RVQ_SLICED=0)");
     }
     FCB_TRY(upload(h, emb->data, &h->embed));
     if (h->use_tc && rvq_tc_supported(D, c.codebook_size)) {
@@ -1779,7 +1780,7 @@ int fcb_set_option(fcb_handle* h, const char* key, int32_t value) {
         h->stft_tc = value != 0;
         return FCB_OK;
     }
-    if (strcmp(key, "rvq_sliced") == 0) {          // column-sliced fp32 RVQ kernel for D > 260 (not hardware-validated yet)
+    if (strcmp(key, "rvq_sliced") == 0) {          // column-sliced fp32 RVQ kernel for D > 260 (default on; 0: refuse such a D)
         if (h->finalized) return fail(h, FCB_E_STATE, "rvq_sliced must be set before fcb_finalize");
         h->rvq_sliced = value != 0;
         return FCB_OK;

@@ -7,7 +7,8 @@ frames, near-tie frames, worst accepted oracle margin, waveform max-abs on clips
               {2,4,8,16,32} is the prefix property; + the B = 64 shape (finite, deterministic, batch-consistent with the 1-clip run)
   config 4    FreqCodec mag_phase ds320, B = 2 x 10 s, groups = 1 and gr8 (as named)
   config 5    ds640, B = 64 per GPU (8 LSTM clip groups at H = 1024): 2 clips against the oracle + consistency with B = 16
-  (the SoundStream YAMLs' own widths -- D = 512 -- are NOT covered here: tools/round3/soundstream_fullwidth_check.py)
+  (f) N2      the SoundStream YAMLs at their real widths (n_filters 32, D = 512 -> column-sliced fp32 RVQ kernel, 3 dilated residual
+              blocks per stage, no sequence model): non-causal time_group_norm and causal weight_norm, B = 2 x 3 s
 """
 import numpy as np
 import pytest
@@ -135,3 +136,18 @@ def test_config5_b64_per_gpu():
     same = (r16["code_indices"][0] == r["code_indices"][0][:, :16]).all(dim=0).float().mean().item()
     record_parity("config 5: first 16 clips in the B=64 batch vs as a B=16 batch", kind="batch_consistency", frame_equal_rate=same)
     assert same >= 0.98
+
+
+@pytest.mark.parametrize("name", ["soundstream_noncausal_16k_n32_ds320", "soundstream_16k_n32_ds320"])
+def test_soundstream_yaml_widths(name):
+    """conf/soundstream_noncausal_16k_n32_600k_step.yaml and conf/soundstream_16k_n32_600k_step.yaml (weight_norm, causal) at the
+    YAMLs' own widths against the oracle (which is pinned on the reference for both branches at small widths).  First measured by
+    tools/soundstream_fullwidth_check.py (r2q, profiles/soundstream_fullwidth_r2q.txt): codes exact, waveform <= 1.3e-6."""
+    cfg, sd, model, oracle = _time_model(name)
+    B, L = 2, 48000
+    wav = 0.1 * torch.randn(B, L, generator=torch.Generator().manual_seed(6006))
+    r = model.inference(wav, need_recon=True, need_sub_quants=False)
+    ora = oracle.inference(wav, want_margin=True)
+    assert tuple(r["code_indices"][0].shape) == tuple(ora["code_indices"][0].shape) == (32, B, 150)
+    # D = 512: the fp32 rounding noise of a distance grows like sqrt(D), so the near-tie margin is the D = 128 one x 2
+    _compare(f"N2 {name}: B=2 x 3 s, n_q=32", r, ora, 0.97, margin=2 * MARGIN)

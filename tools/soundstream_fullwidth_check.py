@@ -1,16 +1,10 @@
-"""PENDING VALIDATION (round 3, needs a GPU): the SoundStream YAMLs at their own widths (n_filters 32, D = 512, three dilated
-residual blocks per stage, no sequence model) -- conf/soundstream_noncausal_16k_n32_600k_step.yaml (time_group_norm) and
-conf/soundstream_16k_n32_600k_step.yaml (weight_norm, causal) -- against the CPU oracle, with the column-sliced fp32 RVQ kernel
-(rvq_simt.cu, option rvq_sliced) switched on.
+"""The SoundStream YAMLs at their own widths (n_filters 32, D = 512, three dilated residual blocks per stage, no sequence model)
+-- conf/soundstream_noncausal_16k_n32_600k_step.yaml (time_group_norm) and conf/soundstream_16k_n32_600k_step.yaml (weight_norm,
+causal) -- against the CPU oracle on both conv paths, one line per case:  gpurun -- 'python tools/soundstream_fullwidth_check.py'
 
-Round 2's last GPU call (r2o) ran exactly this comparison as a test and found that D = 512 never fit the whole-chunk RVQ kernel's
-shared memory (launch_rvq -> invalid argument); the sliced kernel was written afterwards with no GPU minutes left, so it is opt-in
-and this script is how to validate it:
-
-    gpurun -- 'python tools/round3/soundstream_fullwidth_check.py'
-
-Pass = every line prints OK.  Then: make rvq_sliced the default in engine.cu (fcb_finalize), turn the body of this script back into
-tests/test_gpu_fullshape.py::test_soundstream_yaml_widths, and delete tests/test_gpu_parity.py::test_wide_embedding_needs_opt_in.
+History: round 2's r2o run found that D = 512 never fit the whole-chunk RVQ kernel's shared memory (launch_rvq -> invalid
+argument); the column-sliced kernel (rvq_simt.cu) was validated with this script in r2q (profiles/soundstream_fullwidth_r2q.txt)
+and the same comparison now lives in tests/test_gpu_fullshape.py::test_soundstream_yaml_widths.
 """
 import os
 import sys
@@ -18,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from funcodec_b200 import get_config, init_state_dict  # noqa: E402
@@ -37,10 +31,14 @@ def main():
         cfg = get_config(name)
         sd = init_state_dict(cfg, 0)
         wav = 0.1 * torch.randn(2, 48000, generator=torch.Generator().manual_seed(6006))
-        cases[name] = (cfg, sd, wav, O.OracleEncodec.from_config(sd, cfg).inference(wav, want_margin=True))
+        oracle = O.OracleEncodec.from_config(sd, cfg)
+        ora = oracle.inference(wav, want_margin=True)
+        # decode-only reference: the oracle's own quantized embeddings through ITS decoder (no scale applied on this path)
+        ora["decode_emb"] = oracle.inference_decoding_emb(ora["code_embeddings"][0][0])["recon_speech"]
+        cases[name] = (cfg, sd, wav, ora)
     for use_tc in (1, 0):
         for name, (cfg, sd, wav, ora) in cases.items():
-            model = B200Encodec(cfg, sd, "cuda:0", options={"use_tc": use_tc, "rvq_sliced": 1})
+            model = B200Encodec(cfg, sd, "cuda:0", options={"use_tc": use_tc})
             r = model.inference(wav, need_recon=True, need_encoder_out=True, need_sub_quants=False)
             enc_err = float((r["encoder_out"].cpu() - ora["encoder_out"]).abs().max())
             codes = r["code_indices"][0].cpu().numpy()
@@ -50,7 +48,7 @@ def main():
             werr = max([float((rec[b] - ref[b]).abs().max()) for b in np.nonzero(ok_clip)[0]] or [0.0])
             # decode-only: the oracle's own quantized embeddings in (no index contamination)
             d = model.inference_decoding_emb(ora["code_embeddings"][0][0])
-            derr = float((d["recon_speech"].cpu() - ref).abs().max())
+            derr = float((d["recon_speech"].cpu() - ora["decode_emb"]).abs().max())
             frames = codes.shape[1] * codes.shape[2]
             ok = res["bad_frames"] == 0 and res["near_tie_frames"] <= max(2, frames // 100) and werr <= WAV_TOL and derr <= WAV_TOL
             bad += not ok
