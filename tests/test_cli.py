@@ -56,8 +56,12 @@ def _yaml_for(cfg, tmp_path, **model_conf):
         model, extra = "freq_codec", dict(codec_domain=["mag_phase", "mag_phase"])
     else:
         ratios, model, extra = list(cfg.ratios), "encodec", {}
-    conf = dict(norm="time_group_norm", norm_params=dict(num_groups=1), causal=False, ratios=ratios, n_filters=cfg.n_filters,
-                seq_layer_num=cfg.lstm_layers)
+    conf = dict(norm=cfg.norm, causal=cfg.causal, ratios=ratios, n_filters=cfg.n_filters,
+                seq_layer_num=cfg.lstm_layers, n_residual_layers=cfg.n_residual_layers, dilation_base=cfg.dilation_base)
+    if cfg.norm == "time_group_norm":
+        conf["norm_params"] = dict(num_groups=1)
+    if cfg.lstm_layers == 0:
+        conf["seq_model"] = "none"
     if cfg.conv_group_ratio > 0:
         conf["conv_group_ratio"] = cfg.conv_group_ratio
     a = dict(encoder_conf=dict(conf), decoder_conf=dict(conf), model=model,
@@ -73,15 +77,33 @@ def _yaml_for(cfg, tmp_path, **model_conf):
 
 
 @pytest.mark.parametrize("name", ["encodec_16k_n32_ds640", "encodec_16k_n32_ds320", "tiny_ds40", "freqcodec_magphase_16k_n32_ds320",
-                                  "freqcodec_magphase_16k_n32_ds320_gr8", "freq_small_grouped"])
+                                  "freqcodec_magphase_16k_n32_ds320_gr8", "freq_small_grouped", "soundstream_noncausal_16k_n32_ds640",
+                                  "soundstream_16k_n32_ds320", "soundstream_causal_small", "weightnorm_lstm_small"])
 def test_config_from_yaml_roundtrips_the_presets(tmp_path, name):
     cfg = get_config(name)
     got, seg, ov = CLI.config_from_yaml(_yaml_for(cfg, str(tmp_path)))
     for f in ("arch", "ratios", "ratios_f", "n_filters", "dimension", "kernel_size", "last_kernel_size", "residual_kernel_size",
               "lstm_layers", "codebook_size", "num_quantizers", "sample_rate", "audio_normalize", "conv_group_ratio",
-              "tr_conv_group_ratio", "n_fft", "stft_hop", "hop_length"):
+              "tr_conv_group_ratio", "n_fft", "stft_hop", "hop_length", "n_residual_layers", "dilation_base", "norm", "causal"):
         assert getattr(got, f) == getattr(cfg, f), f
     assert seg is None and ov is None
+
+
+@pytest.mark.parametrize("patch", [dict(norm="layer_norm"), dict(norm="spectral_norm"), dict(norm="time_group_norm", causal=True),
+                                   dict(trim_right_ratio=0.5), dict(pad_mode="constant"), dict(activation="ReLU")])
+def test_config_from_yaml_refuses_unbuilt_conv_options(tmp_path, patch):
+    """norm outside {time_group_norm, weight_norm, none}, causal under GroupNorm (the reference itself raises, conv.py:46-47),
+    partial right trimming, other paddings / activations: refused with a message, never approximated."""
+    import yaml
+    path = _yaml_for(get_config("weightnorm_lstm_small"), str(tmp_path))
+    with open(path) as f:
+        a = yaml.safe_load(f)
+    for side in ("encoder_conf", "decoder_conf"):
+        a[side].update(patch)
+    with open(path, "wt") as f:
+        yaml.safe_dump(a, f)
+    with pytest.raises(SystemExit, match="unsupported configuration"):
+        CLI.config_from_yaml(path)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="the reference checkout only exists in the build container")
