@@ -17,12 +17,13 @@ import math
 import os
 import sys
 
+import numpy as np
 import torch
 import yaml
 
 from funcodec_b200.config import CodecConfig
 from funcodec_b200.encodec import B200Encodec
-from funcodec_b200.pipeline import run_decode, run_decode_emb, run_encode
+from funcodec_b200.pipeline import forward_items, load_items, run_decode, run_decode_emb, run_encode
 from funcodec_b200.speech2token import Speech2Token
 
 
@@ -158,6 +159,92 @@ def pick_gpu(output_dir, gpuid_list: str) -> int:
         except ValueError:
             jobid = 1
     return int(ids[(jobid - 1) % len(ids)])
+
+
+def build_speech2token(config_file: str, model_file: str, device: str = "cuda:0", need_sub_quants: bool = False):
+    """`Speech2Token.from_pretrained` without the hub (codec_inference.py:136-150): YAML + checkpoint -> Speech2Token on B200Encodec."""
+    cfg, segment_dur, overlap_ratio = config_from_yaml(config_file)
+    sd = torch.load(model_file, map_location="cpu")
+    if isinstance(sd, dict) and "state_dict" in sd and not any(k.startswith("encoder.") for k in sd):
+        sd = sd["state_dict"]
+    model = B200Encodec(cfg, sd, device, segment_dur=segment_dur, overlap_ratio=overlap_ratio)
+    return Speech2Token(model, device, need_sub_quants=need_sub_quants)
+
+
+def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "float32", ngpu: int = 1, seed: int = 0,
+                         num_workers: int = 0, log_level="INFO", key_file=None, config_file="config.yaml",
+                         model_file="model.pth", model_tag=None, allow_variable_data_keys: bool = True, streaming: bool = False,
+                         sampling_rate: int = 16_000, bit_width: int = 8_000, param_dict=None, use_scale=True, **kwargs):
+    """The callable-pipeline entry the modelscope wrapper and `inference()` use (codec_inference.py:164-382): builds the model once
+    and returns `_forward(data_path_and_name_and_type=None, raw_inputs=None, output_dir_v2=None, param_dict=None)`.  Same
+    arguments, defaults and return convention: with an output directory the results go to files (wav, codecs.txt / indices.ark,
+    codec_emb.ark per `need_indices` / `indices_save_type` / `need_sub_quants` in kwargs / param_dict) and the list is empty; without
+    one, a list of {"key", "value": reconstructed wav [1, L]}.  `raw_inputs`: samples (ndarray / tensor) or a wav path, key "utt" /
+    the file's basename.  Not available here: `model_tag` (hub), `dtype` other than float32, resampling (`file_sampling_rate`),
+    `stat_flops`.  Extra keyword for embedding / tests: `speech2token=` an already built Speech2Token-like callable,
+    `device=` (default cuda:<--gpuid_list pick>)."""
+    if param_dict is not None:
+        kwargs.update(param_dict)
+    if ngpu > 1:
+        raise NotImplementedError("only single GPU decoding is supported")         # as the reference (codec_inference.py:190-191)
+    if dtype != "float32":
+        raise NotImplementedError("dtype: only float32 is implemented (fp32-parity kernels)")
+    if model_tag:
+        raise NotImplementedError("model_tag (model hub download) is not available; pass config_file / model_file")
+    s2t = kwargs.pop("speech2token", None)
+    device = kwargs.pop("device", None) or f"cuda:{pick_gpu(output_dir, kwargs.get('gpuid_list', '') or '')}"
+    if s2t is None:
+        s2t = build_speech2token(config_file, model_file, device, need_sub_quants=bool(kwargs.get("need_sub_quants")))
+    model_rate = s2t.model.quantizer.sampling_rate
+    if model_rate != sampling_rate:
+        raise ValueError(f"sampling_rate {sampling_rate} != model rate {model_rate}")
+
+    def _forward(data_path_and_name_and_type=None, raw_inputs=None, output_dir_v2=None, param_dict=None):
+        if param_dict is not None:
+            kwargs.update(param_dict)
+        if kwargs.get("file_sampling_rate") not in (None, sampling_rate):
+            raise NotImplementedError("file_sampling_rate != sampling_rate: resampling is out of scope of this path")
+        if kwargs.get("stat_flops"):
+            raise NotImplementedError("stat_flops (thop profile of the torch modules) has no counterpart here")
+        run_mod = kwargs.get("run_mod", "inference")
+        if data_path_and_name_and_type is None and raw_inputs is not None:
+            uttid = "utt"
+            if isinstance(raw_inputs, str):
+                uttid = os.path.basename(raw_inputs).rsplit(".")[0]
+                from funcodec_b200.pipeline import load_wav
+                raw_inputs, sr = load_wav(raw_inputs)
+                if sr != sampling_rate:
+                    raise ValueError(f"{uttid}: sample rate {sr} != {sampling_rate} (resampling is out of scope)")
+            if isinstance(raw_inputs, torch.Tensor):
+                raw_inputs = raw_inputs.numpy()
+            items = [(uttid, np.asarray(raw_inputs))]
+        elif data_path_and_name_and_type:
+            path, _name, dtype_ = data_path_and_name_and_type[0]
+            want = {"decode": ("codec_json", "text"), "decode_emb": ("kaldi_ark",)}.get(run_mod, ("sound",))
+            if dtype_ not in want:
+                raise ValueError(f"run_mod {run_mod} reads {want[0]}, got {dtype_}")
+            items = load_items(path, dtype_, key_file)
+        else:
+            raise ValueError("need data_path_and_name_and_type or raw_inputs")
+        bw = param_dict["bit_width"] if param_dict is not None and "bit_width" in param_dict else bit_width
+        output_path = output_dir_v2 if output_dir_v2 is not None else output_dir
+        return forward_items(s2t, items, output_path, batch_size=batch_size, bit_width=bw, use_scale=use_scale, run_mod=run_mod,
+                             need_indices=bool(kwargs.get("need_indices")), indices_save_type=kwargs.get("indices_save_type", "text"),
+                             need_sub_quants=bool(kwargs.get("need_sub_quants")), sample_rate=sampling_rate)
+
+    return _forward
+
+
+def inference(output_dir, batch_size, dtype, ngpu, seed, num_workers, log_level, data_path_and_name_and_type, key_file,
+              config_file, model_file, model_tag, allow_variable_data_keys: bool = True, streaming: bool = False,
+              sampling_rate: int = 24_000, bit_width: int = 24_000, use_scale: bool = True, **kwargs):
+    """codec_inference.py:385-425: build the pipeline, run it once on the data files."""
+    pipeline = inference_modelscope(output_dir=output_dir, batch_size=batch_size, dtype=dtype, ngpu=ngpu, seed=seed,
+                                    num_workers=num_workers, log_level=log_level, key_file=key_file, config_file=config_file,
+                                    model_file=model_file, model_tag=model_tag, allow_variable_data_keys=allow_variable_data_keys,
+                                    streaming=streaming, sampling_rate=sampling_rate, bit_width=bit_width, use_scale=use_scale,
+                                    **kwargs)
+    return pipeline(data_path_and_name_and_type, raw_inputs=None)
 
 
 def main(argv=None):

@@ -221,3 +221,79 @@ def run_decode_emb(s2t, emb_scp: str, output_dir: str, batch_size: int = 16, key
     items = [(k, read_mat(spec)) for k, spec in select_keys(read_scp(emb_scp), key_file)]
     return _decode_groups(s2t, items, output_dir, batch_size, None, "decode_emb",
                           lambda a: torch.from_numpy(a.astype(np.float32)))
+
+
+def load_items(path: str, dtype: str, key_file: Optional[str] = None) -> List[Tuple[str, np.ndarray]]:
+    """The part of `build_streaming_iterator` (codec_inference.py:249-264) this path uses: one data file of type `sound`
+    (wav.scp -> float32 samples), `codec_json` / `text` (codecs.txt -> int codes [T', n_q]) or `kaldi_ark` (scp -> float
+    matrices [T', D]), restricted and ordered by `key_file`."""
+    if dtype == "sound":
+        return [(k, load_wav(pth)) for k, pth in select_keys(read_scp(path), key_file)]
+    if dtype in ("codec_json", "text"):
+        with open(path, "rt") as f:
+            return select_keys([parse_indices_line(line) for line in f if line.strip()], key_file)
+    if dtype == "kaldi_ark":
+        from .kaldi_io import read_mat
+        return [(k, read_mat(spec)) for k, spec in select_keys(read_scp(path), key_file)]
+    raise ValueError(f"data type {dtype!r} is not read by this path (sound, codec_json, kaldi_ark)")
+
+
+def forward_items(s2t, items: Sequence[Tuple[str, np.ndarray]], output_path: Optional[str], batch_size: int = 1,
+                  bit_width: Optional[int] = None, use_scale: bool = True, run_mod: str = "inference",
+                  need_indices: bool = False, indices_save_type: str = "text", need_sub_quants: bool = False,
+                  sample_rate: Optional[int] = None) -> List[Dict]:
+    """The batch loop of `inference_modelscope._forward` (codec_inference.py:313-381) for any run_mod: wrap-padded batches through
+    `s2t`, per-utterance trimming (decode modes: codec_len * hop samples; else the input length and ceil(len / hop) frames), then
+    either files under `output_path` (wav + codecs.txt / indices.ark + codec_emb.ark as requested) or -- with no output path -- the
+    reference's in-memory result list [{"key": uttid, "value": recon_wav [1, L] or None}]."""
+    hop = s2t.model.quantizer.encoder_hop_length
+    sr_model = s2t.model.quantizer.sampling_rate
+    writer, sq_writer = None, None
+    if output_path is not None:
+        os.makedirs(output_path, exist_ok=True)
+        writer = IndicesWriter(output_path, need_indices, indices_save_type)
+        if need_sub_quants:
+            from .kaldi_io import ArkScpWriter
+            sq_writer = ArkScpWriter(os.path.join(output_path, "codec_emb"))
+    results: List[Dict] = []
+    try:
+        for group in batches(list(items), batch_size):
+            arrs = []
+            for key, a in group:
+                if isinstance(a, tuple):                        # (samples, rate) from load_wav
+                    a, sr = a
+                    if sr != sr_model:
+                        raise ValueError(f"{key}: sample rate {sr} != model rate {sr_model} (resampling is out of scope)")
+                arrs.append(np.asarray(a))
+            lens = [int(a.shape[0]) for a in arrs]
+            tmax = max(lens)
+            pad = [np.pad(a, ((0, tmax - a.shape[0]),) + ((0, 0),) * (a.ndim - 1), mode="wrap") for a in arrs]
+            batch = np.stack(pad, axis=0)
+            if run_mod == "decode":
+                speech = torch.from_numpy(batch.astype(np.int64))
+            else:
+                speech = torch.from_numpy(batch.astype(np.float32))
+            codes, _, recon, sub = s2t(speech, need_recon=True, bit_width=bit_width, use_scale=use_scale, run_mod=run_mod)
+            for i, (key, _) in enumerate(group):
+                if run_mod in ("decode", "decode_emb"):
+                    codec_len = lens[i]
+                    ilen = codec_len * hop
+                else:
+                    ilen = lens[i]
+                    codec_len = -(-ilen // hop)
+                recon_wav = recon[i].cpu()[:, :ilen] if recon is not None else None
+                if output_path is None:
+                    results.append({"key": key, "value": recon_wav})
+                    continue
+                if recon_wav is not None:
+                    save_wav_pcm16(_wav_name(output_path, key), recon_wav, sample_rate or sr_model, rescale=True)
+                if codes is not None:
+                    writer.write(key, codes, i, codec_len)
+                if sq_writer is not None and sub is not None and sub[0] is not None:
+                    sq_writer(key, sub_quants_matrix(sub, i, codec_len))
+    finally:
+        if writer is not None:
+            writer.close()
+        if sq_writer is not None:
+            sq_writer.close()
+    return results

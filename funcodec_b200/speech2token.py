@@ -22,6 +22,16 @@ class Speech2Token:
     def from_state_dict(cls, cfg: CodecConfig, state_dict, device: str = "cuda:0"):
         return cls(B200Encodec(cfg, state_dict, device), device)
 
+    @classmethod
+    def from_pretrained(cls, model_tag: Optional[str] = None, config_file: Optional[str] = None, model_file: Optional[str] = None,
+                        device: str = "cuda:0", **kwargs):
+        """codec_inference.py:136-150 without the model hub: `model_tag` cannot be downloaded here (no network), so the
+        YAML and the checkpoint have to be given as files."""
+        if model_tag is not None:
+            raise NotImplementedError("model_tag (model hub download) is not available; pass config_file / model_file")
+        from .bin.codec_inference import build_speech2token
+        return build_speech2token(config_file, model_file, device, need_sub_quants=bool(kwargs.get("need_sub_quants", True)))
+
     @torch.no_grad()
     def __call__(self, speech: Union[torch.Tensor, np.ndarray], ppg=None, need_recon: bool = True,
                  bit_width: Optional[int] = None, use_scale: bool = True, run_mod: str = "inference"):

@@ -234,6 +234,76 @@ def test_three_stages_with_key_file_sharding_on_the_oracle(tmp_path):
         P.select_keys([("a", 1)], os.path.join(d, "logdir", "keys.1.scp"))
 
 
+def test_inference_modelscope_callable_on_the_oracle(tmp_path):
+    """`inference_modelscope(...)` -> `_forward(data | raw_inputs, output_dir_v2, param_dict)` (codec_inference.py:164-382) with the
+    oracle behind Speech2Token's signature: the in-memory result list (no output directory), raw samples / a wav path as
+    `raw_inputs`, files under `output_dir_v2`, the per-call `param_dict` bit_width, the three run_mods and `inference()`."""
+    import types
+    from laura_calls import OracleSpeech2Token
+    from oracle.encodec_oracle import OracleEncodec
+    cfg = get_config("tiny_ds40")
+    sd = init_state_dict(cfg, 3)
+    ora = OracleEncodec.from_config(sd, cfg)
+    s2t = OracleSpeech2Token(ora)
+    s2t.model = types.SimpleNamespace(quantizer=types.SimpleNamespace(encoder_hop_length=cfg.hop_length, sampling_rate=cfg.sample_rate))
+    d = str(tmp_path)
+    lens = [40 * 9 + 5, 40 * 14, 40 * 6 + 39]
+    clips = _write_corpus(d, cfg, lens)
+    bw_all = int(cfg.num_quantizers * cfg.bandwidth_per_quantizer())
+    common = dict(batch_size=2, sampling_rate=cfg.sample_rate, bit_width=bw_all, use_scale=True, speech2token=s2t)
+    fwd = CLI.inference_modelscope(output_dir=None, **common)
+    # (a) data files, no output dir -> [{"key", "value"}] in file order, each trimmed to its own length
+    res = fwd([(os.path.join(d, "wav.scp"), "speech", "sound")])
+    assert [r["key"] for r in res] == ["u0", "u1", "u2"]
+    assert [tuple(r["value"].shape) for r in res] == [(1, n) for n in lens]
+    speech, _ = P.wrap_pad_batch([clips["u0"], clips["u1"]])
+    ref = ora.inference(speech, need_recon=True, bit_width=bw_all, use_scale=True)["recon_speech"]
+    assert torch.equal(res[1]["value"], ref[1][:, :lens[1]])
+    # (b) raw samples and a wav path as raw_inputs
+    one = fwd(raw_inputs=clips["u2"])
+    ref2 = ora.inference(torch.from_numpy(clips["u2"]).view(1, -1), need_recon=True, bit_width=bw_all)["recon_speech"]
+    assert len(one) == 1 and one[0]["key"] == "utt" and torch.equal(one[0]["value"], ref2[0])
+    one = fwd(raw_inputs=torch.from_numpy(clips["u2"]))
+    assert torch.equal(one[0]["value"], ref2[0])
+    one = fwd(raw_inputs=os.path.join(d, "u2.wav"))
+    assert one[0]["key"] == "u2" and torch.equal(one[0]["value"], ref2[0])
+    # (c) param_dict: per-call bit width (fewer quantizers -> a different waveform), need_indices + output_dir_v2 -> files
+    low = int(2 * cfg.bandwidth_per_quantizer())
+    out = os.path.join(d, "out_v2")
+    assert fwd([(os.path.join(d, "wav.scp"), "speech", "sound")], output_dir_v2=out,
+               param_dict=dict(bit_width=low, need_indices=True)) == []
+    assert sorted(os.listdir(out)) == ["codecs.txt", "u0.wav", "u1.wav", "u2.wav"]
+    key, arr = P.parse_indices_line(open(os.path.join(out, "codecs.txt")).readline())
+    assert key == "u0" and arr.shape == (-(-lens[0] // cfg.hop_length), 2)
+    # (d) decode from the codes just written, decode_emb from embeddings, through fresh pipelines (run_mod is a pipeline kwarg)
+    dec = CLI.inference_modelscope(output_dir=os.path.join(d, "dec"), run_mod="decode", **common)
+    assert dec([(os.path.join(out, "codecs.txt"), "codec", "codec_json")]) == []
+    y, sr = P.load_wav(os.path.join(d, "dec", "u1.wav"))
+    assert sr == cfg.sample_rate and y.shape[0] == -(-lens[1] // cfg.hop_length) * cfg.hop_length
+    mem = CLI.inference_modelscope(output_dir=None, run_mod="decode", **common)
+    r = mem(raw_inputs=arr)                                   # codes [T', n_q] as raw input
+    assert tuple(r[0]["value"].shape) == (1, arr.shape[0] * cfg.hop_length)
+    with pytest.raises(ValueError):
+        dec([(os.path.join(d, "wav.scp"), "speech", "sound")])
+    # (e) what this path does not do is refused, not approximated
+    with pytest.raises(NotImplementedError):
+        CLI.inference_modelscope(dtype="float16", **common)
+    with pytest.raises(NotImplementedError):
+        CLI.inference_modelscope(ngpu=2, **common)
+    with pytest.raises(NotImplementedError):
+        fwd(raw_inputs=clips["u0"], param_dict=dict(file_sampling_rate=8000))
+    fwd2 = CLI.inference_modelscope(output_dir=None, **common)
+    with pytest.raises(ValueError):
+        fwd2()
+    # (f) inference(): positional mirror of the reference function, runs the pipeline once
+    out2 = os.path.join(d, "out_inf")
+    assert CLI.inference(out2, 2, "float32", 1, 0, 0, "INFO", [(os.path.join(d, "wav.scp"), "speech", "sound")],
+                         os.path.join(d, "logdir", "keys.2.scp"), None, None, None, sampling_rate=cfg.sample_rate,
+                         bit_width=bw_all, speech2token=s2t, run_mod="encode", need_indices=True) == []
+    assert os.listdir(out2) == ["codecs.txt"]
+    assert [l.split(" ", 1)[0] for l in open(os.path.join(out2, "codecs.txt"))] == ["u2"]
+
+
 @pytest.mark.gpu
 def test_cli_main_runs_the_scripts_three_stages(tmp_path):
     """`python -m funcodec_b200.bin.codec_inference` with encoding_decoding.sh's literal argument lists (stages 1-3, two JOBs):
