@@ -180,8 +180,8 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
     arguments, defaults and return convention: with an output directory the results go to files (wav, codecs.txt / indices.ark,
     codec_emb.ark per `need_indices` / `indices_save_type` / `need_sub_quants` in kwargs / param_dict) and the list is empty; without
     one, a list of {"key", "value": reconstructed wav [1, L]}.  `raw_inputs`: samples (ndarray / tensor) or a wav path, key "utt" /
-    the file's basename.  Not available here: `model_tag` (hub), `dtype` other than float32, resampling (`file_sampling_rate`),
-    `stat_flops`.  Extra keyword for embedding / tests: `speech2token=` an already built Speech2Token-like callable,
+    the file's basename.  `file_sampling_rate` != `sampling_rate` resamples like the reference (torchaudio, host side).  Not
+    available here: `model_tag` (hub), `dtype` other than float32, `stat_flops`.  Extra keyword for embedding / tests: `speech2token=` an already built Speech2Token-like callable,
     `device=` (default cuda:<--gpuid_list pick>)."""
     if param_dict is not None:
         kwargs.update(param_dict)
@@ -202,8 +202,7 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
     def _forward(data_path_and_name_and_type=None, raw_inputs=None, output_dir_v2=None, param_dict=None):
         if param_dict is not None:
             kwargs.update(param_dict)
-        if kwargs.get("file_sampling_rate") not in (None, sampling_rate):
-            raise NotImplementedError("file_sampling_rate != sampling_rate: resampling is out of scope of this path")
+        file_rate = kwargs.get("file_sampling_rate") or sampling_rate
         if kwargs.get("stat_flops"):
             raise NotImplementedError("stat_flops (thop profile of the torch modules) has no counterpart here")
         run_mod = kwargs.get("run_mod", "inference")
@@ -212,9 +211,13 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
             if isinstance(raw_inputs, str):
                 uttid = os.path.basename(raw_inputs).rsplit(".")[0]
                 from funcodec_b200.pipeline import load_wav
-                raw_inputs, sr = load_wav(raw_inputs)
+                if file_rate != sampling_rate:
+                    # (the reference loads the file AT the model rate and then resamples it again by file_sampling_rate)
+                    raise NotImplementedError("a wav path as raw_inputs together with file_sampling_rate != sampling_rate")
+                raw_inputs, sr = load_wav(raw_inputs)       # the reference resamples the file to the model rate while loading
                 if sr != sampling_rate:
-                    raise ValueError(f"{uttid}: sample rate {sr} != {sampling_rate} (resampling is out of scope)")
+                    import torchaudio
+                    raw_inputs = torchaudio.functional.resample(torch.from_numpy(raw_inputs), orig_freq=sr, new_freq=sampling_rate)
             if isinstance(raw_inputs, torch.Tensor):
                 raw_inputs = raw_inputs.numpy()
             items = [(uttid, np.asarray(raw_inputs))]
@@ -230,7 +233,8 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
         output_path = output_dir_v2 if output_dir_v2 is not None else output_dir
         return forward_items(s2t, items, output_path, batch_size=batch_size, bit_width=bw, use_scale=use_scale, run_mod=run_mod,
                              need_indices=bool(kwargs.get("need_indices")), indices_save_type=kwargs.get("indices_save_type", "text"),
-                             need_sub_quants=bool(kwargs.get("need_sub_quants")), sample_rate=sampling_rate)
+                             need_sub_quants=bool(kwargs.get("need_sub_quants")), sample_rate=sampling_rate,
+                             file_sample_rate=file_rate)
 
     return _forward
 
@@ -255,8 +259,9 @@ def main(argv=None):
         raise SystemExit("--dtype: only float32 is implemented (fp32-parity kernels)")
     if args.model_tag:
         raise SystemExit("--model_tag (model hub download) is not available; pass --config_file / --model_file")
-    if args.file_sampling_rate != args.sampling_rate:
-        raise SystemExit("--file_sampling_rate != --sampling_rate: resampling is out of scope of this path")
+    resample = args.file_sampling_rate != args.sampling_rate
+    if resample and args.run_mod in ("decode", "decode_emb"):
+        raise SystemExit("--file_sampling_rate != --sampling_rate is only defined for --run_mod inference / encode")
     if not args.data_path_and_name_and_type:
         raise SystemExit("--data_path_and_name_and_type is required")
     if args.output_dir is None:
@@ -279,6 +284,15 @@ def main(argv=None):
         if dtype not in ("kaldi_ark",):
             raise SystemExit(f"--run_mod decode_emb reads kaldi_ark, got {dtype}")
         n = run_decode_emb(s2t, path, args.output_dir, args.batch_size, key_file=args.key_file)
+    elif resample:
+        # resampled I/O (codec_inference.py:271-274,319-323,353-357): the generic batch loop, which resamples where the reference does
+        if dtype != "sound":
+            raise SystemExit(f"--run_mod {args.run_mod} reads sound, got {dtype}")
+        items = load_items(path, dtype, args.key_file)
+        forward_items(s2t, items, args.output_dir, batch_size=args.batch_size, bit_width=args.bit_width, use_scale=args.use_scale,
+                      run_mod=args.run_mod, need_indices=bool(args.need_indices), indices_save_type=args.indices_save_type,
+                      need_sub_quants=bool(args.need_sub_quants), file_sample_rate=args.file_sampling_rate)
+        n = len(items)
     else:
         if dtype != "sound":
             raise SystemExit(f"--run_mod {args.run_mod} reads sound, got {dtype}")

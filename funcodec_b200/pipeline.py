@@ -241,13 +241,23 @@ def load_items(path: str, dtype: str, key_file: Optional[str] = None) -> List[Tu
 def forward_items(s2t, items: Sequence[Tuple[str, np.ndarray]], output_path: Optional[str], batch_size: int = 1,
                   bit_width: Optional[int] = None, use_scale: bool = True, run_mod: str = "inference",
                   need_indices: bool = False, indices_save_type: str = "text", need_sub_quants: bool = False,
-                  sample_rate: Optional[int] = None) -> List[Dict]:
+                  sample_rate: Optional[int] = None, file_sample_rate: Optional[int] = None) -> List[Dict]:
     """The batch loop of `inference_modelscope._forward` (codec_inference.py:313-381) for any run_mod: wrap-padded batches through
     `s2t`, per-utterance trimming (decode modes: codec_len * hop samples; else the input length and ceil(len / hop) frames), then
     either files under `output_path` (wav + codecs.txt / indices.ark + codec_emb.ark as requested) or -- with no output path -- the
-    reference's in-memory result list [{"key": uttid, "value": recon_wav [1, L] or None}]."""
+    reference's in-memory result list [{"key": uttid, "value": recon_wav [1, L] or None}].
+
+    `file_sample_rate` != the model rate (`--file_sampling_rate`, codec_inference.py:271-274,319-323,353-357; inference / encode
+    only): the wrap-padded batch is resampled to the model rate with torchaudio.functional.resample exactly where the reference
+    does it, the reconstruction is resampled back and trimmed to the input length, files are written at the file rate -- and, as
+    in the reference, the per-utterance frame count is ceil(input length AT THE FILE RATE / hop), which for a higher file rate
+    simply keeps every frame of the (wrap-padded) batch row."""
     hop = s2t.model.quantizer.encoder_hop_length
     sr_model = s2t.model.quantizer.sampling_rate
+    resample = file_sample_rate is not None and int(file_sample_rate) != int(sr_model)
+    if resample and run_mod in ("decode", "decode_emb"):
+        raise NotImplementedError("file_sampling_rate != sampling_rate is only defined for the inference / encode modes")
+    sr_in = int(file_sample_rate) if resample else sr_model
     writer, sq_writer = None, None
     if output_path is not None:
         os.makedirs(output_path, exist_ok=True)
@@ -262,8 +272,8 @@ def forward_items(s2t, items: Sequence[Tuple[str, np.ndarray]], output_path: Opt
             for key, a in group:
                 if isinstance(a, tuple):                        # (samples, rate) from load_wav
                     a, sr = a
-                    if sr != sr_model:
-                        raise ValueError(f"{key}: sample rate {sr} != model rate {sr_model} (resampling is out of scope)")
+                    if sr != sr_in:
+                        raise ValueError(f"{key}: sample rate {sr} != {sr_in} (pass its rate as file_sampling_rate)")
                 arrs.append(np.asarray(a))
             lens = [int(a.shape[0]) for a in arrs]
             tmax = max(lens)
@@ -273,7 +283,12 @@ def forward_items(s2t, items: Sequence[Tuple[str, np.ndarray]], output_path: Opt
                 speech = torch.from_numpy(batch.astype(np.int64))
             else:
                 speech = torch.from_numpy(batch.astype(np.float32))
+            if resample:
+                import torchaudio
+                speech = torchaudio.functional.resample(speech, orig_freq=sr_in, new_freq=sr_model)
             codes, _, recon, sub = s2t(speech, need_recon=True, bit_width=bit_width, use_scale=use_scale, run_mod=run_mod)
+            if resample and recon is not None:
+                recon = torchaudio.functional.resample(recon.cpu(), orig_freq=sr_model, new_freq=sr_in)
             for i, (key, _) in enumerate(group):
                 if run_mod in ("decode", "decode_emb"):
                     codec_len = lens[i]
@@ -286,7 +301,7 @@ def forward_items(s2t, items: Sequence[Tuple[str, np.ndarray]], output_path: Opt
                     results.append({"key": key, "value": recon_wav})
                     continue
                 if recon_wav is not None:
-                    save_wav_pcm16(_wav_name(output_path, key), recon_wav, sample_rate or sr_model, rescale=True)
+                    save_wav_pcm16(_wav_name(output_path, key), recon_wav, sr_in if resample else (sample_rate or sr_model), rescale=True)
                 if codes is not None:
                     writer.write(key, codes, i, codec_len)
                 if sq_writer is not None and sub is not None and sub[0] is not None:

@@ -234,6 +234,18 @@ def test_three_stages_with_key_file_sharding_on_the_oracle(tmp_path):
         P.select_keys([("a", 1)], os.path.join(d, "logdir", "keys.1.scp"))
 
 
+def test_main_refuses_before_touching_the_gpu():
+    """Argument combinations this path does not serve end in SystemExit with a message before any model is built."""
+    base = ["--data_path_and_name_and_type", "codecs.txt,codec,codec_json", "--output_dir", "/tmp/x/output.1",
+            "--config_file", "/nonexistent.yaml", "--model_file", "/nonexistent.pth", "--sampling_rate", "16000"]
+    with pytest.raises(SystemExit, match="inference / encode"):
+        CLI.main(base + ["--file_sampling_rate", "8000", "--run_mod", "decode"])
+    with pytest.raises(SystemExit, match="float32"):
+        CLI.main(base + ["--dtype", "float16"])
+    with pytest.raises(SystemExit, match="model_tag"):
+        CLI.main(base + ["--model_tag", "damo/x"])
+
+
 def test_inference_modelscope_callable_on_the_oracle(tmp_path):
     """`inference_modelscope(...)` -> `_forward(data | raw_inputs, output_dir_v2, param_dict)` (codec_inference.py:164-382) with the
     oracle behind Speech2Token's signature: the in-memory result list (no output directory), raw samples / a wav path as
@@ -290,11 +302,23 @@ def test_inference_modelscope_callable_on_the_oracle(tmp_path):
         CLI.inference_modelscope(dtype="float16", **common)
     with pytest.raises(NotImplementedError):
         CLI.inference_modelscope(ngpu=2, **common)
-    with pytest.raises(NotImplementedError):
-        fwd(raw_inputs=clips["u0"], param_dict=dict(file_sampling_rate=8000))
     fwd2 = CLI.inference_modelscope(output_dir=None, **common)
     with pytest.raises(ValueError):
         fwd2()
+    # (e2) file_sampling_rate != sampling_rate: resample in, resample out, trimmed to the input length at the FILE rate
+    #      (codec_inference.py:271-274,319-323,353-357)
+    import torchaudio
+    half = cfg.sample_rate // 2
+    x8 = clips["u0"][: 40 * 6 + 3]
+    got = fwd2(raw_inputs=x8, param_dict=dict(file_sampling_rate=half))
+    up = torchaudio.functional.resample(torch.from_numpy(x8).view(1, -1), orig_freq=half, new_freq=cfg.sample_rate)
+    rec = ora.inference(up, need_recon=True, bit_width=bw_all)["recon_speech"]
+    want = torchaudio.functional.resample(rec, orig_freq=cfg.sample_rate, new_freq=half)[0][:, : x8.shape[0]]
+    assert tuple(got[0]["value"].shape) == (1, x8.shape[0]) and torch.equal(got[0]["value"], want)
+    with pytest.raises(NotImplementedError):
+        fwd2(raw_inputs=os.path.join(d, "u2.wav"))                       # kwargs still carry file_sampling_rate = half
+    with pytest.raises(NotImplementedError):
+        CLI.inference_modelscope(output_dir=None, run_mod="decode", file_sampling_rate=half, **common)(raw_inputs=arr)
     # (f) inference(): positional mirror of the reference function, runs the pipeline once
     out2 = os.path.join(d, "out_inf")
     assert CLI.inference(out2, 2, "float32", 1, 0, 0, "INFO", [(os.path.join(d, "wav.scp"), "speech", "sound")],
