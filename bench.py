@@ -45,15 +45,17 @@ def load_ncu_traffic(workload):
         return (float(e["bytes"]), e.get("source")) if e else (None, None)
     except Exception:
         return (None, None)
-# SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip
+# SURVEY.md §8(d) / BASELINE.md: algorithmic (layer-boundary) bytes and MACs per 10 s clip; re-derived analytically by
+# funcodec_b200/workload.py and checked against it on CPU (tests/test_workload.py)
 ALGO = {
     "encodec_16k_n32_ds640": dict(conv_bytes_per_10s=1066.6e6, conv_gmac_per_10s=33.10, lstm_gmac_per_10s=8.39,
                                   rvq_gflop_per_10s_nq32=2.10, weight_bytes=230.2e6),
     "freqcodec_magphase_16k_n32_ds320": dict(conv_bytes_per_10s=803.2e6, conv_gmac_per_10s=24.95, lstm_gmac_per_10s=4.20,
-                                             rvq_gflop_per_10s_nq32=2.10, weight_bytes=64.9e6),
-    # gr8: same activations; SURVEY §8(d): 10.42 GMAC per 10 s clip of grouped math (the engine executes the dense 24.95)
+                                             rvq_gflop_per_10s_nq32=4.20, weight_bytes=64.9e6),
+    # gr8: same activations; SURVEY §8(d): 10.42 GMAC per 10 s clip of grouped math (the engine executes the dense 24.95 and
+    # reads the zero-expanded dense weights: 64.9 MB, where the grouped tensors themselves are 39.7 MB)
     "freqcodec_magphase_16k_n32_ds320_gr8": dict(conv_bytes_per_10s=803.2e6, conv_gmac_per_10s=10.42, lstm_gmac_per_10s=4.20,
-                                                 rvq_gflop_per_10s_nq32=2.10, weight_bytes=64.9e6),
+                                                 rvq_gflop_per_10s_nq32=4.20, weight_bytes=64.9e6),
     "encodec_16k_n32_ds320": dict(conv_bytes_per_10s=780.1e6, conv_gmac_per_10s=15.67, lstm_gmac_per_10s=4.19,
                                   rvq_gflop_per_10s_nq32=4.19, weight_bytes=59.4e6),
 }

@@ -161,6 +161,17 @@ def pick_gpu(output_dir, gpuid_list: str) -> int:
     return int(ids[(jobid - 1) % len(ids)])
 
 
+def stat_flops_line(cfg: CodecConfig, bit_width=None) -> str:
+    """`--stat_flops` (codec_inference.py:329-345 profiles the torch modules with thop on ONE SECOND of audio and logs parameters
+    and MACs): the same two totals from the analytic model of this path (funcodec_b200/workload.py), per second of audio."""
+    from funcodec_b200.workload import workload_model
+    n_q = min(cfg.num_quantizers_for_bandwidth(bit_width), cfg.num_quantizers) if bit_width else cfg.num_quantizers
+    w = workload_model(cfg, cfg.sample_rate, n_q=n_q)
+    n_par = w["conv_params"] + w["lstm_params"] + w["codebook_params"]
+    return (f"Model parameters: {n_par / 1e6:.2f}M, model flops: {w['total_macs'] / 1e9:.2f}G MACs per second of audio "
+            f"(conv {w['conv_macs'] / 1e9:.2f}G, LSTM {w['lstm_macs'] / 1e9:.2f}G, RVQ@{n_q} {w['rvq_flops'] / 2e9:.2f}G)")
+
+
 def build_speech2token(config_file: str, model_file: str, device: str = "cuda:0", need_sub_quants: bool = False):
     """`Speech2Token.from_pretrained` without the hub (codec_inference.py:136-150): YAML + checkpoint -> Speech2Token on B200Encodec."""
     cfg, segment_dur, overlap_ratio = config_from_yaml(config_file)
@@ -181,7 +192,7 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
     codec_emb.ark per `need_indices` / `indices_save_type` / `need_sub_quants` in kwargs / param_dict) and the list is empty; without
     one, a list of {"key", "value": reconstructed wav [1, L]}.  `raw_inputs`: samples (ndarray / tensor) or a wav path, key "utt" /
     the file's basename.  `file_sampling_rate` != `sampling_rate` resamples like the reference (torchaudio, host side).  Not
-    available here: `model_tag` (hub), `dtype` other than float32, `stat_flops`.  Extra keyword for embedding / tests: `speech2token=` an already built Speech2Token-like callable,
+    available here: `model_tag` (hub), `dtype` other than float32.  `stat_flops` logs the analytic counts (stat_flops_line).  Extra keyword for embedding / tests: `speech2token=` an already built Speech2Token-like callable,
     `device=` (default cuda:<--gpuid_list pick>)."""
     if param_dict is not None:
         kwargs.update(param_dict)
@@ -203,8 +214,10 @@ def inference_modelscope(output_dir=None, batch_size: int = 1, dtype: str = "flo
         if param_dict is not None:
             kwargs.update(param_dict)
         file_rate = kwargs.get("file_sampling_rate") or sampling_rate
-        if kwargs.get("stat_flops"):
-            raise NotImplementedError("stat_flops (thop profile of the torch modules) has no counterpart here")
+        if kwargs.get("stat_flops") and getattr(s2t.model, "cfg", None) is not None and not getattr(s2t, "already_stat_flops", False):
+            import logging
+            logging.info(stat_flops_line(s2t.model.cfg, bit_width))
+            s2t.already_stat_flops = True
         run_mod = kwargs.get("run_mod", "inference")
         if data_path_and_name_and_type is None and raw_inputs is not None:
             uttid = "utt"
@@ -271,6 +284,8 @@ def main(argv=None):
     cfg, segment_dur, overlap_ratio = config_from_yaml(args.config_file)
     if cfg.sample_rate != args.sampling_rate:
         raise SystemExit(f"--sampling_rate {args.sampling_rate} != model rate {cfg.sample_rate}")
+    if args.stat_flops:
+        print(stat_flops_line(cfg, args.bit_width), file=sys.stderr)
     sd = torch.load(args.model_file, map_location="cpu")
     if isinstance(sd, dict) and "state_dict" in sd and not any(k.startswith("encoder.") for k in sd):
         sd = sd["state_dict"]
