@@ -284,7 +284,8 @@ def segment_plan(length: int, sample_rate: int, segment_dur, overlap_ratio: floa
 
 class OracleEncodec:
     """Restatement of Encodec's inference methods (funcodec/models/codec_basic.py:670-836) for the
-    named configs: time_group_norm, non-causal, audio_normalize, use_ddp RVQ without projections
+    shipped time-domain configs: norm time_group_norm / weight_norm / none (read off the state_dict keys), causal or not,
+    stacked dilated residual blocks, LSTM or no sequence model, audio_normalize, RVQ without projections
     (CostumeQuantizer, costume_quantizer.py:77-119); segment_dur=None (one frame) or a segment length in seconds
     (per-segment normalisation / encode / decode + linear overlap-add, codec_basic.py:334-359,382-396)."""
 
