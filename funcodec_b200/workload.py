@@ -15,45 +15,58 @@ from typing import Dict
 from .config import CodecConfig
 
 
-def _time_stacks(cfg: CodecConfig, L: int):
+def _time_stacks(cfg: CodecConfig, L: int, layers=None):
     nf, D = cfg.n_filters, cfg.dimension
     macs = byts = params = 0
     nres = cfg.n_residual_layers
 
-    def conv(cin, cout, k, s, T, d=1):
+    def note(name, cin, cout, k, s, To, m, b):
+        if layers is not None:
+            layers.append(dict(name=name, cin=cin, cout=cout, k=k, s=s, T_out=To, macs=m, bytes=b))
+
+    def conv(cin, cout, k, s, T, d=1, name="conv"):
         nonlocal macs, byts, params
         To = -(-T // s)
         Tp = (To - 1) * s + (k - 1) * d + 1                 # padded input length (reflect padding incl. the extra padding)
         macs += To * cin * cout * k
         byts += 4 * (Tp * cin + To * cout)
+        note(name, cin, cout, k, s, To, To * cin * cout * k, 4 * (Tp * cin + To * cout))
         params += cin * cout * k + cout + (2 * cout if cfg.norm == "time_group_norm" else (cout if cfg.norm == "weight_norm" else 0))
         return To
 
-    T = conv(1, nf, cfg.kernel_size, 1, L)
+    def lstm_inputs(side, T, H):
+        # the W_ih half of each LSTM layer runs as a 1x1 GEMM launch of the conv kernel (its MACs belong to lstm_macs)
+        for l in range(cfg.lstm_layers):
+            note(f"{side}.lstm.ih_l{l}", H, 4 * H, 1, 1, T, T * H * 4 * H, 4 * (T * H + T * 4 * H))
+
+    T = conv(1, nf, cfg.kernel_size, 1, L, name="enc.conv0")
     mult = 1
-    for r in reversed(cfg.ratios):
+    for i, r in enumerate(reversed(cfg.ratios)):
         for j in range(nres):
-            conv(mult * nf, mult * nf // 2, cfg.residual_kernel_size, 1, T, cfg.dilation_base ** j)
-            conv(mult * nf // 2, mult * nf, 1, 1, T)
-            conv(mult * nf, mult * nf, 1, 1, T)
-        T = conv(mult * nf, 2 * mult * nf, 2 * r, r, T)
+            conv(mult * nf, mult * nf // 2, cfg.residual_kernel_size, 1, T, cfg.dilation_base ** j, name=f"enc.{i}.rb{j}.k3")
+            conv(mult * nf // 2, mult * nf, 1, 1, T, name=f"enc.{i}.rb{j}.1x1")
+            conv(mult * nf, mult * nf, 1, 1, T, name=f"enc.{i}.rb{j}.shortcut")
+        T = conv(mult * nf, 2 * mult * nf, 2 * r, r, T, name=f"enc.{i}.down")
         mult *= 2
     H = mult * nf
-    conv(H, D, cfg.last_kernel_size, 1, T)
+    lstm_inputs("enc", T, H)
+    conv(H, D, cfg.last_kernel_size, 1, T, name="enc.final")
     frames = T
-    conv(D, H, cfg.kernel_size, 1, T)
-    for r in cfg.ratios:
+    conv(D, H, cfg.kernel_size, 1, T, name="dec.conv0")
+    lstm_inputs("dec", T, H)
+    for i, r in enumerate(cfg.ratios):
         cin, cout, k = mult * nf, mult * nf // 2, 2 * r
         macs += T * cin * cout * k
         byts += 4 * (T * cin + (T + 1) * r * cout)           # ConvTranspose1d output before unpad1d: (T - 1) r + 2 r
+        note(f"dec.{i}.up", cin, cout, k, r, T * r, T * cin * cout * k, 4 * (T * cin + (T + 1) * r * cout))
         params += cin * cout * k + cout + (2 * cout if cfg.norm == "time_group_norm" else (cin if cfg.norm == "weight_norm" else 0))
         T *= r
         for j in range(nres):
-            conv(cout, cout // 2, cfg.residual_kernel_size, 1, T, cfg.dilation_base ** j)
-            conv(cout // 2, cout, 1, 1, T)
-            conv(cout, cout, 1, 1, T)
+            conv(cout, cout // 2, cfg.residual_kernel_size, 1, T, cfg.dilation_base ** j, name=f"dec.{i}.rb{j}.k3")
+            conv(cout // 2, cout, 1, 1, T, name=f"dec.{i}.rb{j}.1x1")
+            conv(cout, cout, 1, 1, T, name=f"dec.{i}.rb{j}.shortcut")
         mult //= 2
-    conv(nf, 1, cfg.last_kernel_size, 1, T)
+    conv(nf, 1, cfg.last_kernel_size, 1, T, name="dec.final")
     return macs, byts, params, frames, H
 
 
@@ -101,6 +114,16 @@ def _freq_stacks(cfg: CodecConfig, L: int):
         mult //= 2
     conv2(nf, 3, cfg.last_kernel_size, cfg.last_kernel_size, 1, 1, F, T)
     return macs, byts, params, frames, H
+
+
+def conv_launches(cfg: CodecConfig, L: int):
+    """The conv-kernel launches of one time-domain round trip in the engine's launch order (per clip): name, shape, MACs and
+    layer-boundary bytes of each -- what tools/per_layer_roofline.py lines up with an ncu launch list."""
+    if cfg.arch != 0:
+        raise ValueError("per-launch list: time-domain stacks only")
+    layers = []
+    _time_stacks(cfg, L, layers)
+    return layers
 
 
 def workload_model(cfg: CodecConfig, L: int, n_q: int = 0) -> Dict[str, float]:

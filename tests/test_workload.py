@@ -68,3 +68,17 @@ def test_stat_flops_line_quotes_the_per_second_totals():
     assert "model flops: 4.25G MACs per second" in stat_flops_line(get_config("encodec_16k_n32_ds640"), 16000)
     assert "model flops: 2.20G MACs per second" in stat_flops_line(get_config("encodec_16k_n32_ds320"))
     assert "RVQ@2 " in stat_flops_line(get_config("encodec_16k_n32_ds640"), 500)
+
+
+def test_conv_launch_list_matches_the_engine_order_and_totals():
+    """48 conv-kernel launches per ds640 round trip (24 per side, the four LSTM input GEMMs among them); without those four the
+    per-launch bytes and MACs add up to the stack totals."""
+    from funcodec_b200.workload import conv_launches
+    cfg = get_config("encodec_16k_n32_ds640")
+    ls = conv_launches(cfg, 160000)
+    assert len(ls) == 48 and [l["name"] for l in ls[:5]] == ["enc.conv0", "enc.0.rb0.k3", "enc.0.rb0.1x1", "enc.0.rb0.shortcut", "enc.0.down"]
+    assert ls[23]["name"] == "enc.final" and ls[24]["name"] == "dec.conv0" and ls[-1]["name"] == "dec.final"
+    w = workload_model(cfg, 160000)
+    core = [l for l in ls if ".lstm." not in l["name"]]
+    assert len(core) == 44 and sum(l["macs"] for l in core) == w["conv_macs"] and sum(l["bytes"] for l in core) == w["conv_bytes"]
+    assert sum(l["macs"] for l in ls if ".lstm." in l["name"]) * 2 == w["lstm_macs"]      # W_ih half of the LSTM work
